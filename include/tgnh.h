@@ -1,0 +1,158 @@
+/*
+ * tgnh.h — C-ABI of the B200-native DrudeTGNHIntegrator step (libtgnh.so, sm_100a, AOT).
+ *
+ * This is the drop-in boundary for ONE hot path of scychon/openmm_drudeNose: everything
+ * CudaIntegrateDrudeTGNHStepKernel does on the device and on the host critical path
+ * (reference paths relative to /root/reference):
+ *     platforms/cuda/src/CudaDrudeTGNHKernels.cpp:75-282   initialize   -> tgnh_create
+ *     platforms/cuda/src/CudaDrudeTGNHKernels.cpp:284-408  execute      -> tgnh_half1 / tgnh_half2 / tgnh_step
+ *     platforms/cuda/src/CudaDrudeTGNHKernels.cpp:433-652  propagateNHChain (host fp64 chain, 2 blocking
+ *                                                          D2H + 2 H2D per step) -> device-resident chain
+ *     platforms/cuda/src/CudaDrudeTGNHKernels.cpp:654-661  computeKineticEnergy -> tgnh_kinetic_energy
+ *     platforms/cuda/src/kernels/drudeTGNH.cu:82-574       the 8 live runtime-compiled kernels
+ * It is called from the C++ OpenMM KernelImpl (plugin/), one host thread per handle (OpenMM
+ * contexts are not thread-safe either).  Plain pointers and sizes only; no exceptions, STL or
+ * torch types cross it.  Every function returns TGNH_OK or an error code; the message is
+ * available from tgnh_last_error() (thread-local).
+ *
+ * Buffers handed to the step functions are DEVICE pointers owned by the caller, in the layout
+ * OpenMM's CudaContext uses in single precision:
+ *     velm   float4[paddedN]   (vx, vy, vz, 1/m)   cu.getVelm();  w == 0 marks an immovable particle
+ *     posq   float4[paddedN]   (x, y, z, q)        cu.getPosq();  w is preserved
+ *     force  SoA [3][paddedN]  force[i + k*paddedN]                cu.getForce()
+ *            TGNH_FORCE_I64_SOA: long long fixed point, scale 2^32 (CudaDrudeTGNHKernels.cpp:295)
+ *            TGNH_FORCE_F32_SOA: float (synthetic-force bench; same indexing)
+ * Units: nm, ps, amu, kJ/mol, K.
+ */
+#ifndef TGNH_H_
+#define TGNH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* OpenMM's BOLTZ (RGAS/1000, SimTKOpenMMRealType.h; external constant, pinned here) */
+#define TGNH_BOLTZ (1.380649e-23 * 6.02214076e23 / 1000.0)
+
+enum {
+    TGNH_OK = 0,
+    TGNH_ERR_INVALID_ARGUMENT = 1,   /* bad sizes / indices / pointers */
+    TGNH_ERR_TEMP_GROUP = 2,         /* Drude pair or constraint spans two temperature groups (CudaDrudeTGNHKernels.cpp:146,193) */
+    TGNH_ERR_UNSUPPORTED = 3,        /* layout the AOT kernels do not cover (see message) */
+    TGNH_ERR_CUDA = 4,
+    TGNH_ERR_NCCL = 5,
+    TGNH_ERR_NO_DEVICE = 6
+};
+
+enum { TGNH_FORCE_F32_SOA = 0, TGNH_FORCE_I64_SOA = 1 };
+
+/* flags for tgnh_half2 */
+enum {
+    TGNH_HALF2_DEFAULT = 0,
+    TGNH_HALF2_DEFER_SCALE = 1       /* leave the second thermostat half-step's velocity scaling pending; it is folded
+                                        into the next tgnh_half1 (or applied by tgnh_flush).  Only legal when nothing
+                                        reads or writes velm in between. */
+};
+
+typedef struct tgnh_handle tgnh_handle;
+typedef struct tgnh_comm tgnh_comm;
+
+typedef struct {
+    /* sizes */
+    int32_t num_particles;           /* N  (of THIS shard when comm != NULL) */
+    int32_t padded_num_particles;    /* stride of the SoA force components; multiple of 4, >= N (OpenMM: multiple of 32) */
+    int32_t num_pairs;               /* P  DrudeForce entries */
+    int32_t num_residues;            /* R  molecules (ContextImpl::getMolecules) */
+    int32_t num_temp_groups;         /* G  DrudeTGNHIntegrator::getNumTempGroups */
+    int32_t num_constraints;         /* only used for DOF bookkeeping (constraints stay in OpenMM) */
+    /* integrator parameters (openmmapi/include/openmm/DrudeTGNHIntegrator.h:71) */
+    int32_t num_nh_chains;
+    int32_t drude_steps_per_real_step;
+    int32_t use_drude_nh_chains;
+    int32_t use_com_temp_group;
+    int32_t has_cm_motion_remover;   /* System contains a CMMotionRemover (CudaDrudeTGNHKernels.cpp:204-212) */
+    int32_t force_format;            /* TGNH_FORCE_* */
+    int32_t device;                  /* CUDA device ordinal; -1 = current device */
+    int32_t reserved;
+    double temperature;
+    double coupling_time;
+    double drude_temperature;
+    double drude_coupling_time;
+    double step_size;
+    double max_drude_distance;       /* 0 disables the hard wall */
+    /* host tables, copied during tgnh_create */
+    const double* masses;            /* [N] System::getParticleMass */
+    const int32_t* pair_drude;       /* [P] DrudeForce::getParticleParameters particle  */
+    const int32_t* pair_parent;      /* [P] DrudeForce::getParticleParameters particle1 */
+    const int32_t* particle_temp_group; /* [N] */
+    const int32_t* particle_res_id;  /* [N]; each residue must be a contiguous index range (the reference assumes it, drudeTGNH.cu:86-101) */
+    const int32_t* constraint_p;     /* [C] */
+    const int32_t* constraint_p1;    /* [C] */
+    /* sharding: NULL = single GPU.  With a communicator the tables above describe this rank's molecule-aligned
+       particle range; DOF / thermostat masses are summed over ranks at create time and the per-group
+       kinetic-energy vector is all-reduced (NCCL, double[G+2]) before every chain update. */
+    tgnh_comm* comm;
+} tgnh_params;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int tgnh_create(const tgnh_params* params, tgnh_handle** out);
+void tgnh_destroy(tgnh_handle* h);
+const char* tgnh_last_error(void);
+/* "sm_100a" build info, for diagnostics */
+const char* tgnh_build_info(void);
+
+/* ---- the step (streams are cudaStream_t passed as void*) ---------------------------------- */
+/* First half: thermostat half-step (KE -> chain -> scale), half kick, drift, hard wall.
+ * = CudaDrudeTGNHKernels.cpp:336-376 without the OpenMM constraint call at :363. */
+int tgnh_half1(tgnh_handle* h, void* stream, void* velm, void* posq, const void* force);
+/* Second half: half kick with the new forces, thermostat half-step.  = :384-402 without :391. */
+int tgnh_half2(tgnh_handle* h, void* stream, void* velm, const void* force, int flags);
+/* Apply a pending (deferred) velocity scaling so that velm is what the reference would hold. */
+int tgnh_flush(tgnh_handle* h, void* stream, void* velm);
+/* nsteps full steps with the SAME force array in both halves (integrator-only path with fixed
+ * synthetic forces).  Internally defers/folds the scaling between steps; velm is consistent on return. */
+int tgnh_step(tgnh_handle* h, void* stream, void* velm, void* posq, const void* force, int nsteps);
+/* Host-buffer convenience (end-to-end path): copies velm/posq/force from pinned or pageable HOST memory,
+ * runs nsteps, copies velm/posq back and the 2*KE vector into ke2_host ([G+2], may be NULL). Blocking. */
+int tgnh_step_host(tgnh_handle* h, void* velm_host, void* posq_host, const void* force_host, int nsteps, double* ke2_host);
+/* The velocities were changed behind the integrator's back (DrudeTGNHIntegrator::stateChanged,
+ * openmmapi/src/DrudeTGNHIntegrator.cpp:166-170): cached kinetic energies are dropped. */
+int tgnh_invalidate(tgnh_handle* h);
+
+/* ---- thermostat state (blocking; they synchronise `stream`) -------------------------------- */
+/* sizes: T = G+2 thermostats (G relative groups, COM group at G, Drude group at G+1) */
+int tgnh_num_thermostats(const tgnh_handle* h);
+/* 2*KE per thermostat as consumed by the most recent chain update (kineticEnergiesVec, :490) */
+int tgnh_get_kinetic_energies(tgnh_handle* h, void* stream, double* ke2 /*[T]*/);
+/* 0.5 * sum(2KE) cached by the last chain update (KESum, :493-497 / :654-658) */
+int tgnh_kinetic_energy(tgnh_handle* h, void* stream, double* ke_sum);
+/* 2*KE per thermostat of the velocities as they are now (runs the reduction kernel) */
+int tgnh_compute_kinetic_energies(tgnh_handle* h, void* stream, const void* velm, double* ke2 /*[T]*/);
+/* eta [T*M], eta_dot [T*(M+1)] (last column is the permanent 0), eta_dot_dot [T*M]  (CudaDrudeTGNHKernels.h:90-93) */
+int tgnh_get_chain_state(tgnh_handle* h, void* stream, double* eta, double* eta_dot, double* eta_dot_dot);
+int tgnh_set_chain_state(tgnh_handle* h, void* stream, const double* eta, const double* eta_dot, const double* eta_dot_dot);
+/* velocity scale factors produced by the most recent chain update (vscaleFactorsVec) */
+int tgnh_get_vscale(tgnh_handle* h, void* stream, double* vscale /*[T]*/);
+/* dof[T] (dof - COM share), NkT[T], eta_mass[T*M]  (tempGroupDof/tempGroupNkbT/etaMass, :215-235) */
+int tgnh_get_thermostat_params(const tgnh_handle* h, double* dof, double* nkbt, double* eta_mass);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t tgnh_launch_count(const tgnh_handle* h);
+/* Per-launch device timing: while enabled every streaming launch is bracketed by CUDA events on its stream.
+ * tgnh_get_profile synchronises, returns accumulated milliseconds and launch counts for
+ * [0] first-half kernel, [1] second-half kernel, [2] reduce/flush kernel, and resets the accumulators. */
+int tgnh_set_profiling(tgnh_handle* h, int enabled);
+int tgnh_get_profile(tgnh_handle* h, double* ms /*[3]*/, int64_t* counts /*[3]*/);
+
+/* ---- sharding over the GPUs of one node (NCCL over NVLink) --------------------------------- */
+#define TGNH_UNIQUE_ID_BYTES 128
+int tgnh_comm_get_unique_id(void* id_out /*[128]*/);
+int tgnh_comm_create(const void* unique_id, int world_size, int rank, int device, tgnh_comm** out);
+void tgnh_comm_destroy(tgnh_comm* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGNH_H_ */

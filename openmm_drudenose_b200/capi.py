@@ -1,0 +1,229 @@
+"""ctypes binding of libtgnh.so (include/tgnh.h) — the only way Python reaches the CUDA path.
+
+There is no fallback: if the library is missing or no B200 is visible, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtgnh.so")
+
+OK, ERR_INVALID_ARGUMENT, ERR_TEMP_GROUP, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE = range(7)
+FORCE_F32_SOA, FORCE_I64_SOA = 0, 1
+HALF2_DEFAULT, HALF2_DEFER_SCALE = 0, 1
+UNIQUE_ID_BYTES = 128
+BOLTZ = 1.380649e-23 * 6.02214076e23 / 1000.0
+
+# every symbol include/tgnh.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "tgnh_create", "tgnh_destroy", "tgnh_last_error", "tgnh_build_info", "tgnh_half1", "tgnh_half2", "tgnh_flush",
+    "tgnh_step", "tgnh_step_host", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_get_kinetic_energies",
+    "tgnh_kinetic_energy", "tgnh_compute_kinetic_energies", "tgnh_get_chain_state", "tgnh_set_chain_state",
+    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
+    "tgnh_comm_create", "tgnh_comm_destroy",
+]
+
+
+class TgnhError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libtgnh error {code}: {message}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "num_particles", "padded_num_particles", "num_pairs", "num_residues", "num_temp_groups", "num_constraints",
+        "num_nh_chains", "drude_steps_per_real_step", "use_drude_nh_chains", "use_com_temp_group",
+        "has_cm_motion_remover", "force_format", "device", "reserved")] + [(n, C.c_double) for n in (
+        "temperature", "coupling_time", "drude_temperature", "drude_coupling_time", "step_size",
+        "max_drude_distance")] + [
+        ("masses", C.POINTER(C.c_double)), ("pair_drude", C.POINTER(C.c_int32)), ("pair_parent", C.POINTER(C.c_int32)),
+        ("particle_temp_group", C.POINTER(C.c_int32)), ("particle_res_id", C.POINTER(C.c_int32)),
+        ("constraint_p", C.POINTER(C.c_int32)), ("constraint_p1", C.POINTER(C.c_int32)), ("comm", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libtgnh.so; raises if it has not been built (no CPU path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        dp, vp = C.POINTER(C.c_double), C.c_void_p
+        L.tgnh_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+        L.tgnh_destroy.argtypes = [vp]
+        L.tgnh_destroy.restype = None
+        L.tgnh_last_error.restype = C.c_char_p
+        L.tgnh_build_info.restype = C.c_char_p
+        L.tgnh_half1.argtypes = [vp, vp, vp, vp, vp]
+        L.tgnh_half2.argtypes = [vp, vp, vp, vp, C.c_int]
+        L.tgnh_flush.argtypes = [vp, vp, vp]
+        L.tgnh_step.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+        L.tgnh_step_host.argtypes = [vp, vp, vp, vp, C.c_int, dp]
+        L.tgnh_invalidate.argtypes = [vp]
+        L.tgnh_num_thermostats.argtypes = [vp]
+        L.tgnh_get_kinetic_energies.argtypes = [vp, vp, dp]
+        L.tgnh_kinetic_energy.argtypes = [vp, vp, dp]
+        L.tgnh_compute_kinetic_energies.argtypes = [vp, vp, vp, dp]
+        L.tgnh_get_chain_state.argtypes = [vp, vp, dp, dp, dp]
+        L.tgnh_set_chain_state.argtypes = [vp, vp, dp, dp, dp]
+        L.tgnh_get_vscale.argtypes = [vp, vp, dp]
+        L.tgnh_get_thermostat_params.argtypes = [vp, dp, dp, dp]
+        L.tgnh_launch_count.argtypes = [vp]
+        L.tgnh_launch_count.restype = C.c_int64
+        L.tgnh_set_profiling.argtypes = [vp, C.c_int]
+        L.tgnh_get_profile.argtypes = [vp, dp, C.POINTER(C.c_int64)]
+        L.tgnh_comm_get_unique_id.argtypes = [vp]
+        L.tgnh_comm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.tgnh_comm_destroy.argtypes = [vp]
+        L.tgnh_comm_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise TgnhError(rc, lib().tgnh_last_error().decode())
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None and len(a) else None
+
+
+class Comm:
+    """NCCL communicator for particle-range sharding (one process per GPU)."""
+
+    def __init__(self, unique_id: bytes, world_size: int, rank: int, device: int):
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, UNIQUE_ID_BYTES)
+        check(lib().tgnh_comm_create(buf, world_size, rank, device, C.byref(h)))
+        self.h, self.world_size, self.rank = h, world_size, rank
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+        check(lib().tgnh_comm_get_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if self.h:
+            lib().tgnh_comm_destroy(self.h)
+            self.h = None
+
+
+class Handle:
+    """Owns one tgnh_handle.  Buffers are passed as raw device pointers (ints), e.g. tensor.data_ptr()."""
+
+    def __init__(self, system, *, force_format=FORCE_F32_SOA, padded=None, device=-1, comm=None,
+                 has_cm_motion_remover=False, constraints=None, **overrides):
+        s = system
+        n = s.num_particles
+        padded = padded or ((n + 31) // 32) * 32
+        cons = s.constraints if constraints is None else constraints
+        cons = np.ascontiguousarray(cons, np.int32).reshape(-1, 2)
+        self._keep = dict(
+            masses=np.ascontiguousarray(s.masses, np.float64), pd=np.ascontiguousarray(s.pair_drude, np.int32),
+            pp=np.ascontiguousarray(s.pair_parent, np.int32), tg=np.ascontiguousarray(s.temp_group, np.int32),
+            res=np.ascontiguousarray(s.res_id, np.int32), c0=np.ascontiguousarray(cons[:, 0]),
+            c1=np.ascontiguousarray(cons[:, 1]))
+        k = self._keep
+        p = Params(
+            num_particles=n, padded_num_particles=padded, num_pairs=len(k["pd"]), num_residues=s.num_residues,
+            num_temp_groups=s.num_temp_groups, num_constraints=len(cons), num_nh_chains=s.num_nh_chains,
+            drude_steps_per_real_step=s.drude_steps, use_drude_nh_chains=int(s.use_drude_nh_chains),
+            use_com_temp_group=int(s.use_com_temp_group), has_cm_motion_remover=int(has_cm_motion_remover),
+            force_format=force_format, device=device, temperature=s.temperature, coupling_time=s.coupling_time,
+            drude_temperature=s.drude_temperature, drude_coupling_time=s.drude_coupling_time, step_size=s.step_size,
+            max_drude_distance=s.max_drude_distance, masses=_dp(k["masses"]), pair_drude=_ip(k["pd"]),
+            pair_parent=_ip(k["pp"]), particle_temp_group=_ip(k["tg"]), particle_res_id=_ip(k["res"]),
+            constraint_p=_ip(k["c0"]), constraint_p1=_ip(k["c1"]), comm=comm.h if comm is not None else None)
+        for key, val in overrides.items():
+            setattr(p, key, val)
+        self.padded = padded
+        self.num_particles = n
+        self.M = p.num_nh_chains
+        h = C.c_void_p()
+        check(lib().tgnh_create(C.byref(p), C.byref(h)))
+        self.h = h
+        self.T = lib().tgnh_num_thermostats(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tgnh_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- the step ----
+    def half1(self, velm, posq, force, stream=0):
+        check(lib().tgnh_half1(self.h, stream, velm, posq, force))
+
+    def half2(self, velm, force, flags=HALF2_DEFAULT, stream=0):
+        check(lib().tgnh_half2(self.h, stream, velm, force, flags))
+
+    def flush(self, velm, stream=0):
+        check(lib().tgnh_flush(self.h, stream, velm))
+
+    def step(self, velm, posq, force, nsteps=1, stream=0):
+        check(lib().tgnh_step(self.h, stream, velm, posq, force, nsteps))
+
+    def step_host(self, velm_host, posq_host, force_host, nsteps=1):
+        """host numpy arrays (or pinned pointers as ints); returns the 2*KE vector consumed by the last chain update"""
+        ke2 = np.zeros(self.T)
+        as_ptr = lambda a: a if isinstance(a, int) else a.ctypes.data
+        check(lib().tgnh_step_host(self.h, as_ptr(velm_host), as_ptr(posq_host), as_ptr(force_host), nsteps, _dp(ke2)))
+        return ke2
+
+    def invalidate(self):
+        check(lib().tgnh_invalidate(self.h))
+
+    # ---- thermostat state ----
+    def kinetic_energies(self, stream=0):
+        out = np.zeros(self.T); check(lib().tgnh_get_kinetic_energies(self.h, stream, _dp(out))); return out
+
+    def kinetic_energy(self, stream=0):
+        out = C.c_double(); check(lib().tgnh_kinetic_energy(self.h, stream, C.byref(out))); return out.value
+
+    def compute_kinetic_energies(self, velm, stream=0):
+        out = np.zeros(self.T); check(lib().tgnh_compute_kinetic_energies(self.h, stream, velm, _dp(out))); return out
+
+    def vscale(self, stream=0):
+        out = np.zeros(self.T); check(lib().tgnh_get_vscale(self.h, stream, _dp(out))); return out
+
+    def chain_state(self, stream=0):
+        eta = np.zeros((self.T, self.M)); ed = np.zeros((self.T, self.M + 1)); edd = np.zeros((self.T, self.M))
+        check(lib().tgnh_get_chain_state(self.h, stream, _dp(eta), _dp(ed), _dp(edd)))
+        return eta, ed, edd
+
+    def set_chain_state(self, eta, ed, edd, stream=0):
+        eta = np.ascontiguousarray(eta, np.float64); ed = np.ascontiguousarray(ed, np.float64)
+        edd = np.ascontiguousarray(edd, np.float64)
+        check(lib().tgnh_set_chain_state(self.h, stream, _dp(eta), _dp(ed), _dp(edd)))
+
+    def thermostat_params(self):
+        dof = np.zeros(self.T); nkbt = np.zeros(self.T); q = np.zeros((self.T, self.M))
+        check(lib().tgnh_get_thermostat_params(self.h, _dp(dof), _dp(nkbt), _dp(q)))
+        return dof, nkbt, q
+
+    def set_profiling(self, enabled=True):
+        check(lib().tgnh_set_profiling(self.h, int(enabled)))
+
+    def profile(self):
+        """{'half1': (ms, launches), 'half2': ..., 'reduce': ...} accumulated since the last call"""
+        ms = np.zeros(3); cnt = np.zeros(3, np.int64)
+        check(lib().tgnh_get_profile(self.h, _dp(ms), cnt.ctypes.data_as(C.POINTER(C.c_int64))))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("half1", "half2", "reduce"))}
+
+    @property
+    def launch_count(self):
+        return lib().tgnh_launch_count(self.h)

@@ -1,0 +1,694 @@
+// libtgnh.so — C-ABI (include/tgnh.h) over the sm_100a TGNH kernels.
+//
+// Host half of the hot path: what CudaIntegrateDrudeTGNHStepKernel::initialize / execute /
+// propagateNHChain do in the reference (platforms/cuda/src/CudaDrudeTGNHKernels.cpp:75-282, 284-408,
+// 433-652), re-designed so that a step is two streaming launches with the Nose-Hoover chain resident
+// on the device: no D2H/H2D on the step path, no runtime kernel compilation.
+#include "../../include/tgnh.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tgnh_kernels.cuh"
+
+using namespace tgnh;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) return fail(TGNH_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define TGNH_STR2(x) #x
+#define TGNH_STR(x) TGNH_STR2(x)
+extern "C" const char* tgnh_last_error(void) { return g_error.c_str(); }
+extern "C" const char* tgnh_build_info(void) { return "libtgnh sm_100a AOT (CUDA " TGNH_STR(CUDART_VERSION) "), TMA bulk pipeline, device-resident NH chain"; }
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time so that a process that already loaded a libnccl.so.2 (e.g. torch) shares it
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.lib) return TGNH_OK;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(TGNH_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.GetErrorString)
+        return fail(TGNH_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
+    g_nccl.lib = lib;
+    return TGNH_OK;
+}
+
+#define NCCL_TRY(expr)                                                                               \
+    do {                                                                                             \
+        ncclResult_t r_ = (expr);                                                                    \
+        if (r_ != ncclSuccess) return fail(TGNH_ERR_NCCL, "%s failed: %s", #expr, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+struct tgnh_comm {
+    ncclComm_t comm = nullptr;
+    int worldSize = 1, rank = 0, device = 0;
+};
+
+extern "C" int tgnh_comm_get_unique_id(void* id_out) {
+    if (!id_out) return fail(TGNH_ERR_INVALID_ARGUMENT, "id_out is null");
+    if (int rc = nccl_load()) return rc;
+    static_assert(sizeof(ncclUniqueId) == TGNH_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_comm_create(const void* unique_id, int world_size, int rank, int device, tgnh_comm** out) {
+    if (!unique_id || !out || world_size < 1 || rank < 0 || rank >= world_size)
+        return fail(TGNH_ERR_INVALID_ARGUMENT, "bad communicator arguments");
+    if (int rc = nccl_load()) return rc;
+    if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+    else CUDA_TRY(cudaGetDevice(&device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    tgnh_comm* c = new tgnh_comm();
+    c->worldSize = world_size; c->rank = rank; c->device = device;
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world_size, id, rank);
+    if (r != ncclSuccess) { delete c; return fail(TGNH_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); }
+    *out = c;
+    return TGNH_OK;
+}
+
+extern "C" void tgnh_comm_destroy(tgnh_comm* c) {
+    if (!c) return;
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct tgnh_handle {
+    int device = 0, numSMs = 0;
+    int N = 0, paddedN = 0, P = 0, R = 0, G = 0, T = 0, M = 0, S = 0;
+    int useDrudeNH = 0, useCOM = 0, ffmt = 0, hardwall = 0;
+    bool uniformGroups = true;   // every residue lies in one temperature group (folding / KE carry-over legal)
+    double dt = 0, rmax = 0, kT = 0, kTD = 0;
+    int numTiles = 0;
+    // device
+    uint32_t* dDesc = nullptr;
+    int* dTileStart = nullptr;
+    double* dChain = nullptr;     // one allocation holding every ChainView array
+    double* dPartials = nullptr;
+    unsigned int* dTicket = nullptr;
+    ChainView chain{};
+    size_t chainDoubles = 0;
+    int gridA = 0, gridB = 0, gridKE = 0;
+    int smemA = 0, smemB = 0, smemKE = 0;
+    // host copies of the thermostat parameters
+    std::vector<double> dof, nkbt, etaMass;
+    // state machine
+    bool keValid = false;         // chain.ke2 describes the velocities as stored
+    bool scalePending = false;    // chain.pending != 1 has not been applied to velm yet
+    int64_t launches = 0;
+    tgnh_comm* comm = nullptr;
+    // optional per-launch device timing (bench.py's roofline leg)
+    bool profiling = false;
+    std::vector<cudaEvent_t> evPool;
+    std::vector<int> evKind;      // kind of the launch bracketed by evPool[2i], evPool[2i+1]
+    size_t evUsed = 0;
+    // staging buffers of tgnh_step_host
+    void *hsVelm = nullptr, *hsPosq = nullptr, *hsForce = nullptr;
+    cudaStream_t hsStream = nullptr;
+};
+
+typedef void (*StreamKernel)(const StreamArgs);
+
+template <int KIND, int FFMT>
+static StreamKernel pick2(bool useCOM, bool hardwall) {
+    if (KIND == KIND_A) {   // only the first-half kernel contains the hard wall
+        if (useCOM) return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, true, true> : tgnh_stream_kernel<KIND_A, FFMT, true, false>;
+        return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, false, true> : tgnh_stream_kernel<KIND_A, FFMT, false, false>;
+    }
+    return useCOM ? tgnh_stream_kernel<KIND, FFMT, true, false> : tgnh_stream_kernel<KIND, FFMT, false, false>;
+}
+
+static StreamKernel pick(int kind, int ffmt, bool useCOM, bool hardwall) {
+    switch (kind) {
+        case KIND_A: return ffmt ? pick2<KIND_A, 1>(useCOM, hardwall) : pick2<KIND_A, 0>(useCOM, hardwall);
+        case KIND_B: return ffmt ? pick2<KIND_B, 1>(useCOM, false) : pick2<KIND_B, 0>(useCOM, false);
+        default: return pick2<KIND_KE, 0>(useCOM, false);
+    }
+}
+
+static int smem_bytes(int kind, int ffmt, bool useCOM, int T) {
+    switch (kind) {
+        case KIND_A:
+            if (ffmt) return useCOM ? SmemLayout<KIND_A, 1, true>::bytes(T) : SmemLayout<KIND_A, 1, false>::bytes(T);
+            return useCOM ? SmemLayout<KIND_A, 0, true>::bytes(T) : SmemLayout<KIND_A, 0, false>::bytes(T);
+        case KIND_B:
+            if (ffmt) return useCOM ? SmemLayout<KIND_B, 1, true>::bytes(T) : SmemLayout<KIND_B, 1, false>::bytes(T);
+            return useCOM ? SmemLayout<KIND_B, 0, true>::bytes(T) : SmemLayout<KIND_B, 0, false>::bytes(T);
+        default:
+            return useCOM ? SmemLayout<KIND_KE, 0, true>::bytes(T) : SmemLayout<KIND_KE, 0, false>::bytes(T);
+    }
+}
+
+static int configure_kernel(tgnh_handle* h, int kind, int* grid, int* smem) {
+    StreamKernel k = pick(kind, h->ffmt, h->useCOM, h->hardwall);
+    *smem = smem_bytes(kind, h->ffmt, h->useCOM, h->T);
+    if (*smem > 227 * 1024)
+        return fail(TGNH_ERR_UNSUPPORTED, "%d temperature groups need %d bytes of shared memory per CTA (limit 232448)", h->G, *smem);
+    CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem));
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, TILE, *smem));
+    if (occ < 1) return fail(TGNH_ERR_CUDA, "kernel kind %d cannot be resident (smem %d B)", kind, *smem);
+    int g = occ * h->numSMs;
+    if (g > h->numTiles) g = h->numTiles;
+    if (g < 1) g = 1;
+    *grid = g;
+    return TGNH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// create: index tables, DOF bookkeeping, thermostat masses (CudaDrudeTGNHKernels.cpp:75-235)
+// ------------------------------------------------------------------------------------------------
+extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
+    if (!p || !out) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    const int N = p->num_particles, P = p->num_pairs, R = p->num_residues, G = p->num_temp_groups, M = p->num_nh_chains;
+    const int T = G + 2;
+    if (N < 1) return fail(TGNH_ERR_INVALID_ARGUMENT, "num_particles must be positive");
+    if (P < 0 || R < 1 || G < 1) return fail(TGNH_ERR_INVALID_ARGUMENT, "num_pairs/num_residues/num_temp_groups out of range");
+    if (!p->masses || !p->particle_temp_group || !p->particle_res_id || (P > 0 && (!p->pair_drude || !p->pair_parent)))
+        return fail(TGNH_ERR_INVALID_ARGUMENT, "a required host table is null");
+    if (p->num_constraints < 0 || (p->num_constraints > 0 && (!p->constraint_p || !p->constraint_p1)))
+        return fail(TGNH_ERR_INVALID_ARGUMENT, "constraint tables missing");
+    if (T > MAX_T) return fail(TGNH_ERR_UNSUPPORTED, "at most %d temperature groups are supported (got %d)", MAX_T - 2, G);
+    if (M < 1 || M > MAX_M) return fail(TGNH_ERR_UNSUPPORTED, "numNHChains must be in [1,%d] (got %d)", MAX_M, M);
+    if (p->drude_steps_per_real_step < 1) return fail(TGNH_ERR_INVALID_ARGUMENT, "drudeStepsPerRealStep must be >= 1");
+    if (p->padded_num_particles < N || (p->padded_num_particles & 3))
+        return fail(TGNH_ERR_INVALID_ARGUMENT, "padded_num_particles must be a multiple of 4 and >= num_particles");
+    if (p->force_format != TGNH_FORCE_F32_SOA && p->force_format != TGNH_FORCE_I64_SOA)
+        return fail(TGNH_ERR_INVALID_ARGUMENT, "unknown force_format %d", p->force_format);
+    if (p->max_drude_distance < 0) return fail(TGNH_ERR_INVALID_ARGUMENT, "setMaxDrudeDistance: Distance cannot be negative");
+    if (!(p->step_size > 0)) return fail(TGNH_ERR_INVALID_ARGUMENT, "step_size must be positive");
+
+    int deviceCount = 0;
+    if (cudaGetDeviceCount(&deviceCount) != cudaSuccess || deviceCount == 0)
+        return fail(TGNH_ERR_NO_DEVICE, "no CUDA device: libtgnh has no CPU fallback");
+    int device = p->device;
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(TGNH_ERR_NO_DEVICE, "device %d is sm_%d%d; libtgnh is built for sm_100a (B200) only", device, prop.major, prop.minor);
+
+    // ---- residues: contiguous ranges (drudeTGNH.cu:86-101 assumes it silently; we check) ----
+    std::vector<int> resFirst(R, -1), resLast(R, -1);
+    std::vector<double> resMass(R, 0.0);
+    for (int i = 0; i < N; i++) {
+        const int r = p->particle_res_id[i];
+        if (r < 0 || r >= R) return fail(TGNH_ERR_INVALID_ARGUMENT, "particle %d has residue id %d outside [0,%d)", i, r, R);
+        if (resFirst[r] < 0) resFirst[r] = i;
+        else if (resLast[r] != i - 1)
+            return fail(TGNH_ERR_UNSUPPORTED, "residue %d is not a contiguous particle range (particle %d)", r, i);
+        resLast[r] = i;
+        resMass[r] += p->masses[i];                                   // DrudeTGNHIntegrator.cpp:147-148
+        const int tg = p->particle_temp_group[i];
+        if (tg < 0 || tg >= G) return fail(TGNH_ERR_INVALID_ARGUMENT, "particle %d has temperature group %d outside [0,%d)", i, tg, G);
+    }
+    bool uniform = true;
+    for (int r = 0; r < R; r++) {
+        if (resFirst[r] < 0) return fail(TGNH_ERR_INVALID_ARGUMENT, "residue %d has no particles", r);
+        if (resLast[r] - resFirst[r] + 1 > MAX_RES)
+            return fail(TGNH_ERR_UNSUPPORTED, "residue %d has %d particles; the in-tile COM path handles at most %d", r,
+                        resLast[r] - resFirst[r] + 1, MAX_RES);
+        for (int i = resFirst[r] + 1; i <= resLast[r]; i++)
+            if (p->particle_temp_group[i] != p->particle_temp_group[resFirst[r]]) uniform = false;
+    }
+
+    // ---- DOF bookkeeping (CudaDrudeTGNHKernels.cpp:114-150, 186-212) ----
+    std::vector<double> dofv(T, 0.0), redMass(G + 1, 0.0);
+    for (int i = 0; i < N; i++) {
+        const int tg = p->particle_temp_group[i];
+        const double mass = p->masses[i];
+        if (mass != 0.0) {
+            dofv[tg] += 3;
+            if (p->use_com_temp_group) redMass[tg] += 3 * mass * (1.0 / resMass[p->particle_res_id[i]]);
+        }
+    }
+    std::vector<int> partner(N, 0);
+    std::vector<uint32_t> role(N, ROLE_NORMAL);
+    double drudeDof = 0;
+    for (int i = 0; i < P; i++) {
+        const int d = p->pair_drude[i], q = p->pair_parent[i];
+        if (d < 0 || d >= N || q < 0 || q >= N || d == q) return fail(TGNH_ERR_INVALID_ARGUMENT, "Drude pair %d has a bad particle index", i);
+        if (role[d] != ROLE_NORMAL || role[q] != ROLE_NORMAL)
+            return fail(TGNH_ERR_UNSUPPORTED, "particle of Drude pair %d belongs to more than one pair", i);
+        if (p->particle_temp_group[d] != p->particle_temp_group[q])
+            return fail(TGNH_ERR_TEMP_GROUP, "Temperature group for drude particle must be the same as the parent particle");
+        if (p->particle_res_id[d] != p->particle_res_id[q])
+            return fail(TGNH_ERR_UNSUPPORTED, "Drude pair %d spans two residues", i);
+        if (p->masses[d] == 0.0) return fail(TGNH_ERR_INVALID_ARGUMENT, "Drude particle %d is massless", d);
+        role[d] = ROLE_DRUDE; role[q] = ROLE_PARENT;
+        partner[d] = q - d; partner[q] = d - q;
+        dofv[p->particle_temp_group[d]] -= 3;
+        drudeDof += 3;
+    }
+    for (int i = 0; i < p->num_constraints; i++) {
+        const int a = p->constraint_p[i], b = p->constraint_p1[i];
+        if (a < 0 || a >= N || b < 0 || b >= N) return fail(TGNH_ERR_INVALID_ARGUMENT, "constraint %d has a bad particle index", i);
+        if (p->particle_temp_group[a] != p->particle_temp_group[b])
+            return fail(TGNH_ERR_TEMP_GROUP, "Temperature group of constrained particles must be the same");
+        dofv[p->particle_temp_group[a]] -= 1;
+    }
+    double comDof = p->use_com_temp_group ? 3.0 * R : 0.0;
+
+    tgnh_handle* h = new tgnh_handle();
+    h->device = device; h->numSMs = prop.multiProcessorCount;
+    h->N = N; h->paddedN = p->padded_num_particles; h->P = P; h->R = R; h->G = G; h->T = T; h->M = M;
+    h->S = p->drude_steps_per_real_step;
+    h->useDrudeNH = p->use_drude_nh_chains != 0; h->useCOM = p->use_com_temp_group != 0;
+    h->ffmt = p->force_format; h->hardwall = p->max_drude_distance > 0;
+    h->uniformGroups = uniform;
+    h->dt = p->step_size; h->rmax = p->max_drude_distance;
+    h->kT = TGNH_BOLTZ * p->temperature; h->kTD = TGNH_BOLTZ * p->drude_temperature;
+    h->comm = p->comm;
+    auto bail = [&](int rc) { tgnh_destroy(h); return rc; };
+
+    // ---- sharded: DOF sums are global (the thermostats see the whole system) ----
+    if (h->comm && h->comm->worldSize > 1) {
+        std::vector<double> pack(T + G + 3, 0.0);
+        for (int g = 0; g < T; g++) pack[g] = dofv[g];
+        for (int g = 0; g <= G; g++) pack[T + g] = redMass[g];
+        pack[T + G + 1] = drudeDof; pack[T + G + 2] = comDof;
+        double* dpack = nullptr;
+        if (cudaMalloc(&dpack, pack.size() * sizeof(double)) != cudaSuccess) return bail(fail(TGNH_ERR_CUDA, "cudaMalloc failed"));
+        cudaMemcpy(dpack, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice);
+        ncclResult_t r = g_nccl.AllReduce(dpack, dpack, pack.size(), ncclDouble, ncclSum, h->comm->comm, 0);
+        cudaError_t e = cudaStreamSynchronize(0);
+        cudaMemcpy(pack.data(), dpack, pack.size() * sizeof(double), cudaMemcpyDeviceToHost);
+        cudaFree(dpack);
+        if (r != ncclSuccess || e != cudaSuccess) return bail(fail(TGNH_ERR_NCCL, "all-reduce of the DOF table failed"));
+        for (int g = 0; g < T; g++) dofv[g] = pack[g];
+        for (int g = 0; g <= G; g++) redMass[g] = pack[T + g];
+        drudeDof = pack[T + G + 1]; comDof = pack[T + G + 2];
+    }
+    if (p->use_com_temp_group) {
+        dofv[G] = comDof;                                             // :197-199
+        if (p->has_cm_motion_remover) dofv[G] -= 3;                   // :204-212
+    }
+    dofv[G + 1] = drudeDof;                                           // :201
+
+    // ---- thermostat masses (CudaDrudeTGNHKernels.cpp:215-235) ----
+    const double realkbT = h->kT, drudekbT = h->kTD;
+    const double realUnit = realkbT * p->coupling_time * p->coupling_time;
+    const double drudeUnit = drudekbT * p->drude_coupling_time * p->drude_coupling_time;
+    h->dof.assign(T, 0.0); h->nkbt.assign(T, 0.0); h->etaMass.assign((size_t)T * M, 0.0);
+    std::vector<double> etaDotDot((size_t)T * M, 0.0);
+    for (int g = 0; g <= G; g++) {
+        h->dof[g] = dofv[g] - redMass[g];
+        h->nkbt[g] = (dofv[g] - redMass[g]) * realkbT;
+        h->etaMass[g * M] = (dofv[g] - redMass[g]) * realUnit;
+        for (int i = 1; i < M; i++) {
+            h->etaMass[g * M + i] = realUnit;
+            etaDotDot[g * M + i] = (h->etaMass[g * M + i - 1] * 0.0 - realkbT) / h->etaMass[g * M + i];
+        }
+    }
+    h->dof[G + 1] = drudeDof;
+    h->nkbt[G + 1] = drudeDof * drudekbT;
+    h->etaMass[(G + 1) * M] = drudeDof * drudeUnit;
+    for (int i = 1; i < M; i++) {
+        h->etaMass[(G + 1) * M + i] = drudeUnit;
+        if (h->useDrudeNH) etaDotDot[(G + 1) * M + i] = (h->etaMass[(G + 1) * M + i - 1] * 0.0 - drudekbT) / h->etaMass[(G + 1) * M + i];
+    }
+
+    // ---- descriptors and residue-aligned tiles ----
+    const int descLen = (N + 3) & ~3;
+    std::vector<uint32_t> desc(descLen, 0u);
+    for (int i = 0; i < N; i++) {
+        const int r = p->particle_res_id[i];
+        if (partner[i] < -128 || partner[i] > 127) return bail(fail(TGNH_ERR_UNSUPPORTED, "Drude pair partner of particle %d is %d particles away (limit 127)", i, partner[i]));
+        desc[i] = desc_pack(p->particle_temp_group[i], role[i], i - resFirst[r], resLast[r] - i, partner[i]);
+    }
+    std::vector<int> tileStart;
+    tileStart.push_back(0);
+    {
+        int cur = 0;                          // particles in the open tile
+        int r = p->particle_res_id[0];
+        int i = 0;
+        while (i < N) {
+            r = p->particle_res_id[i];
+            const int len = resLast[r] - resFirst[r] + 1;
+            if (cur + len > TILE) { tileStart.push_back(i); cur = 0; }
+            cur += len;
+            i += len;
+        }
+        tileStart.push_back(N);
+    }
+    h->numTiles = (int)tileStart.size() - 1;
+
+    // ---- device allocations ----
+    auto dmalloc = [&](void** ptr, size_t bytes) { return cudaMalloc(ptr, bytes ? bytes : 16) == cudaSuccess; };
+    if (!dmalloc((void**)&h->dDesc, desc.size() * 4) || !dmalloc((void**)&h->dTileStart, tileStart.size() * 4) ||
+        !dmalloc((void**)&h->dTicket, 4))
+        return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the index tables failed"));
+    cudaMemcpy(h->dDesc, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->dTileStart, tileStart.data(), tileStart.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(h->dTicket, 0, 4);
+
+    // chain block: etaMass, eta, etaDot, etaDotDot, nkbt, ke2, ke2Local, ke2Used, pending, scaleA, vscale, keSum
+    const size_t TM = (size_t)T * M;
+    h->chainDoubles = 3 * TM + (size_t)T * (M + 1) + 7 * T + 1;
+    if (!dmalloc((void**)&h->dChain, h->chainDoubles * 8)) return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the chain state failed"));
+    std::vector<double> init(h->chainDoubles, 0.0);
+    {
+        double* b = h->dChain;
+        ChainView& c = h->chain;
+        c.T = T; c.G = G; c.M = M; c.S = h->S; c.useDrudeNH = h->useDrudeNH;
+        c.dt = h->dt; c.kT = h->kT; c.kTD = h->kTD;
+        size_t o = 0;
+        c.etaMass = b + o; memcpy(&init[o], h->etaMass.data(), TM * 8); o += TM;
+        c.eta = b + o; o += TM;
+        c.etaDot = b + o; o += (size_t)T * (M + 1);
+        c.etaDotDot = b + o; memcpy(&init[o], etaDotDot.data(), TM * 8); o += TM;
+        c.nkbt = b + o; memcpy(&init[o], h->nkbt.data(), T * 8); o += T;
+        c.ke2 = b + o; o += T;
+        c.ke2Local = b + o; o += T;
+        c.ke2Used = b + o; o += T;
+        c.pending = b + o; for (int g = 0; g < T; g++) init[o + g] = 1.0; o += T;
+        c.scaleA = b + o; for (int g = 0; g < T; g++) init[o + g] = 1.0; o += T;
+        c.vscale = b + o; for (int g = 0; g < T; g++) init[o + g] = 1.0; o += T;
+        c.keSum = b + o; o += 1;
+        if (!(h->comm && h->comm->worldSize > 1)) c.ke2Local = nullptr;
+    }
+    cudaMemcpy(h->dChain, init.data(), h->chainDoubles * 8, cudaMemcpyHostToDevice);
+
+    int rc;
+    if ((rc = configure_kernel(h, KIND_A, &h->gridA, &h->smemA)) || (rc = configure_kernel(h, KIND_B, &h->gridB, &h->smemB)) ||
+        (rc = configure_kernel(h, KIND_KE, &h->gridKE, &h->smemKE)))
+        return bail(rc);
+    int maxGrid = h->gridA > h->gridB ? h->gridA : h->gridB;
+    if (h->gridKE > maxGrid) maxGrid = h->gridKE;
+    if (!dmalloc((void**)&h->dPartials, (size_t)maxGrid * T * 8)) return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the partial sums failed"));
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(TGNH_ERR_CUDA, "device error during tgnh_create: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = h;
+    return TGNH_OK;
+}
+
+extern "C" void tgnh_destroy(tgnh_handle* h) {
+    if (!h) return;
+    cudaFree(h->dDesc); cudaFree(h->dTileStart); cudaFree(h->dChain); cudaFree(h->dPartials); cudaFree(h->dTicket);
+    cudaFree(h->hsVelm); cudaFree(h->hsPosq); cudaFree(h->hsForce);
+    for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
+    if (h->hsStream) cudaStreamDestroy(h->hsStream);
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+static bool sharded(const tgnh_handle* h) { return h->comm && h->comm->worldSize > 1; }
+
+static int check_ptrs(const tgnh_handle* h, const void* velm, const void* posq, const void* force, bool needX, bool needF) {
+    if (!h) return fail(TGNH_ERR_INVALID_ARGUMENT, "null handle");
+    if (!velm || ((uintptr_t)velm & 15)) return fail(TGNH_ERR_INVALID_ARGUMENT, "velm must be a 16-byte aligned device pointer");
+    if (needX && (!posq || ((uintptr_t)posq & 15))) return fail(TGNH_ERR_INVALID_ARGUMENT, "posq must be a 16-byte aligned device pointer");
+    if (needF && (!force || ((uintptr_t)force & 15))) return fail(TGNH_ERR_INVALID_ARGUMENT, "force must be a 16-byte aligned device pointer");
+    return TGNH_OK;
+}
+
+static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, void* posq, const void* force, int applyScale, int chainMode) {
+    StreamArgs a;
+    a.velm = (float4*)velm; a.posq = (float4*)posq; a.force = force;
+    a.desc = h->dDesc; a.tileStart = h->dTileStart; a.numTiles = h->numTiles; a.paddedN = h->paddedN;
+    a.dt = (float)h->dt;
+    a.fscale = (float)(h->ffmt == TGNH_FORCE_I64_SOA ? 0.5 * h->dt / 4294967296.0 : 0.5 * h->dt);   // CudaDrudeTGNHKernels.cpp:295
+    a.rmax = (float)h->rmax;
+    a.hardwallScale = (float)std::sqrt(h->kTD);                                                       // :299
+    a.applyScale = applyScale;
+    a.chainMode = sharded(h) ? CHAIN_NONE : chainMode;
+    a.partials = h->dPartials; a.ticket = h->dTicket; a.chain = h->chain;
+    const int grid = kind == KIND_A ? h->gridA : kind == KIND_B ? h->gridB : h->gridKE;
+    const int smem = kind == KIND_A ? h->smemA : kind == KIND_B ? h->smemB : h->smemKE;
+    StreamKernel k = pick(kind, h->ffmt, h->useCOM, h->hardwall);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profiling) {
+        if (h->evUsed + 2 > h->evPool.size()) {
+            cudaEvent_t a0, a1;
+            CUDA_TRY(cudaEventCreate(&a0));
+            CUDA_TRY(cudaEventCreate(&a1));
+            h->evPool.push_back(a0); h->evPool.push_back(a1);
+        }
+        e0 = h->evPool[h->evUsed]; e1 = h->evPool[h->evUsed + 1];
+        h->evKind.resize(h->evUsed / 2 + 1);
+        h->evKind[h->evUsed / 2] = kind;
+        h->evUsed += 2;
+        CUDA_TRY(cudaEventRecord(e0, s));
+    }
+    k<<<grid, TILE, smem, s>>>(a);
+    if (e1) CUDA_TRY(cudaEventRecord(e1, s));
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (kind != KIND_A && sharded(h)) {
+        // the only collective on the path: double[G+2] kinetic-energy vector over NVLink
+        NCCL_TRY(g_nccl.AllReduce(h->chain.ke2Local, h->chain.ke2, h->T, ncclDouble, ncclSum, h->comm->comm, s));
+        if (chainMode != CHAIN_NONE) {
+            tgnh_chain_kernel<<<1, 32, 0, s>>>(h->chain, chainMode);
+            h->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    return TGNH_OK;
+}
+
+static int launch_chain(tgnh_handle* h, cudaStream_t s, int mode) {
+    tgnh_chain_kernel<<<1, 32, 0, s>>>(h->chain, mode);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return TGNH_OK;
+}
+
+// make chain.ke2 describe velm; runs CHAIN_FIRST in the same launch when asked to
+static int ensure_ke(tgnh_handle* h, cudaStream_t s, void* velm, int chainMode) {
+    if (h->keValid) return chainMode == CHAIN_NONE ? TGNH_OK : launch_chain(h, s, chainMode);
+    int rc = launch_stream(h, s, KIND_KE, velm, nullptr, nullptr, 0, chainMode);
+    if (rc == TGNH_OK) h->keValid = true;
+    return rc;
+}
+
+// apply chain.pending to velm (integrateDrudeTGNHChain) and refresh ke2 from the scaled velocities
+static int flush_scale(tgnh_handle* h, cudaStream_t s, void* velm) {
+    if (!h->scalePending) return TGNH_OK;
+    int rc = launch_stream(h, s, KIND_KE, velm, nullptr, nullptr, 1, CHAIN_NONE);
+    if (rc) return rc;
+    // the kernel's last CTA resets pending to 1 (scaleA keeps the factors that were just applied)
+    h->scalePending = false;
+    h->keValid = true;
+    if (!h->uniformGroups) {
+        // residues that span temperature groups: COM velocities do not simply scale, recompute from scratch
+        h->keValid = false;
+        rc = ensure_ke(h, s, velm, CHAIN_NONE);
+    }
+    return rc;
+}
+
+extern "C" int tgnh_half1(tgnh_handle* h, void* stream, void* velm, void* posq, const void* force) {
+    if (int rc = check_ptrs(h, velm, posq, force, true, true)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (int rc = ensure_ke(h, s, velm, CHAIN_FIRST)) return rc;      // :336-337, chain on the device
+    h->scalePending = false;                                         // folded into scaleA
+    h->keValid = false;
+    return launch_stream(h, s, KIND_A, velm, posq, force, 1, CHAIN_NONE);   // :351-376
+}
+
+extern "C" int tgnh_half2(tgnh_handle* h, void* stream, void* velm, const void* force, int flags) {
+    if (int rc = check_ptrs(h, velm, nullptr, force, false, true)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (int rc = launch_stream(h, s, KIND_B, velm, nullptr, force, 0, CHAIN_SECOND)) return rc;   // :384-395
+    h->keValid = true;
+    h->scalePending = true;
+    if ((flags & TGNH_HALF2_DEFER_SCALE) && h->uniformGroups) return TGNH_OK;
+    return flush_scale(h, s, velm);                                  // :402
+}
+
+extern "C" int tgnh_flush(tgnh_handle* h, void* stream, void* velm) {
+    if (int rc = check_ptrs(h, velm, nullptr, nullptr, false, false)) return rc;
+    CUDA_TRY(cudaSetDevice(h->device));
+    return flush_scale(h, (cudaStream_t)stream, velm);
+}
+
+extern "C" int tgnh_step(tgnh_handle* h, void* stream, void* velm, void* posq, const void* force, int nsteps) {
+    if (int rc = check_ptrs(h, velm, posq, force, true, true)) return rc;
+    if (nsteps < 0) return fail(TGNH_ERR_INVALID_ARGUMENT, "nsteps must be >= 0");
+    if (nsteps == 0) return TGNH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->uniformGroups) {
+        for (int i = 0; i < nsteps; i++) {
+            if (int rc = tgnh_half1(h, stream, velm, posq, force)) return rc;
+            if (int rc = tgnh_half2(h, stream, velm, force, TGNH_HALF2_DEFAULT)) return rc;
+        }
+        return TGNH_OK;
+    }
+    if (int rc = ensure_ke(h, s, velm, CHAIN_FIRST)) return rc;
+    for (int i = 0; i < nsteps; i++) {
+        if (int rc = launch_stream(h, s, KIND_A, velm, posq, force, 1, CHAIN_NONE)) return rc;
+        // the thermostat half-step that ends step i and the one that begins step i+1 run back to back in the
+        // tail of the same launch; their scale factors are applied together by the next KIND_A pass
+        const int mode = (i + 1 < nsteps) ? CHAIN_SECOND_FIRST : CHAIN_SECOND;
+        if (int rc = launch_stream(h, s, KIND_B, velm, nullptr, force, 0, mode)) return rc;
+    }
+    h->keValid = true;
+    h->scalePending = true;
+    return flush_scale(h, s, velm);
+}
+
+extern "C" int tgnh_invalidate(tgnh_handle* h) {
+    if (!h) return fail(TGNH_ERR_INVALID_ARGUMENT, "null handle");
+    h->keValid = false;
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_step_host(tgnh_handle* h, void* velm_host, void* posq_host, const void* force_host, int nsteps, double* ke2_host) {
+    if (!h || !velm_host || !posq_host || !force_host) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t fbytes = (size_t)3 * h->paddedN * (h->ffmt == TGNH_FORCE_I64_SOA ? 8 : 4);
+    if (!h->hsStream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->hsStream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc(&h->hsVelm, (size_t)h->paddedN * 16));
+        CUDA_TRY(cudaMalloc(&h->hsPosq, (size_t)h->paddedN * 16));
+        CUDA_TRY(cudaMalloc(&h->hsForce, fbytes));
+    }
+    cudaStream_t s = h->hsStream;
+    CUDA_TRY(cudaMemcpyAsync(h->hsVelm, velm_host, (size_t)h->N * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->hsPosq, posq_host, (size_t)h->N * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->hsForce, force_host, fbytes, cudaMemcpyHostToDevice, s));
+    h->keValid = false;
+    if (int rc = tgnh_step(h, s, h->hsVelm, h->hsPosq, h->hsForce, nsteps)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(velm_host, h->hsVelm, (size_t)h->N * 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(posq_host, h->hsPosq, (size_t)h->N * 16, cudaMemcpyDeviceToHost, s));
+    if (ke2_host) CUDA_TRY(cudaMemcpyAsync(ke2_host, h->chain.ke2Used, h->T * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return TGNH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// thermostat state
+// ------------------------------------------------------------------------------------------------
+extern "C" int tgnh_num_thermostats(const tgnh_handle* h) { return h ? h->T : 0; }
+extern "C" int64_t tgnh_launch_count(const tgnh_handle* h) { return h ? h->launches : 0; }
+
+static int d2h(tgnh_handle* h, void* stream, double* dst, const double* src, size_t n) {
+    if (!h || !dst) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_get_kinetic_energies(tgnh_handle* h, void* stream, double* ke2) { return d2h(h, stream, ke2, h ? h->chain.ke2Used : nullptr, h ? h->T : 0); }
+extern "C" int tgnh_kinetic_energy(tgnh_handle* h, void* stream, double* ke_sum) { return d2h(h, stream, ke_sum, h ? h->chain.keSum : nullptr, 1); }
+extern "C" int tgnh_get_vscale(tgnh_handle* h, void* stream, double* vscale) { return d2h(h, stream, vscale, h ? h->chain.vscale : nullptr, h ? h->T : 0); }
+
+extern "C" int tgnh_compute_kinetic_energies(tgnh_handle* h, void* stream, const void* velm, double* ke2) {
+    if (int rc = check_ptrs(h, velm, nullptr, nullptr, false, false)) return rc;
+    if (!ke2) return fail(TGNH_ERR_INVALID_ARGUMENT, "ke2 is null");
+    if (h->scalePending) return fail(TGNH_ERR_INVALID_ARGUMENT, "a deferred velocity scaling is pending; call tgnh_flush first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->keValid = false;
+    if (int rc = ensure_ke(h, (cudaStream_t)stream, const_cast<void*>(velm), CHAIN_NONE)) return rc;
+    return d2h(h, stream, ke2, h->chain.ke2, h->T);
+}
+
+extern "C" int tgnh_get_chain_state(tgnh_handle* h, void* stream, double* eta, double* eta_dot, double* eta_dot_dot) {
+    if (!h || !eta || !eta_dot || !eta_dot_dot) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t TM = (size_t)h->T * h->M;
+    CUDA_TRY(cudaMemcpyAsync(eta, h->chain.eta, TM * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(eta_dot, h->chain.etaDot, (size_t)h->T * (h->M + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(eta_dot_dot, h->chain.etaDotDot, TM * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_set_chain_state(tgnh_handle* h, void* stream, const double* eta, const double* eta_dot, const double* eta_dot_dot) {
+    if (!h || !eta || !eta_dot || !eta_dot_dot) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t TM = (size_t)h->T * h->M;
+    CUDA_TRY(cudaMemcpyAsync(h->chain.eta, eta, TM * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->chain.etaDot, eta_dot, (size_t)h->T * (h->M + 1) * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->chain.etaDotDot, eta_dot_dot, TM * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_set_profiling(tgnh_handle* h, int enabled) {
+    if (!h) return fail(TGNH_ERR_INVALID_ARGUMENT, "null handle");
+    h->profiling = enabled != 0;
+    h->evUsed = 0;
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_get_profile(tgnh_handle* h, double* ms, int64_t* counts) {
+    if (!h || !ms || !counts) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int k = 0; k < 3; k++) { ms[k] = 0.0; counts[k] = 0; }
+    for (size_t i = 0; i + 1 < h->evUsed; i += 2) {
+        CUDA_TRY(cudaEventSynchronize(h->evPool[i + 1]));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, h->evPool[i], h->evPool[i + 1]));
+        ms[h->evKind[i / 2]] += t;
+        counts[h->evKind[i / 2]]++;
+    }
+    h->evUsed = 0;
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_get_thermostat_params(const tgnh_handle* h, double* dof, double* nkbt, double* eta_mass) {
+    if (!h || !dof || !nkbt || !eta_mass) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    memcpy(dof, h->dof.data(), h->T * 8);
+    memcpy(nkbt, h->nkbt.data(), h->T * 8);
+    memcpy(eta_mass, h->etaMass.data(), (size_t)h->T * h->M * 8);
+    return TGNH_OK;
+}

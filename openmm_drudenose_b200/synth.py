@@ -1,0 +1,273 @@
+"""Deterministic synthetic Drude-polarizable systems (BASELINE.json configs C1-C5).
+
+A system is described the way the reference integrator sees it after
+DrudeTGNHIntegrator::initialize (openmmapi/src/DrudeTGNHIntegrator.cpp:103-160): particle
+masses, the DrudeForce (drude, parent) pairs, per-particle temperature groups and residue
+(molecule) ids.  Random data comes from Philox streams keyed by (seed, chunk of molecules), so
+any contiguous molecule range (a shard) reproduces exactly the same particles.
+
+numpy only; no GPU code here.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+BOLTZ = 1.380649e-23 * 6.02214076e23 / 1000.0      # kJ/mol/K, OpenMM's BOLTZ
+ONE_4PI_EPS0 = 138.935456                          # OpenMM's ONE_4PI_EPS0 (older literal used by the tests' era)
+SEED = 20261018
+_CHUNK = 1 << 16                                    # molecules per Philox stream
+
+
+@dataclass
+class Template:
+    """One molecule type: masses, local (drude, parent) pairs, local geometry offsets (nm)."""
+    name: str
+    masses: np.ndarray
+    pairs: np.ndarray            # [p, 2] local (drude, parent)
+    offsets: np.ndarray          # [k, 3] position of each particle relative to the first
+    constraints: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), np.int32))  # DOF bookkeeping only
+
+    @property
+    def size(self):
+        return len(self.masses)
+
+
+@dataclass
+class DrudeSystem:
+    masses: np.ndarray           # [N] f64
+    pair_drude: np.ndarray       # [P] i32   (pairParticles.x, CudaDrudeTGNHKernels.cpp:147)
+    pair_parent: np.ndarray      # [P] i32   (pairParticles.y)
+    temp_group: np.ndarray       # [N] i32
+    res_id: np.ndarray           # [N] i32
+    positions: np.ndarray        # [N,3] f64 (values representable in f32)
+    velocities: np.ndarray       # [N,3] f64 (values representable in f32)
+    forces: np.ndarray           # [N,3] f64 (values representable in f32)
+    k_spring: np.ndarray         # [P] f64
+    constraints: np.ndarray      # [C,2] i32 (DOF bookkeeping only; never applied)
+    num_temp_groups: int
+    num_residues: int
+    # integrator parameters (DrudeTGNHIntegrator.h:71)
+    temperature: float = 300.0
+    coupling_time: float = 0.1
+    drude_temperature: float = 1.0
+    drude_coupling_time: float = 0.005
+    step_size: float = 0.001
+    drude_steps: int = 20
+    num_nh_chains: int = 3
+    use_drude_nh_chains: bool = True
+    use_com_temp_group: bool = True
+    max_drude_distance: float = 0.02
+
+    @property
+    def num_particles(self):
+        return len(self.masses)
+
+    @property
+    def num_pairs(self):
+        return len(self.pair_drude)
+
+    @property
+    def inv_masses(self):
+        with np.errstate(divide="ignore"):
+            return np.where(self.masses == 0.0, 0.0, 1.0 / np.where(self.masses == 0.0, 1.0, self.masses))
+
+    # ---- boundary layouts (OpenMM single-precision arrays) ----
+    def velm_f32(self):
+        """float4 (vx, vy, vz, 1/m) like cu.getVelm() in single precision."""
+        out = np.zeros((self.num_particles, 4), np.float32)
+        out[:, :3] = self.velocities
+        out[:, 3] = self.inv_masses
+        return out
+
+    def posq_f32(self, charges=None):
+        """float4 (x, y, z, q) like cu.getPosq()."""
+        out = np.zeros((self.num_particles, 4), np.float32)
+        out[:, :3] = self.positions
+        if charges is not None:
+            out[:, 3] = charges
+        return out
+
+    def force_f32_soa(self, padded=None):
+        """float SoA [3, paddedN]: force[i + k*paddedN] (same indexing as cu.getForce(), fp32 instead of int64)."""
+        n = self.num_particles
+        padded = padded or n
+        out = np.zeros((3, padded), np.float32)
+        out[:, :n] = self.forces.T
+        return out
+
+    def force_i64_soa(self, padded=None):
+        """OpenMM's fixed-point force buffer: long long [3, paddedN], scale 2^32 (CudaDrudeTGNHKernels.cpp:295)."""
+        n = self.num_particles
+        padded = padded or n
+        out = np.zeros((3, padded), np.int64)
+        out[:, :n] = np.rint(self.forces.T * 4294967296.0).astype(np.int64)
+        return out
+
+
+def _f32(x):
+    return np.asarray(x, np.float32).astype(np.float64)
+
+
+# ---- molecule templates -------------------------------------------------------------------
+# masses from platforms/cuda/tests/TestCudaDrudeTGNHIntegrator.cpp:132-136; geometry :158-161
+WATER4 = Template("water4", np.array([15.6, 0.4, 1.0, 1.0]), np.array([[1, 0]], np.int32),
+                  np.array([[0, 0, 0], [0, 0, 0], [0.09572, 0, 0], [-0.023999, 0.092663, 0]]))
+SWM4 = Template("swm4", np.array([15.6, 0.4, 1.0, 1.0, 0.0]), np.array([[1, 0]], np.int32),
+                np.array([[0, 0, 0], [0, 0, 0], [0.09572, 0, 0], [-0.023999, 0.092663, 0], [0.0, 0.0247, 0.0]]),
+                np.array([[0, 2], [0, 3], [2, 3]], np.int32))
+SOD = Template("sod", np.array([22.59, 0.4]), np.array([[1, 0]], np.int32), np.zeros((2, 3)))
+CLA = Template("cla", np.array([35.05, 0.4]), np.array([[1, 0]], np.int32), np.zeros((2, 3)))
+
+
+def _ionic_templates():
+    """[BMIM]+ (25 atoms, 10 heavy atoms carrying Drudes -> 35 particles) and [BF4]- (5 atoms, all
+    polarizable -> 10 particles); masses are element masses minus 0.4 for Drude carriers."""
+    heavy = [14.007, 12.011, 14.007, 12.011, 12.011, 12.011, 12.011, 12.011, 12.011, 12.011]
+    masses, pairs = [], []
+    for m in heavy:
+        masses += [m - 0.4, 0.4]
+        pairs.append([len(masses) - 1, len(masses) - 2])
+    masses += [1.008] * 15
+    rng = np.random.Generator(np.random.Philox(key=[SEED, 777]))
+    off = rng.uniform(-0.3, 0.3, (35, 3))
+    for d, p in pairs:
+        off[d] = off[p]
+    bmim = Template("bmim", np.array(masses), np.array(pairs, np.int32), off)
+    am, ap = [], []
+    for m in [10.811, 18.998, 18.998, 18.998, 18.998]:
+        am += [m - 0.4, 0.4]
+        ap.append([len(am) - 1, len(am) - 2])
+    aoff = rng.uniform(-0.14, 0.14, (10, 3))
+    for d, p in ap:
+        aoff[d] = aoff[p]
+    bf4 = Template("bf4", np.array(am), np.array(ap, np.int32), aoff)
+    return bmim, bf4
+
+
+def build(templates, mol_types, mol_groups, num_temp_groups, *, seed=SEED, first_molecule=0,
+          density=33.4, box_molecules=None, drude_sigma=0.005, force_sigma=200.0,
+          k_spring=100000 * 4.184, temperature=300.0, frozen_spring_force=True, **params):
+    """Assemble a system from per-molecule template ids / temperature groups.
+
+    mol_types[j], mol_groups[j] describe global molecule first_molecule + j.  Random data for a
+    molecule depends only on (seed, its global index), never on the shard it is generated in.
+    """
+    mol_types = np.asarray(mol_types, np.int32)
+    mol_groups = np.asarray(mol_groups, np.int32)
+    nmol = len(mol_types)
+    sizes = np.array([t.size for t in templates], np.int64)
+    kmax = int(sizes.max())
+    msize = sizes[mol_types]
+    start = np.concatenate([[0], np.cumsum(msize)])
+    N = int(start[-1])
+
+    # per-particle static tables
+    res_id = np.repeat(np.arange(nmol, dtype=np.int32), msize)
+    local = np.arange(N, dtype=np.int64) - np.repeat(start[:-1], msize)
+    ptype = np.repeat(mol_types, msize)
+    mass_tab = np.zeros((len(templates), kmax)); off_tab = np.zeros((len(templates), kmax, 3))
+    for ti, t in enumerate(templates):
+        mass_tab[ti, :t.size] = t.masses
+        off_tab[ti, :t.size] = t.offsets
+    masses = mass_tab[ptype, local]
+    temp_group = np.repeat(mol_groups, msize).astype(np.int32)
+
+    pd, pp, cons = [], [], []
+    for ti, t in enumerate(templates):
+        sel = np.nonzero(mol_types == ti)[0]
+        if len(sel) == 0:
+            continue
+        base = start[sel]
+        for d, p in t.pairs:
+            pd.append(base + d); pp.append(base + p)
+        for a, b in t.constraints:
+            cons.append(np.stack([base + a, base + b], 1))
+    if pd:
+        pair_drude = np.concatenate(pd); pair_parent = np.concatenate(pp)
+        order = np.argsort(pair_drude, kind="stable")
+        pair_drude = pair_drude[order].astype(np.int32); pair_parent = pair_parent[order].astype(np.int32)
+    else:
+        pair_drude = np.zeros(0, np.int32); pair_parent = np.zeros(0, np.int32)
+    constraints = np.concatenate(cons).astype(np.int32) if cons else np.zeros((0, 2), np.int32)
+
+    # per-molecule random data: one Philox stream per chunk of _CHUNK global molecules
+    total = box_molecules if box_molecules is not None else first_molecule + nmol
+    box = (total / density) ** (1.0 / 3.0)
+    u_center = np.empty((nmol, 3)); n_mol = np.empty((nmol, kmax, 9))
+    g0 = first_molecule
+    j = 0
+    while j < nmol:
+        chunk = (g0 + j) // _CHUNK
+        lo = chunk * _CHUNK
+        cnt = min(nmol - j, lo + _CHUNK - (g0 + j))
+        rng = np.random.Generator(np.random.Philox(key=[seed, chunk]))
+        uc = rng.random((_CHUNK, 3)); nm = rng.standard_normal((_CHUNK, kmax, 9))
+        a = g0 + j - lo
+        u_center[j:j + cnt] = uc[a:a + cnt]; n_mol[j:j + cnt] = nm[a:a + cnt]
+        j += cnt
+    nrm = n_mol[res_id, local]                        # [N, 9]: 0-2 drude displacement, 3-5 velocity, 6-8 force
+
+    positions = u_center[res_id] * box + off_tab[ptype, local]
+    positions[pair_drude] = positions[pair_parent] + drude_sigma * nrm[pair_drude, 0:3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        vsig = np.where(masses > 0, np.sqrt(BOLTZ * temperature / np.where(masses > 0, masses, 1.0)), 0.0)
+    velocities = vsig[:, None] * nrm[:, 3:6]
+    positions = _f32(positions); velocities = _f32(velocities)
+    forces = force_sigma * nrm[:, 6:9]
+    forces[masses == 0] = 0.0
+    ks = np.full(len(pair_drude), float(k_spring))
+    if len(pair_drude):
+        if frozen_spring_force:                       # spring evaluated once at t=0 and frozen
+            fd = -ks[:, None] * (positions[pair_drude] - positions[pair_parent])
+            forces[pair_drude] = fd
+            forces[pair_parent] = -fd
+        else:
+            forces[pair_drude] = 0.0; forces[pair_parent] = 0.0
+    forces = _f32(forces)
+    return DrudeSystem(masses=masses, pair_drude=pair_drude, pair_parent=pair_parent, temp_group=temp_group,
+                       res_id=res_id, positions=positions, velocities=velocities, forces=forces, k_spring=ks,
+                       constraints=constraints, num_temp_groups=int(num_temp_groups), num_residues=nmol,
+                       temperature=temperature, **params)
+
+
+def water_box(num_molecules, num_temp_groups=4, *, first_molecule=0, box_molecules=None, **kw):
+    """C4 / C5: 4-particle molecules [parent 15.6, drude 0.4, a 1.0, b 1.0]; group of molecule k = k mod G."""
+    gidx = np.arange(first_molecule, first_molecule + num_molecules)
+    return build([WATER4], np.zeros(num_molecules, np.int32), gidx % num_temp_groups, num_temp_groups,
+                 first_molecule=first_molecule, box_molecules=box_molecules, **kw)
+
+
+def swm4_box(num_molecules=10000, **kw):
+    """C2: SWM4-NDP waters incl. the massless M site (5 particles), 1 temperature group."""
+    kw.setdefault("num_nh_chains", 1)
+    return build([SWM4], np.zeros(num_molecules, np.int32), np.zeros(num_molecules, np.int32), 1, **kw)
+
+
+def nacl_box(**kw):
+    """C1 (example/nacl_1m_pos.pdb shape): 492 SWM4 waters + 10 Na+ + 10 Cl-, N = 2500, P = 512, G = 2."""
+    types = np.array([0] * 492 + [1] * 10 + [2] * 10, np.int32)
+    groups = np.array([0] * 492 + [1] * 20, np.int32)
+    kw.setdefault("num_nh_chains", 1)
+    kw.setdefault("use_drude_nh_chains", False)
+    return build([SWM4, SOD, CLA], types, groups, 2, **kw)
+
+
+def ionic_liquid(num_ion_pairs=1000, **kw):
+    """C3: [BMIM][BF4]-like, 35 + 10 particles per ion pair, G = 3 (cations, anions, spare solvent group)."""
+    bmim, bf4 = _ionic_templates()
+    types = np.tile(np.array([0, 1], np.int32), num_ion_pairs)
+    kw.setdefault("density", 3.0)
+    return build([bmim, bf4], types, types.copy(), 3, **kw)
+
+
+def single_pair():
+    """The 2-particle system of testSinglePair (platforms/reference/tests/TestReferenceDrudeTGNHIntegrator.cpp:54-109)."""
+    k = ONE_4PI_EPS0 * 1.5
+    return DrudeSystem(masses=np.array([1.0, 0.1]), pair_drude=np.array([1], np.int32), pair_parent=np.array([0], np.int32),
+                       temp_group=np.zeros(2, np.int32), res_id=np.zeros(2, np.int32),
+                       positions=np.array([[0, 0, 0], [0, 0, 0.01]], np.float64),
+                       velocities=np.array([[1, 0, 0], [1, 0, 0.01]], np.float64),
+                       forces=np.zeros((2, 3)), k_spring=np.array([k]), constraints=np.zeros((0, 2), np.int32),
+                       num_temp_groups=1, num_residues=1, temperature=300.0, coupling_time=0.1,
+                       drude_temperature=10.0, drude_coupling_time=0.005, step_size=0.003, drude_steps=20,
+                       num_nh_chains=2, use_drude_nh_chains=False, use_com_temp_group=True, max_drude_distance=0.05)
