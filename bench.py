@@ -35,9 +35,13 @@ ALG_BYTES_HALF2 = 44      # second-half kernel: reads velm, force; writes velm
 C4_MOLECULES = 2_500_000  # x 4 particles = 10M
 C5_MOLECULES = 50_000_000 # x 4 particles = 200M
 
+MOLECULES_OVERRIDE = 0
+
 WORKLOADS = {
     "c4": "C4 synthetic 10M-particle Drude system (2.5M 4-particle molecules, 2.5M Drude pairs), G=4, M=3, S=20, "
           "COM group on, hard wall 0.02 nm, fixed fp32 SoA forces",
+    "c4-wall": "C4 with the frozen-spring pair forces of SURVEY.md 8d: every Drude pair hits the hard wall on every step "
+               "(hard-wall stress case)",
     "c5": "C5 synthetic 200M-particle Drude system sharded over the ranks, G=4",
     "c1": "C1 NaCl 1M box shape, N=2500, G=2", "c2": "C2 SWM4-NDP 10k waters, N=50000, G=1",
     "c3": "C3 [BMIM][BF4]-like 1000 ion pairs, N=45000, G=3",
@@ -88,8 +92,10 @@ class ClockSampler:
 
 
 def make_system(workload, rank, world):
-    if workload == "c4":
-        return synth.water_box(C4_MOLECULES, 4, first_molecule=rank * C4_MOLECULES, box_molecules=world * C4_MOLECULES)
+    if workload in ("c4", "c4-wall"):
+        mol = MOLECULES_OVERRIDE or C4_MOLECULES
+        return synth.water_box(mol, 4, first_molecule=rank * mol, box_molecules=world * mol,
+                               pair_force="frozen_spring" if workload == "c4-wall" else "common")
     if workload == "c5":
         per = C5_MOLECULES // world
         return synth.water_box(per, 4, first_molecule=rank * per, box_molecules=C5_MOLECULES)
@@ -126,7 +132,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     sample_mol = 250_000                       # 1M particles of the C4 generator per step
-    system = synth.water_box(sample_mol, 4, box_molecules=C4_MOLECULES) if args.workload in ("c4", "c5") else make_system(args.workload, 0, 1)
+    system = synth.water_box(sample_mol, 4, box_molecules=C4_MOLECULES) if args.workload in ("c4", "c4-wall", "c5") else make_system(args.workload, 0, 1)
     dt = cpu_run(system, args.steps, args.warmup, cores)
     value = system.num_particles * args.steps / dt
     sample = f"{system.num_particles} particles of the same generator x {args.steps} steps ({dt:.2f} s)"
@@ -212,14 +218,16 @@ def run_ours(args):
 
     # ---- end to end through the C-ABI with HOST buffers: every step copies velm/posq/force in from pinned
     #      memory, runs one step, and copies velm/posq + the 2*KE vector back (tgnh_step_host) ----
-    e2e_steps = max(3, min(args.steps, 10))
-    h.step_host(h_velm.data_ptr(), h_posq.data_ptr(), h_force.data_ptr(), 1)
+    e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 10))
+    ke2 = h.kinetic_energies()
+    if e2e_steps:
+        h.step_host(h_velm.data_ptr(), h_posq.data_ptr(), h_force.data_ptr(), 1)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         ke2 = h.step_host(h_velm.data_ptr(), h_posq.data_ptr(), h_force.data_ptr(), 1)
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max(time.perf_counter() - t0, 1e-9)
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -259,7 +267,7 @@ def run_ours(args):
         # CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same generator, 1 core (the
         # reference platform is serial)
         if world == 1 and not args.no_cpu_baseline:
-            sample_mol = 250_000 if args.workload in ("c4", "c5") else None
+            sample_mol = 250_000 if args.workload in ("c4", "c4-wall", "c5") else None
             sysb = synth.water_box(sample_mol, 4, box_molecules=C4_MOLECULES) if sample_mol else system
             bsteps = 20
             dt = cpu_run(sysb, bsteps, 2, 1)
@@ -280,7 +288,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--molecules", type=int, default=0, help="override molecules per GPU of the c4 generator (profiling runs)")
     args = ap.parse_args()
+    global MOLECULES_OVERRIDE
+    MOLECULES_OVERRIDE = args.molecules
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -132,6 +133,9 @@ struct tgnh_handle {
     // device
     uint32_t* dDesc = nullptr;
     int* dTileStart = nullptr;
+    int* dResStart = nullptr;     // first particle of every residue in particle order, then N (padded to a multiple of 4)
+    int* dTileFirstRes = nullptr; // index into dResStart of each tile's first residue
+    int kindB = KIND_B;           // KIND_BU when every residue lies in one temperature group
     double* dChain = nullptr;     // one allocation holding every ChainView array
     double* dPartials = nullptr;
     unsigned int* dTicket = nullptr;
@@ -171,6 +175,7 @@ static StreamKernel pick(int kind, int ffmt, bool useCOM, bool hardwall) {
     switch (kind) {
         case KIND_A: return ffmt ? pick2<KIND_A, 1>(useCOM, hardwall) : pick2<KIND_A, 0>(useCOM, hardwall);
         case KIND_B: return ffmt ? pick2<KIND_B, 1>(useCOM, false) : pick2<KIND_B, 0>(useCOM, false);
+        case KIND_BU: return ffmt ? pick2<KIND_BU, 1>(useCOM, false) : pick2<KIND_BU, 0>(useCOM, false);
         default: return pick2<KIND_KE, 0>(useCOM, false);
     }
 }
@@ -183,6 +188,9 @@ static int smem_bytes(int kind, int ffmt, bool useCOM, int T) {
         case KIND_B:
             if (ffmt) return useCOM ? SmemLayout<KIND_B, 1, true>::bytes(T) : SmemLayout<KIND_B, 1, false>::bytes(T);
             return useCOM ? SmemLayout<KIND_B, 0, true>::bytes(T) : SmemLayout<KIND_B, 0, false>::bytes(T);
+        case KIND_BU:
+            if (ffmt) return useCOM ? SmemLayout<KIND_BU, 1, true>::bytes(T) : SmemLayout<KIND_BU, 1, false>::bytes(T);
+            return useCOM ? SmemLayout<KIND_BU, 0, true>::bytes(T) : SmemLayout<KIND_BU, 0, false>::bytes(T);
         default:
             return useCOM ? SmemLayout<KIND_KE, 0, true>::bytes(T) : SmemLayout<KIND_KE, 0, false>::bytes(T);
     }
@@ -383,19 +391,36 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         tileStart.push_back(N);
     }
     h->numTiles = (int)tileStart.size() - 1;
+    // residues in particle order (tiles are residue-aligned, so each tile owns a contiguous slice of this list)
+    std::vector<int> resStart, tileFirstRes;
+    {
+        size_t t = 0;
+        for (int i = 0; i < N;) {
+            if (t < tileStart.size() && tileStart[t] == i) { tileFirstRes.push_back((int)resStart.size()); t++; }
+            resStart.push_back(i);
+            i = resLast[p->particle_res_id[i]] + 1;
+        }
+        tileFirstRes.push_back((int)resStart.size());
+        resStart.push_back(N);
+        while (resStart.size() & 3) resStart.push_back(N);
+    }
+    h->kindB = uniform ? KIND_BU : KIND_B;
 
     // ---- device allocations ----
     auto dmalloc = [&](void** ptr, size_t bytes) { return cudaMalloc(ptr, bytes ? bytes : 16) == cudaSuccess; };
     if (!dmalloc((void**)&h->dDesc, desc.size() * 4) || !dmalloc((void**)&h->dTileStart, tileStart.size() * 4) ||
+        !dmalloc((void**)&h->dResStart, resStart.size() * 4) || !dmalloc((void**)&h->dTileFirstRes, tileFirstRes.size() * 4) ||
         !dmalloc((void**)&h->dTicket, 4))
         return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the index tables failed"));
     cudaMemcpy(h->dDesc, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(h->dTileStart, tileStart.data(), tileStart.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->dResStart, resStart.data(), resStart.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->dTileFirstRes, tileFirstRes.data(), tileFirstRes.size() * 4, cudaMemcpyHostToDevice);
     cudaMemset(h->dTicket, 0, 4);
 
-    // chain block: etaMass, eta, etaDot, etaDotDot, nkbt, ke2, ke2Local, ke2Used, pending, scaleA, vscale, keSum
+    // chain block: etaMass, invEtaMass, eta, etaDot, etaDotDot, nkbt, ke2, ke2Local, ke2Used, pending, scaleA, vscale, keSum
     const size_t TM = (size_t)T * M;
-    h->chainDoubles = 3 * TM + (size_t)T * (M + 1) + 7 * T + 1;
+    h->chainDoubles = 4 * TM + (size_t)T * (M + 1) + 7 * T + 1;
     if (!dmalloc((void**)&h->dChain, h->chainDoubles * 8)) return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the chain state failed"));
     std::vector<double> init(h->chainDoubles, 0.0);
     {
@@ -403,8 +428,10 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         ChainView& c = h->chain;
         c.T = T; c.G = G; c.M = M; c.S = h->S; c.useDrudeNH = h->useDrudeNH;
         c.dt = h->dt; c.kT = h->kT; c.kTD = h->kTD;
+        c.dtc = h->dt / h->S;                                         // CudaDrudeTGNHKernels.cpp:440
         size_t o = 0;
         c.etaMass = b + o; memcpy(&init[o], h->etaMass.data(), TM * 8); o += TM;
+        c.invEtaMass = b + o; for (size_t i = 0; i < TM; i++) init[o + i] = h->etaMass[i] != 0.0 ? 1.0 / h->etaMass[i] : 0.0; o += TM;
         c.eta = b + o; o += TM;
         c.etaDot = b + o; o += (size_t)T * (M + 1);
         c.etaDotDot = b + o; memcpy(&init[o], etaDotDot.data(), TM * 8); o += TM;
@@ -421,7 +448,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
     cudaMemcpy(h->dChain, init.data(), h->chainDoubles * 8, cudaMemcpyHostToDevice);
 
     int rc;
-    if ((rc = configure_kernel(h, KIND_A, &h->gridA, &h->smemA)) || (rc = configure_kernel(h, KIND_B, &h->gridB, &h->smemB)) ||
+    if ((rc = configure_kernel(h, KIND_A, &h->gridA, &h->smemA)) || (rc = configure_kernel(h, h->kindB, &h->gridB, &h->smemB)) ||
         (rc = configure_kernel(h, KIND_KE, &h->gridKE, &h->smemKE)))
         return bail(rc);
     int maxGrid = h->gridA > h->gridB ? h->gridA : h->gridB;
@@ -434,7 +461,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
 
 extern "C" void tgnh_destroy(tgnh_handle* h) {
     if (!h) return;
-    cudaFree(h->dDesc); cudaFree(h->dTileStart); cudaFree(h->dChain); cudaFree(h->dPartials); cudaFree(h->dTicket);
+    cudaFree(h->dDesc); cudaFree(h->dTileStart); cudaFree(h->dResStart); cudaFree(h->dTileFirstRes); cudaFree(h->dChain); cudaFree(h->dPartials); cudaFree(h->dTicket);
     cudaFree(h->hsVelm); cudaFree(h->hsPosq); cudaFree(h->hsForce);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     if (h->hsStream) cudaStreamDestroy(h->hsStream);
@@ -454,19 +481,48 @@ static int check_ptrs(const tgnh_handle* h, const void* velm, const void* posq, 
     return TGNH_OK;
 }
 
+// every launch carries the programmatic-stream-serialization attribute: the kernels call
+// griddepcontrol.wait before touching global data, so the next launch's prologue (barrier init, smem
+// clears, residency) overlaps the previous launch's tail instead of paying a full launch gap
+template <typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(Args...), int grid, int block, int smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+static int launch_chain(tgnh_handle* h, cudaStream_t s, int mode) {
+    CUDA_TRY(launch_pdl(tgnh_chain_kernel, 1, 32, 0, s, h->chain, mode));
+    h->launches++;
+    return TGNH_OK;
+}
+
+// one streaming launch; for the reducing kinds (KIND_B / KIND_KE) followed by the all-reduce of the
+// kinetic-energy vector when sharded and by the chain update `chainMode` asks for
 static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, void* posq, const void* force, int applyScale, int chainMode) {
     StreamArgs a;
     a.velm = (float4*)velm; a.posq = (float4*)posq; a.force = force;
     a.desc = h->dDesc; a.tileStart = h->dTileStart; a.numTiles = h->numTiles; a.paddedN = h->paddedN;
+    a.resStart = h->dResStart; a.tileFirstRes = h->dTileFirstRes;
+    const int prof = kind;               // profiling slot (first half / second half / reduce)
+    if (kind == KIND_B) kind = h->kindB;
     a.dt = (float)h->dt;
     a.fscale = (float)(h->ffmt == TGNH_FORCE_I64_SOA ? 0.5 * h->dt / 4294967296.0 : 0.5 * h->dt);   // CudaDrudeTGNHKernels.cpp:295
     a.rmax = (float)h->rmax;
     a.hardwallScale = (float)std::sqrt(h->kTD);                                                       // :299
     a.applyScale = applyScale;
-    a.chainMode = sharded(h) ? CHAIN_NONE : chainMode;
+    a.useLocalKE = sharded(h) ? 1 : 0;
+    a.reverse = (prof == KIND_B) ? 1 : 0;   // first-half and reduce/flush launches walk forward, second-half backward
+    static const int tuneReverse = getenv("TGNH_TUNE_REVERSE") ? atoi(getenv("TGNH_TUNE_REVERSE")) : -1;   // experiments only
+    if (tuneReverse == 0) a.reverse = 0;
+    if (tuneReverse == 2) a.reverse = (prof == KIND_B) ? 0 : 1;
     a.partials = h->dPartials; a.ticket = h->dTicket; a.chain = h->chain;
-    const int grid = kind == KIND_A ? h->gridA : kind == KIND_B ? h->gridB : h->gridKE;
-    const int smem = kind == KIND_A ? h->smemA : kind == KIND_B ? h->smemB : h->smemKE;
+    const int grid = prof == KIND_A ? h->gridA : prof == KIND_B ? h->gridB : h->gridKE;
+    const int smem = prof == KIND_A ? h->smemA : prof == KIND_B ? h->smemB : h->smemKE;
     StreamKernel k = pick(kind, h->ffmt, h->useCOM, h->hardwall);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
@@ -478,30 +534,17 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
         }
         e0 = h->evPool[h->evUsed]; e1 = h->evPool[h->evUsed + 1];
         h->evKind.resize(h->evUsed / 2 + 1);
-        h->evKind[h->evUsed / 2] = kind;
+        h->evKind[h->evUsed / 2] = prof;
         h->evUsed += 2;
         CUDA_TRY(cudaEventRecord(e0, s));
     }
-    k<<<grid, TILE, smem, s>>>(a);
+    CUDA_TRY(launch_pdl(k, grid, TILE, smem, s, (const StreamArgs)a));
     if (e1) CUDA_TRY(cudaEventRecord(e1, s));
     h->launches++;
-    CUDA_TRY(cudaGetLastError());
-    if (kind != KIND_A && sharded(h)) {
-        // the only collective on the path: double[G+2] kinetic-energy vector over NVLink
+    if (prof == KIND_A) return TGNH_OK;
+    if (sharded(h))   // the only collective on the path: double[G+2] kinetic-energy vector over NVLink
         NCCL_TRY(g_nccl.AllReduce(h->chain.ke2Local, h->chain.ke2, h->T, ncclDouble, ncclSum, h->comm->comm, s));
-        if (chainMode != CHAIN_NONE) {
-            tgnh_chain_kernel<<<1, 32, 0, s>>>(h->chain, chainMode);
-            h->launches++;
-            CUDA_TRY(cudaGetLastError());
-        }
-    }
-    return TGNH_OK;
-}
-
-static int launch_chain(tgnh_handle* h, cudaStream_t s, int mode) {
-    tgnh_chain_kernel<<<1, 32, 0, s>>>(h->chain, mode);
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
+    if (chainMode != CHAIN_NONE) return launch_chain(h, s, chainMode);
     return TGNH_OK;
 }
 

@@ -43,6 +43,20 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Departure counter of a pipeline stage (relaxed shared-memory atomic).  No fence is needed for the refill that
+// follows the last departure: SMs issue in order and an instruction issues only once its source registers
+// are ready, so every shared-memory load of the stage whose value is consumed before this atomic (all of
+// them: nothing but accumulators is carried across tiles) has returned its data by the time the atomic
+// issues, i.e. long before the TMA write of the next tile can land.  (A release/acquire atomic here makes
+// every warp wait for its outstanding global stores: measured +13 % on the second-half kernel.)
+__device__ __forceinline__ uint32_t atom_add_shared(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -64,6 +78,15 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// asynchronous prefetch of a contiguous range into L2 (no register or shared-memory footprint)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // global -> shared bulk copy; completion is signalled on `bar` as transaction bytes (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
     asm volatile(
@@ -76,6 +99,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void st_stream(float4* p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// 128-bit store with the default L2 policy (velm: re-read by the next launch, see "L2 hand-over")
+__device__ __forceinline__ void st_global(float4* p, float4 v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // programmatic dependent launch
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -85,7 +112,9 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 struct ChainView {
     int T, G, M, S, useDrudeNH;
     double dt, kT, kTD;
+    double dtc;         // dt / S
     double* etaMass;    // [T][M]
+    double* invEtaMass; // [T][M]   1 / etaMass (0 where the mass is 0)
     double* eta;        // [T][M]
     double* etaDot;     // [T][M+1]   last column: permanent 0 (CudaDrudeTGNHKernels.cpp:96,252)
     double* etaDotDot;  // [T][M]
@@ -100,7 +129,7 @@ struct ChainView {
 };
 
 enum ChainMode {
-    CHAIN_NONE = 0,        // reduction only (sharded runs: all-reduce first, chain in its own launch)
+    CHAIN_NONE = 0,        // no chain update
     CHAIN_FIRST = 1,       // first half-step of a step: consumes pending^2 * ke2, scaleA = pending * s
     CHAIN_SECOND = 2,      // second half-step: consumes ke2, pending = s, scaleA = s
     CHAIN_SECOND_FIRST = 3 // second half-step immediately followed by the next step's first half-step
@@ -110,105 +139,208 @@ enum ChainMode {
 // polynomial is exact to < 0.25 ulp before the final rounding, which puts it in the same <= 1 ulp
 // class as CUDA's exp() and glibc's, at a fraction of the dependent-instruction depth.  The chain is
 // strictly serial (40 updates x ~3 dependent exps per step) and sits between two streaming kernels,
-// so its latency is directly visible in the step time.
-__device__ __forceinline__ double chain_exp(double x) {
-    if (fabs(x) <= 0.03125) {
-        const double x2 = x * x;
-        // Estrin: pairs of terms, then powers of x^2
-        const double p01 = 1.0 + x;
-        const double p23 = fma(x, 1.0 / 6.0, 0.5);
-        const double p45 = fma(x, 1.0 / 120.0, 1.0 / 24.0);
-        const double p67 = fma(x, 1.0 / 5040.0, 1.0 / 720.0);
-        const double p89 = fma(x, 1.0 / 362880.0, 1.0 / 40320.0);
-        const double x4 = x2 * x2;
-        const double q0 = fma(p23, x2, p01);
-        const double q1 = fma(p67, x2, p45);
-        const double x8 = x4 * x4;
-        return fma(p89, x8, fma(q1, x4, q0));
+// so its latency is directly visible in the step time.  FAST = false is the library exp().
+// Full-range exp with a short dependency chain (~11 levels against ~20 for the library's Horner form):
+// Cody-Waite reduction x = k ln2 + r, |r| <= 0.347, degree-13 Taylor polynomial in Estrin form (truncation
+// 4e-18), scaling by 2^k through the exponent field.  <= 2 ulp; results below the normal range flush to 0.
+__device__ __forceinline__ double exp_full(double x) {
+    const double MAGIC = 6755399441055744.0;                  // 1.5 * 2^52: rounds to nearest integer
+    const double t = fma(x, 1.4426950408889634, MAGIC);
+    const int k = __double2loint(t);
+    const double kd = t - MAGIC;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    const double r2 = r * r;
+    const double p01 = 1.0 + r;
+    const double p23 = fma(r, 1.0 / 6.0, 0.5);
+    const double p45 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    const double p67 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+    const double p89 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+    const double pab = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+    const double pcd = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+    const double r4 = r2 * r2;
+    const double q0 = fma(p23, r2, p01), q1 = fma(p67, r2, p45), q2 = fma(pab, r2, p89);
+    const double r8 = r4 * r4;
+    const double s0 = fma(q1, r4, q0), s1 = fma(pcd, r4, q2);
+    const double p = fma(s1, r8, s0);
+    const int kc = max(-1022, min(1023, k));
+    double y = p * __hiloint2double((kc + 1023) << 20, 0);
+    if (x < -708.0) y = 0.0;
+    if (x > 709.7) y = __longlong_as_double(0x7ff0000000000000LL);
+    return y;
+}
+
+// exp(x) for the chain.  |x| is ~1e-3 here (dtc/8 * etaDot) when the thermostats are near equilibrium; for
+// |x| <= 2^-5 a degree-9 Taylor polynomial is exact to < 0.25 ulp before the final rounding, which puts it in
+// the same <= 1 ulp class as CUDA's exp() and glibc's at a fraction of the dependent-instruction depth.  The
+// chain is strictly serial (40 sub-steps x ~4 dependent exps per step) and sits between two streaming kernels,
+// so its latency is directly visible in the step time.  FAST = false is the full-range version.
+template <bool FAST>
+__device__ __forceinline__ double chain_exp(double x, bool& outOfRange) {
+    if (!FAST) return exp_full(x);
+    outOfRange |= fabs(x) > 0.03125;
+    const double x2 = x * x;
+    // Estrin: pairs of terms, then powers of x^2
+    const double p01 = 1.0 + x;
+    const double p23 = fma(x, 1.0 / 6.0, 0.5);
+    const double p45 = fma(x, 1.0 / 120.0, 1.0 / 24.0);
+    const double p67 = fma(x, 1.0 / 5040.0, 1.0 / 720.0);
+    const double p89 = fma(x, 1.0 / 362880.0, 1.0 / 40320.0);
+    const double x4 = x2 * x2;
+    const double q0 = fma(p23, x2, p01);
+    const double q1 = fma(p67, x2, p45);
+    const double x8 = x4 * x4;
+    return fma(p89, x8, fma(q1, x4, q0));
+}
+
+struct ChainConst {
+    double dtc, dtc2, dtc4, dtc8, kTl, nkbt, invQ0;
+    bool live;
+};
+
+// One of the S sub-steps of a thermostat's half-step update (the body of the `iter` loops at
+// CudaDrudeTGNHKernels.cpp:565-593 / :606-642).  Returns false when the FAST polynomial left its range.
+template <int NL, bool FAST>
+__device__ __forceinline__ bool chain_substep(const ChainConst& k, const double (&Q)[NL], const double (&invQ)[NL], double (&eta)[NL],
+                                              double (&ed)[NL], double (&edd)[NL], double (&ef)[NL], double& ke, double& scale) {
+    bool bad = false;
+#pragma unroll
+    for (int i = NL - 1; i >= 0; i--) {
+        if (i < NL - 1) ef[i] = chain_exp<FAST>(-k.dtc8 * ed[i + 1], bad);
+        ed[i] *= ef[i]; ed[i] += edd[i] * k.dtc4; ed[i] *= ef[i];
     }
-    return exp(x);
+    scale *= chain_exp<FAST>(-k.dtc2 * ed[0], bad);
+    ke *= chain_exp<FAST>(-k.dtc * ed[0], bad);
+#pragma unroll
+    for (int i = 0; i < NL; i++) eta[i] += k.dtc2 * ed[i];
+    if (k.live) edd[0] = (ke - k.nkbt) * k.invQ0;
+    ed[0] *= ef[0]; ed[0] += edd[0] * k.dtc4; ed[0] *= ef[0];
+#pragma unroll
+    for (int i = 1; i < NL; i++) {
+        ed[i] *= ef[i];
+        edd[i] = (Q[i - 1] * ed[i - 1] * ed[i - 1] - k.kTl) * invQ[i];
+        ed[i] += edd[i] * k.dtc4; ed[i] *= ef[i];
+    }
+    return !bad;
 }
 
 // One thermostat's half-step chain update; restates CudaDrudeTGNHKernels.cpp:560-595 (relative and COM
 // groups) and :597-642 (Drude group) as one loop nest: the Drude group differs only in the number of
 // live links (1 unless useDrudeNHChains) and in kT.  Returns the velocity scale factor.
+//
+// Same arithmetic as the reference with latency cuts that do not change any value beyond the last ulp:
+//   * the factor exp(-dtc/8 * etaDot[top+1]) of the top live link is loop-invariant (etaDot[M] is the
+//     permanent zero) and computed once;
+//   * the second (upward) sweep re-evaluates exp(-dtc/8 * etaDot[i+1]) on values the first sweep left
+//     unchanged, so the first sweep's factors are reused (":583" already reuses a stale expfac this way);
+//   * divisions by the constant thermostat masses become multiplications by their reciprocals;
+//   * every sub-step first runs branch-free with the small-argument exp polynomial; only if an argument
+//     left the polynomial's range is the sub-step redone from the saved state with the full-range exp_full().
 // Deviation (documented in DESIGN.md): the Q0 > 0 guard of :561 is applied to the Drude group too, so a
 // system without Drude pairs yields scale 1 instead of NaN.
-template <int MC>  // MC > 0: chain length known at compile time (registers); MC == 0: runtime M <= MAX_M
-__device__ double chain_update(const ChainView& c, int g, double ke) {
-    constexpr int CAP = MC > 0 ? MC : MAX_M;
-    const int M = MC > 0 ? MC : c.M;
+template <int NL>  // live links, known at compile time so that the state sits in registers
+__device__ __forceinline__ double chain_update(const ChainView& c, int g, double ke) {
+    const int M = c.M;
     const bool isDrude = (g == c.T - 1);
-    const int nl = (isDrude && !c.useDrudeNH) ? 1 : M;
-    const double kTl = isDrude ? c.kTD : c.kT;
-    const double dtc = c.dt / c.S, dtc2 = dtc / 2.0, dtc4 = dtc / 4.0, dtc8 = dtc / 8.0;
-    double Q[CAP], invQ[CAP], eta[CAP], ed[CAP + 1], edd[CAP];
+    ChainConst k;
+    k.dtc = c.dtc; k.dtc2 = k.dtc / 2.0; k.dtc4 = k.dtc / 4.0; k.dtc8 = k.dtc / 8.0;
+    k.kTl = isDrude ? c.kTD : c.kT;
+    k.nkbt = c.nkbt[g];
+    double Q[NL], invQ[NL], eta[NL], ed[NL], edd[NL], ef[NL];
 #pragma unroll
-    for (int i = 0; i < CAP; i++) {
-        invQ[i] = 1.0;
-        if (i < M) {
-            Q[i] = c.etaMass[g * M + i];
-            invQ[i] = 1.0 / Q[i];
-            eta[i] = c.eta[g * M + i];
-            ed[i] = c.etaDot[g * (M + 1) + i];
-            edd[i] = c.etaDotDot[g * M + i];
-        } else {
-            Q[i] = 1.0; eta[i] = 0.0; ed[i] = 0.0; edd[i] = 0.0;
-        }
+    for (int i = 0; i < NL; i++) {
+        Q[i] = c.etaMass[g * M + i];
+        invQ[i] = c.invEtaMass[g * M + i];
+        eta[i] = c.eta[g * M + i];
+        ed[i] = c.etaDot[g * (M + 1) + i];
+        edd[i] = c.etaDotDot[g * M + i];
+        ef[i] = 1.0;
     }
-    ed[CAP] = 0.0;
-    // ed[M] is the permanent zero; for a Drude group without chains ed[1] may hold user-set state
-    const double edTop = c.etaDot[g * (M + 1) + nl];
+    // etaDot[M] is the permanent zero; for a Drude group without chains etaDot[1] may hold user-set state
+    ef[NL - 1] = exp(-k.dtc8 * c.etaDot[g * (M + 1) + NL]);
+    k.live = Q[0] > 0;
+    k.invQ0 = k.live ? invQ[0] : 0.0;
+    double scale = 1.0;
+    if (k.live) edd[0] = (ke - k.nkbt) * k.invQ0;
+    // The lanes of the warp run in lockstep, so a lane that needs the full-range exp makes everybody pay for it:
+    // the choice is therefore made once for all converged lanes and is sticky for the rest of this update.
+    bool full = false;
+    for (int iter = 0; iter < c.S; iter++) {
+        if (!full) {
+            double eta0[NL], ed0[NL], edd0[NL], ef0[NL];
+            const double ke0 = ke, scale0 = scale;
+#pragma unroll
+            for (int i = 0; i < NL; i++) { eta0[i] = eta[i]; ed0[i] = ed[i]; edd0[i] = edd[i]; ef0[i] = ef[i]; }
+            const bool ok = chain_substep<NL, true>(k, Q, invQ, eta, ed, edd, ef, ke, scale);
+            full = __any_sync(__activemask(), !ok);
+            if (!full) continue;
+#pragma unroll
+            for (int i = 0; i < NL; i++) { eta[i] = eta0[i]; ed[i] = ed0[i]; edd[i] = edd0[i]; ef[i] = ef0[i]; }
+            ke = ke0; scale = scale0;
+        }
+        chain_substep<NL, false>(k, Q, invQ, eta, ed, edd, ef, ke, scale);
+    }
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+        c.eta[g * M + i] = eta[i];
+        c.etaDot[g * (M + 1) + i] = ed[i];
+        c.etaDotDot[g * M + i] = edd[i];
+    }
+    return scale;
+}
+
+// runtime chain length (M > 4): same algorithm on local arrays, library exp
+__device__ __noinline__ double chain_update_generic(const ChainView& c, int g, double ke, int nl) {
+    const int M = c.M;
+    const bool isDrude = (g == c.T - 1);
+    const double kTl = isDrude ? c.kTD : c.kT;
+    const double dtc = c.dtc, dtc2 = dtc / 2.0, dtc4 = dtc / 4.0, dtc8 = dtc / 8.0;
+    double Q[MAX_M], invQ[MAX_M], eta[MAX_M], ed[MAX_M], edd[MAX_M], ef[MAX_M];
+    for (int i = 0; i < nl; i++) {
+        Q[i] = c.etaMass[g * M + i];
+        invQ[i] = c.invEtaMass[g * M + i];
+        eta[i] = c.eta[g * M + i];
+        ed[i] = c.etaDot[g * (M + 1) + i];
+        edd[i] = c.etaDotDot[g * M + i];
+    }
+    ef[nl - 1] = exp(-dtc8 * c.etaDot[g * (M + 1) + nl]);
     const double nkbt = c.nkbt[g];
     const bool live = Q[0] > 0;
-    const double invQ0 = live ? 1.0 / Q[0] : 0.0;
-    double scale = 1.0, ef = 1.0;
+    const double invQ0 = live ? invQ[0] : 0.0;
+    double scale = 1.0;
     if (live) edd[0] = (ke - nkbt) * invQ0;
     for (int iter = 0; iter < c.S; iter++) {
-#pragma unroll
-        for (int i = CAP - 1; i >= 0; i--) {
-            if (i < nl) {
-                const double up = (i == nl - 1) ? edTop : ed[i + 1];
-                ef = chain_exp(-dtc8 * up);
-                ed[i] *= ef; ed[i] += edd[i] * dtc4; ed[i] *= ef;
-            }
+        for (int i = nl - 1; i >= 0; i--) {
+            if (i < nl - 1) ef[i] = exp(-dtc8 * ed[i + 1]);
+            ed[i] *= ef[i]; ed[i] += edd[i] * dtc4; ed[i] *= ef[i];
         }
-        scale *= chain_exp(-dtc2 * ed[0]);
-        ke *= chain_exp(-dtc * ed[0]);
-#pragma unroll
-        for (int i = 0; i < CAP; i++)
-            if (i < nl) eta[i] += dtc2 * ed[i];
+        scale *= exp(-dtc2 * ed[0]);
+        ke *= exp(-dtc * ed[0]);
+        for (int i = 0; i < nl; i++) eta[i] += dtc2 * ed[i];
         if (live) edd[0] = (ke - nkbt) * invQ0;
-        ed[0] *= ef; ed[0] += edd[0] * dtc4; ed[0] *= ef;
-#pragma unroll
-        for (int i = 1; i < CAP; i++) {
-            if (i < nl) {
-                const double up = (i == nl - 1) ? edTop : ed[i + 1];
-                ef = chain_exp(-dtc8 * up);
-                ed[i] *= ef;
-                edd[i] = (Q[i - 1] * ed[i - 1] * ed[i - 1] - kTl) * invQ[i];
-                ed[i] += edd[i] * dtc4; ed[i] *= ef;
-            }
+        ed[0] *= ef[0]; ed[0] += edd[0] * dtc4; ed[0] *= ef[0];
+        for (int i = 1; i < nl; i++) {
+            ed[i] *= ef[i];
+            edd[i] = (Q[i - 1] * ed[i - 1] * ed[i - 1] - kTl) * invQ[i];
+            ed[i] += edd[i] * dtc4; ed[i] *= ef[i];
         }
     }
-#pragma unroll
-    for (int i = 0; i < CAP; i++) {
-        if (i < M) {
-            c.eta[g * M + i] = eta[i];
-            c.etaDot[g * (M + 1) + i] = ed[i];
-            c.etaDotDot[g * M + i] = edd[i];
-        }
+    for (int i = 0; i < nl; i++) {
+        c.eta[g * M + i] = eta[i];
+        c.etaDot[g * (M + 1) + i] = ed[i];
+        c.etaDotDot[g * M + i] = edd[i];
     }
     return scale;
 }
 
 __device__ __forceinline__ double chain_update_any(const ChainView& c, int g, double ke) {
-    switch (c.M) {
+    const int nl = (g == c.T - 1 && !c.useDrudeNH) ? 1 : c.M;
+    switch (nl) {
         case 1: return chain_update<1>(c, g, ke);
         case 2: return chain_update<2>(c, g, ke);
         case 3: return chain_update<3>(c, g, ke);
         case 4: return chain_update<4>(c, g, ke);
-        default: return chain_update<0>(c, g, ke);
+        default: return chain_update_generic(c, g, ke, nl);
     }
 }
 

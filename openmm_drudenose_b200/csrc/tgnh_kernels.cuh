@@ -4,24 +4,40 @@
 //                            integrateDrudeTGNHPositions + applyHardWallConstraints
 //                            (platforms/cuda/src/kernels/drudeTGNH.cu:249-301, 307-365, 435-466, 471-574)
 //   KIND_B  (second half)  = integrateDrudeTGNHVelocities + calcCOMVelocities + normalizeVelocities +
-//                            computeNormalizedKineticEnergies + sumNormalizedKineticEnergies + the chain
-//                            (drudeTGNH.cu:307-365, 82-133, 138-242; CudaDrudeTGNHKernels.cpp:559-642)
+//                            computeNormalizedKineticEnergies + sumNormalizedKineticEnergies
+//                            (drudeTGNH.cu:307-365, 82-133, 138-242)
+//   KIND_BU                = KIND_B for systems whose residues each lie in ONE temperature group (the normal
+//                            case): sum_u m_u |v_u - V|^2 = sum_u m_u |v_u|^2 - M |V|^2 per residue, so particles
+//                            never need their residue's COM velocity; one thread per RESIDUE (densely packed
+//                            lanes instead of every member redoing the residue sum) adds the M |V|^2 terms
 //   KIND_KE (reduce/flush) = the kinetic-energy reduction alone, optionally applying a pending scaling
 //                            (drudeTGNH.cu:82-242, 249-301)
 //
 // Data movement: every CTA is persistent and walks residue-aligned tiles of <= 512 consecutive
 // particles.  One elected thread streams each tile's velm / posq / force / descriptor slices into a
-// ring of shared-memory stages with cp.async.bulk (TMA) completing on an mbarrier; thread i owns
-// particle i of the tile, reads its pair partner and its residue's momenta out of shared memory
+// ring of shared-memory stages with cp.async.bulk (TMA) completing on a "full" mbarrier; warps hand a
+// stage back through an "empty" mbarrier, so no CTA-wide barrier sits on the streaming path.  Thread i
+// owns particle i of the tile, reads its pair partner and its residue's members out of shared memory
 // (that is where pair / residue indexing would break coalescing), and writes its own float4 results
 // straight back with fully coalesced 128-bit stores.  No temporary arrays (normVelm, comVelm,
 // posDelta, kineticEnergyBuffer of the reference) ever touch HBM.
+//
+// Arithmetic: the reference transforms each Drude pair to (centre of mass, relative) coordinates and
+// back in every kernel.  Algebraically, with f_j = m_j / (m_i + m_j) and rel = v_j - v_i,
+//     scaling:  v_i <- sT (v_i - V) + sCOM V + (sT - sDrude) f_j rel        (drudeTGNH.cu:270-300)
+//     kick:     v_i <- v_i + fscale w_i F_i                                 (drudeTGNH.cu:330-364; the cm/rel
+//                                                                            form reduces to the direct kick)
+// which holds for both members of a pair and, with "partner = self" (rel = 0), for ordinary particles:
+// one branch-free code path, and no (f_i + f_j != 1) round-trip error in fp32.
 #pragma once
 #include "tgnh_device.cuh"
 
 namespace tgnh {
 
-enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2 };
+enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2, KIND_BU = 3 };
+constexpr int NWARPS = TILE / 32;
+constexpr int PF_DIST = 0;         // L2 prefetch distance in tiles (per CTA), 0 = off
+constexpr int TLIST_CAP = 128;     // tile bounds cached in shared memory per CTA (later tiles are looked up in global memory)
 
 struct StreamArgs {
     float4* velm;
@@ -29,6 +45,8 @@ struct StreamArgs {
     const void* force;        // SoA [3][paddedN], float or long long
     const uint32_t* desc;     // [roundup4(N)]
     const int* tileStart;     // [numTiles + 1]
+    const int* resStart;      // [R + 1] first particle of every residue in particle order, then N   (KIND_BU)
+    const int* tileFirstRes;  // [numTiles + 1] index into resStart of each tile's first residue      (KIND_BU)
     int numTiles;
     int paddedN;
     float dt;                 // step size
@@ -36,7 +54,8 @@ struct StreamArgs {
     float rmax;               // maxDrudeDistance
     float hardwallScale;      // sqrt(kB * T_drude)
     int applyScale;           // KIND_KE: scale velocities by scaleA and write them back
-    int chainMode;            // ChainMode run by the last CTA to finish (KIND_B / KIND_KE)
+    int useLocalKE;           // sharded: reduce into chain.ke2Local (all-reduced into ke2 afterwards)
+    int reverse;              // walk the tiles from the last to the first (see "L2 hand-over" below)
     double* partials;         // [gridDim.x][T]
     unsigned int* ticket;     // last-CTA-done counter (self-resetting)
     ChainView chain;
@@ -51,7 +70,10 @@ struct StageLayout {
     static constexpr int OFF_X = OFF_V + TILE * 16;
     static constexpr int OFF_F = OFF_X + (HAS_X ? TILE * 16 : 0);
     static constexpr int OFF_D = OFF_F + (HAS_F ? 3 * PADW * FBYTES : 0);
-    static constexpr int BYTES = OFF_D + PADW * 4;
+    static constexpr bool HAS_R = (KIND == KIND_BU);
+    static constexpr int OFF_R = OFF_D + PADW * 4;              // residue starts of the tile (KIND_BU)
+    static constexpr int OFF_HDR = OFF_R + (HAS_R ? PADW * 4 : 0);   // int4 {first particle, count, first residue, residues}
+    static constexpr int BYTES = OFF_HDR + 16;
 };
 
 template <int KIND, int FFMT, bool USE_COM>
@@ -59,9 +81,9 @@ struct SmemLayout {
     using Stage = StageLayout<KIND, FFMT>;
     static constexpr bool HAS_KE = (KIND != KIND_A);
     static constexpr int NSTAGE = (KIND == KIND_A) ? 3 : 4;
-    static constexpr int OFF_MOM = NSTAGE * Stage::BYTES;
-    static constexpr int OFF_BAR = OFF_MOM + (USE_COM ? TILE * 16 : 0);
-    static constexpr int OFF_SCALE = OFF_BAR + 64;                // float[MAX_T]
+    static constexpr int OFF_BAR = NSTAGE * Stage::BYTES;         // full[NS], empty[NS] mbarriers
+    static constexpr int OFF_TLIST = OFF_BAR + 128;               // int4[TLIST_CAP] bounds of this CTA's first tiles
+    static constexpr int OFF_SCALE = OFF_TLIST + TLIST_CAP * 16;  // float[MAX_T]
     static constexpr int OFF_MISC = OFF_SCALE + MAX_T * 4;        // int[4]
     static constexpr int OFF_WARP = OFF_MISC + 16;                // double[T][16]   (HAS_KE)
     static constexpr int OFF_KE = OFF_WARP + (HAS_KE ? MAX_T * 16 * 8 : 0);
@@ -69,49 +91,61 @@ struct SmemLayout {
 };
 
 template <int FFMT>
-__device__ __forceinline__ float load_force(const unsigned char* sF, int comp, int idx) {
-    if (FFMT == 1) return (float)reinterpret_cast<const long long*>(sF)[comp * PADW + idx];
-    return reinterpret_cast<const float*>(sF)[comp * PADW + idx];
+__device__ __forceinline__ float3 load_force3(const unsigned char* sF, int idx) {
+    if (FFMT == 1) {
+        const long long* f = reinterpret_cast<const long long*>(sF);
+        return make_float3((float)f[idx], (float)f[PADW + idx], (float)f[2 * PADW + idx]);
+    }
+    const float* f = reinterpret_cast<const float*>(sF);
+    return make_float3(f[idx], f[PADW + idx], f[2 * PADW + idx]);
 }
 
-struct PairOut { float3 v1, v2; };
+// approximate reciprocal / rsqrt: 1 MUFU each, <= 1 ulp-class error; exact IEEE division would cost ~10
+// instructions plus a divergent slow path in kernels that are issue-bound, not DRAM-bound, without it
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
-// applyHardWallConstraints (drudeTGNH.cu:487-572).  1 = Drude particle, 2 = parent.  `delta` is x1 - x2.
-__device__ __forceinline__ void hard_wall(float3 delta, float3& x1, float3& x2, float3& v1, float3& v2, float w1, float w2,
-                                          float rmax, float hardwallScale, float dt, bool& moved) {
-    const float r2 = delta.x * delta.x + delta.y * delta.y + delta.z * delta.z;
-    moved = false;
-    if (!(r2 > rmax * rmax)) return;      // rInv*maxDrudeDistance < 1  <=>  r > rmax
-    moved = true;
-    const float r = sqrtf(r2);
-    const float rInv = 1.0f / r;
+// applyHardWallConstraints (drudeTGNH.cu:487-572) for one pair that is beyond the wall.
+// 1 = Drude particle, 2 = parent.  `delta` is x1 - x2, r2 its squared length.
+__device__ __forceinline__ void hard_wall(float3 delta, float r2, float3& x1, float3& x2, float3& v1, float3& v2, float w1, float w2,
+                                       float rmax, float hardwallScale, float dt) {
+    const float rInv = rsqrt_fast(r2);
+    const float r = r2 * rInv;
     const float3 bondDir = make_float3(delta.x * rInv, delta.y * rInv, delta.z * rInv);
-    const float mass1 = 1.0f / w1;
+    const float mass1 = rcp_fast(w1);
     const float deltaR = r - rmax;
     float deltaT = dt;
     float dotvr1 = v1.x * bondDir.x + v1.y * bondDir.y + v1.z * bondDir.z;
     const float3 vp1 = make_float3(v1.x - bondDir.x * dotvr1, v1.y - bondDir.y * dotvr1, v1.z - bondDir.z * dotvr1);
+    const float vBond = hardwallScale * sqrtf(w1);                    // hardwallscaleDrude / SQRT(mass1)
     if (w2 == 0.0f) {
         // massless parent: only the Drude particle moves (:504-526)
-        if (dotvr1 != 0.0f) deltaT = deltaR / fabsf(dotvr1);
+        if (dotvr1 != 0.0f) deltaT = __fdividef(deltaR, fabsf(dotvr1));
         if (deltaT > dt) deltaT = dt;
-        dotvr1 = -dotvr1 * hardwallScale / (fabsf(dotvr1) * sqrtf(mass1));
+        dotvr1 = -copysignf(vBond, dotvr1);                           // -dotvr1*scale/(|dotvr1|*sqrt(m1))
         const float dr = -deltaR + deltaT * dotvr1;
         x1.x += bondDir.x * dr; x1.y += bondDir.y * dr; x1.z += bondDir.z * dr;
         v1 = make_float3(vp1.x + bondDir.x * dotvr1, vp1.y + bondDir.y * dotvr1, vp1.z + bondDir.z * dotvr1);
     } else {
-        const float mass2 = 1.0f / w2;
-        const float invTotalMass = 1.0f / (mass1 + mass2);
+        const float mass2 = rcp_fast(w2);
+        const float invTotalMass = rcp_fast(mass1 + mass2);
         float dotvr2 = v2.x * bondDir.x + v2.y * bondDir.y + v2.z * bondDir.z;
         const float3 vp2 = make_float3(v2.x - bondDir.x * dotvr2, v2.y - bondDir.y * dotvr2, v2.z - bondDir.z * dotvr2);
         const float vbCMass = (mass1 * dotvr1 + mass2 * dotvr2) * invTotalMass;
         dotvr1 -= vbCMass;
         dotvr2 -= vbCMass;
-        if (dotvr1 != dotvr2) deltaT = deltaR / fabsf(dotvr1 - dotvr2);
+        if (dotvr1 != dotvr2) deltaT = __fdividef(deltaR, fabsf(dotvr1 - dotvr2));
         if (deltaT > dt) deltaT = dt;
-        const float vBond = hardwallScale / sqrtf(mass1);
-        dotvr1 = -dotvr1 * vBond * mass2 * invTotalMass / fabsf(dotvr1);
-        dotvr2 = -dotvr2 * vBond * mass1 * invTotalMass / fabsf(dotvr2);
+        dotvr1 = -copysignf(vBond * mass2 * invTotalMass, dotvr1);    // :542  (-dotvr1*vBond*m2/M/|dotvr1|)
+        dotvr2 = -copysignf(vBond * mass1 * invTotalMass, dotvr2);    // :543
         const float dr1 = -deltaR * mass2 * invTotalMass + deltaT * dotvr1;
         const float dr2 = deltaR * mass1 * invTotalMass + deltaT * dotvr2;
         dotvr1 += vbCMass;
@@ -123,254 +157,272 @@ __device__ __forceinline__ void hard_wall(float3 delta, float3& x1, float3& x2, 
     }
 }
 
-__device__ __forceinline__ double sq3(float x, float y, float z) {
-    const double dx = x, dy = y, dz = z;
-    return fma(dx, dx, fma(dy, dy, dz * dz));
+__device__ __forceinline__ float dot3(float3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+
+// sT*r + sCOM*V + c*rel with a fixed evaluation order, so that the two threads of a Drude pair compute
+// bit-identical values for each other's particle (both must take the same side of the hard-wall test)
+__device__ __forceinline__ float3 scaled_velocity(float sT, float3 r, float sCOM, float3 V, float c, float3 rel) {
+    return make_float3(fmaf(c, rel.x, fmaf(sT, r.x, sCOM * V.x)), fmaf(c, rel.y, fmaf(sT, r.y, sCOM * V.y)),
+                       fmaf(c, rel.z, fmaf(sT, r.z, sCOM * V.z)));
+}
+__device__ __forceinline__ float3 kicked(float3 v, float fw, float3 F) {
+    return make_float3(fmaf(fw, F.x, v.x), fmaf(fw, F.y, v.y), fmaf(fw, F.z, v.z));
 }
 
+// L2 hand-over: velm is written by one streaming launch and read (then overwritten) by the next.  B200's L2
+// holds 126 MB, so when consecutive launches walk the tiles in opposite directions the tail of what the
+// previous launch wrote is still resident: those reads never reach HBM and the dirty lines are overwritten in
+// L2 before they are evicted.  velm stores therefore use the default L2 policy while everything that is touched
+// once per step (posq, forces, descriptors) is loaded evict-first / stored streaming.
 template <int KIND, int FFMT, bool USE_COM, bool HARDWALL>
 __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_constant__ StreamArgs a) {
     using L = SmemLayout<KIND, FFMT, USE_COM>;
     using St = typename L::Stage;
     constexpr int NS = L::NSTAGE;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* empty = full + NS;
+    int4* tlist = reinterpret_cast<int4*>(smem + L::OFF_TLIST);
     float* sscale = reinterpret_cast<float*>(smem + L::OFF_SCALE);
     int* smisc = reinterpret_cast<int*>(smem + L::OFF_MISC);
-    float4* smom = reinterpret_cast<float4*>(smem + L::OFF_MOM);
     double* ske = reinterpret_cast<double*>(smem + L::OFF_KE);
     double* swarp = reinterpret_cast<double*>(smem + L::OFF_WARP);
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = a.chain.T, G = a.chain.G;
     const int myTiles = blockIdx.x < a.numTiles ? (a.numTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // bounds of this CTA's it-th tile: {first particle, end particle, first residue, end residue}
+    auto tile_bounds = [&](int it) {
+        const int t = blockIdx.x + it * gridDim.x;
+        const int tile = a.reverse ? a.numTiles - 1 - t : t;
+        return make_int4(a.tileStart[tile], a.tileStart[tile + 1], St::HAS_R ? a.tileFirstRes[tile] : 0, St::HAS_R ? a.tileFirstRes[tile + 1] : 0);
+    };
 
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARPS); }
         fence_mbar_init();
     }
+    for (int it = tid; it < myTiles && it < TLIST_CAP; it += TILE) tlist[it] = tile_bounds(it);   // static tables: safe before pdl_wait
     if (L::HAS_KE)
         for (int g = 0; g < T; g++) ske[g * TILE + tid] = 0.0;
-    if (tid < T) sscale[tid] = (KIND == KIND_B) ? 1.0f : (float)a.chain.scaleA[tid];
+    pdl_wait();                                         // everything below reads what earlier launches wrote
+    if (tid < T) sscale[tid] = (KIND == KIND_B || KIND == KIND_BU) ? 1.0f : (float)a.chain.scaleA[tid];
     __syncthreads();
 
-    const uint64_t policy = policy_evict_first();
+    const uint64_t polOnce = policy_evict_first();
+    const uint64_t polKeep = policy_evict_last();
+    // L2 prefetch of the tile this CTA will request PF_DIST requests from now: the HBM latency (2-3 us under load) is
+    // then covered by L2 capacity instead of shared-memory stages, of which only 3-4 fit per CTA
+    auto prefetch = [&](int it) {
+        if (PF_DIST == 0 || it >= myTiles) return;
+        const int4 b = it < TLIST_CAP ? tlist[it] : tile_bounds(it);
+        const int start = b.x, end = b.y;
+        const int n = end - start, a0 = start & ~3, na = ((end + 3) & ~3) - a0;
+        if (KIND == KIND_KE) bulk_prefetch_l2(a.velm + start, n * 16);   // velm of the other kinds was just written by the previous launch
+        if (St::HAS_X) bulk_prefetch_l2(a.posq + start, n * 16);
+        if (St::HAS_F) {
+            const unsigned char* f = static_cast<const unsigned char*>(a.force);
+            for (int c = 0; c < 3; c++) bulk_prefetch_l2(f + ((size_t)c * a.paddedN + a0) * St::FBYTES, na * St::FBYTES);
+        }
+        bulk_prefetch_l2(a.desc + a0, na * 4);
+    };
+    // Request tile `it` of this CTA into its stage (thread 0 only).
     auto issue = [&](int it) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int start = a.tileStart[tile], end = a.tileStart[tile + 1];
+        const int4 b = it < TLIST_CAP ? tlist[it] : tile_bounds(it);
+        const int start = b.x, end = b.y, r0 = b.z, r1 = b.w;
         const int n = end - start, a0 = start & ~3, na = ((end + 3) & ~3) - a0;
         unsigned char* st = smem + (it % NS) * St::BYTES;
-        uint64_t* bar = &bars[it % NS];
+        uint64_t* bar = &full[it % NS];
+        *reinterpret_cast<int4*>(st + St::OFF_HDR) = make_int4(start, n, r0, r1 - r0);
         uint32_t bytes = n * 16 + na * 4;
+        const int ra0 = r0 & ~3, rna = ((r1 + 1 + 3) & ~3) - ra0;     // residues r0..r1 inclusive (r1 = end marker)
+        if (St::HAS_R) bytes += rna * 4;
         if (St::HAS_X) bytes += n * 16;
         if (St::HAS_F) bytes += 3 * na * St::FBYTES;
         mbar_arrive_expect_tx(bar, bytes);
-        bulk_g2s(st + St::OFF_V, a.velm + start, n * 16, bar, policy);
-        if (St::HAS_X) bulk_g2s(st + St::OFF_X, a.posq + start, n * 16, bar, policy);
+        bulk_g2s(st + St::OFF_V, a.velm + start, n * 16, bar, polOnce);
+        if (St::HAS_X) bulk_g2s(st + St::OFF_X, a.posq + start, n * 16, bar, polOnce);
         if (St::HAS_F) {
             const unsigned char* f = static_cast<const unsigned char*>(a.force);
             for (int c = 0; c < 3; c++)
                 bulk_g2s(st + St::OFF_F + c * PADW * St::FBYTES, f + ((size_t)c * a.paddedN + a0) * St::FBYTES, na * St::FBYTES, bar,
-                         policy);
+                         polOnce);
         }
-        bulk_g2s(st + St::OFF_D, a.desc + a0, na * 4, bar, policy);
+        bulk_g2s(st + St::OFF_D, a.desc + a0, na * 4, bar, polOnce);
+        if (St::HAS_R) bulk_g2s(st + St::OFF_R, a.resStart + ra0, rna * 4, bar, polOnce);
     };
-    if (tid == 0)
+    if (tid == 0) {
         for (int it = 0; it < NS && it < myTiles; it++) issue(it);
+        for (int it = NS; it < NS + PF_DIST; it++) prefetch(it);
+    }
 
-    const float sCOM = (KIND == KIND_B) ? 1.0f : sscale[G];
-    const float sDrude = (KIND == KIND_B) ? 1.0f : sscale[G + 1];
     const bool doScale = (KIND == KIND_A) || (KIND == KIND_KE && a.applyScale);
+    const float sCOM = doScale ? sscale[G] : 1.0f;
+    const float sDrude = doScale ? sscale[G + 1] : 1.0f;
+    const float rmax2 = a.rmax * a.rmax;
+    double accCOM = 0.0, accDrude = 0.0;               // this thread's share of the COM-group and Drude-group sums
 
     for (int it = 0; it < myTiles; it++) {
         const int stg = it % NS;
         const uint32_t phase = (it / NS) & 1;
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int start = a.tileStart[tile];
-        const int n = a.tileStart[tile + 1] - start;
-        const int fo = start & 3;                     // offset of the tile inside its 4-aligned window
         unsigned char* st = smem + stg * St::BYTES;
         const float4* sv = reinterpret_cast<const float4*>(st + St::OFF_V);
         const float4* sx = reinterpret_cast<const float4*>(st + St::OFF_X);
         const unsigned char* sF = st + St::OFF_F;
         const uint32_t* sd = reinterpret_cast<const uint32_t*>(st + St::OFF_D);
 
-        mbar_wait(&bars[stg], phase);
+        mbar_wait(&full[stg], phase);
+        const int4 hdr = *reinterpret_cast<const int4*>(st + St::OFF_HDR);
+        const int start = hdr.x, n = hdr.y;
+        const int fo = start & 3;                     // offset of the tile inside its 4-aligned window
 
         const bool active = tid < n;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t d = 0;
+        uint32_t d = 0;                               // inactive lanes: ordinary particle, partner = self, residue = self
         if (active) { v = sv[tid]; d = sd[fo + tid]; }
-        const uint32_t role = desc_role(d);
         const int tg = desc_tg(d);
+        const uint32_t role = desc_role(d);
         const bool massive = v.w != 0.0f;
-        const float m = massive ? 1.0f / v.w : 0.0f;
-        const int pj = tid + desc_partner(d);
+        const int pj = tid + desc_partner(d);         // ordinary particles: partner == self
+        const float4 vj = active ? sv[pj] : v;
+        const float m = massive ? rcp_fast(v.w) : 0.0f;
+        const float mj = rcp_fast(vj.w);
+        const float invTot = rcp_fast(m + mj);
+        const float fi = m * invTot, fj = mj * invTot;        // mass fractions of this particle and of its partner
+        float3 rel = make_float3(vj.x - v.x, vj.y - v.y, vj.z - v.z);   // partner minus me (0 for ordinary particles)
+        const float sT = doScale ? sscale[tg] : 1.0f;
+        const float coef = (sT - sDrude);
 
-        // ---- per-thread velocity update that does not need the residue's COM velocity (KIND_B: the kick) ----
-        float3 nv = make_float3(v.x, v.y, v.z);       // this particle's new velocity
-        float3 cmv = make_float3(0.f, 0.f, 0.f), relv = cmv;   // pair: centre-of-mass / relative velocity (KIND_B: after the kick)
-        float m1 = 0.f, m2 = 0.f, f1 = 0.f, f2 = 0.f, w1 = 0.f, w2 = 0.f;
-        float4 vo = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool isPair = active && role != ROLE_NORMAL;
-        const bool iAmDrude = role == ROLE_DRUDE;
-        if (isPair) {
-            vo = sv[pj];
-            w1 = iAmDrude ? v.w : vo.w;               // 1 = Drude particle, 2 = parent (pairParticles.x / .y)
-            w2 = iAmDrude ? vo.w : v.w;
-            m1 = 1.0f / w1; m2 = 1.0f / w2;
-            const float invTot = 1.0f / (m1 + m2);
-            f1 = invTot * m1; f2 = invTot * m2;
-        }
-        if (KIND == KIND_B) {
-            // integrateDrudeTGNHVelocities (drudeTGNH.cu:314-364), updatePosDelta = false
-            if (active) {
-                const float fx = load_force<FFMT>(sF, 0, fo + tid), fy = load_force<FFMT>(sF, 1, fo + tid), fz = load_force<FFMT>(sF, 2, fo + tid);
-                if (!isPair) {
-                    if (massive) {
-                        nv.x = v.x + a.fscale * v.w * fx; nv.y = v.y + a.fscale * v.w * fy; nv.z = v.z + a.fscale * v.w * fz;
-                    }
-                } else {
-                    const float ox = load_force<FFMT>(sF, 0, fo + pj), oy = load_force<FFMT>(sF, 1, fo + pj), oz = load_force<FFMT>(sF, 2, fo + pj);
-                    const float3 v1 = iAmDrude ? make_float3(v.x, v.y, v.z) : make_float3(vo.x, vo.y, vo.z);
-                    const float3 v2 = iAmDrude ? make_float3(vo.x, vo.y, vo.z) : make_float3(v.x, v.y, v.z);
-                    const float3 F1 = iAmDrude ? make_float3(fx, fy, fz) : make_float3(ox, oy, oz);
-                    const float3 F2 = iAmDrude ? make_float3(ox, oy, oz) : make_float3(fx, fy, fz);
-                    const float invTot = 1.0f / (m1 + m2);
-                    const float invRed = (m1 + m2) * w1 * w2;
-                    cmv = make_float3(v1.x * f1 + v2.x * f2, v1.y * f1 + v2.y * f2, v1.z * f1 + v2.z * f2);
-                    relv = make_float3(v2.x - v1.x, v2.y - v1.y, v2.z - v1.z);
-                    cmv.x += a.fscale * invTot * (F1.x + F2.x); cmv.y += a.fscale * invTot * (F1.y + F2.y); cmv.z += a.fscale * invTot * (F1.z + F2.z);
-                    relv.x += a.fscale * invRed * (F2.x * f1 - F1.x * f2);
-                    relv.y += a.fscale * invRed * (F2.y * f1 - F1.y * f2);
-                    relv.z += a.fscale * invRed * (F2.z * f1 - F1.z * f2);
-                    nv = iAmDrude ? make_float3(cmv.x - relv.x * f2, cmv.y - relv.y * f2, cmv.z - relv.z * f2)
-                                  : make_float3(cmv.x + relv.x * f1, cmv.y + relv.y * f1, cmv.z + relv.z * f1);
-                }
-                if (massive) st_stream(a.velm + start + tid, make_float4(nv.x, nv.y, nv.z, v.w));
-            }
-        }
+        float3 F = make_float3(0.f, 0.f, 0.f), Fj = F;
+        if (St::HAS_F && active) { F = load_force3<FFMT>(sF, fo + tid); Fj = load_force3<FFMT>(sF, fo + pj); }
+        const float fw = a.fscale * v.w, fwj = a.fscale * vj.w;
 
-        // ---- residue centre-of-mass velocity (calcCOMVelocities, drudeTGNH.cu:86-105) ----
+        // residue centre-of-mass velocity (calcCOMVelocities, drudeTGNH.cu:86-105); for the second half it is taken
+        // after the kick: sum_j m_j (v_j + fscale w_j F_j) = sum_j (m_j v_j + fscale F_j) over the massive members
         float3 V = make_float3(0.f, 0.f, 0.f);
         float Mres = 0.f;
-        if (USE_COM) {
-            smom[tid] = make_float4(nv.x * m, nv.y * m, nv.z * m, m);   // inactive lanes and massless particles: zeros
-            __syncthreads();
-            if (active) {
-                const int j0 = tid - desc_off_first(d), j1 = tid + desc_off_last(d);
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int j = j0; j <= j1; j++) {
-                    const float4 q = smom[j];
-                    acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
-                }
-                Mres = acc.w;
-                const float inv = 1.0f / acc.w;
-                V = make_float3(acc.x * inv, acc.y * inv, acc.z * inv);
-            }
-        }
-
-        if (KIND == KIND_A || KIND == KIND_KE) {
-            // ---- thermostat scaling (integrateDrudeTGNHChain, drudeTGNH.cu:255-300) ----
-            if (isPair) {
-                const float3 v1 = iAmDrude ? make_float3(v.x, v.y, v.z) : make_float3(vo.x, vo.y, vo.z);
-                const float3 v2 = iAmDrude ? make_float3(vo.x, vo.y, vo.z) : make_float3(v.x, v.y, v.z);
-                // cm' = centre of mass of the pair relative to the residue, rel = v2 - v1
-                cmv = make_float3((v1.x - V.x) * f1 + (v2.x - V.x) * f2, (v1.y - V.y) * f1 + (v2.y - V.y) * f2, (v1.z - V.z) * f1 + (v2.z - V.z) * f2);
-                relv = make_float3(v2.x - v1.x, v2.y - v1.y, v2.z - v1.z);
-            }
-            float3 rv = make_float3(v.x - V.x, v.y - V.y, v.z - V.z);    // ordinary particle relative to the residue
-            float3 Vs = V;
-            if (doScale) {
-                const float sT = sscale[tg];
-                rv.x *= sT; rv.y *= sT; rv.z *= sT;
-                cmv.x *= sT; cmv.y *= sT; cmv.z *= sT;
-                relv.x *= sDrude; relv.y *= sDrude; relv.z *= sDrude;
-                Vs.x *= sCOM; Vs.y *= sCOM; Vs.z *= sCOM;
-            }
-            if (L::HAS_KE && active) {
-                // computeNormalizedKineticEnergies (drudeTGNH.cu:152-188) on the (scaled) velocities
-                if (!isPair) {
-                    if (massive) ske[tg * TILE + tid] += (double)m * sq3(rv.x, rv.y, rv.z);
-                } else if (iAmDrude) {
-                    ske[tg * TILE + tid] += (double)(m1 + m2) * sq3(cmv.x, cmv.y, cmv.z);
-                    ske[(G + 1) * TILE + tid] += (double)(m1 * m2 / (m1 + m2)) * sq3(relv.x, relv.y, relv.z);
-                }
-                if (USE_COM && desc_off_first(d) == 0) ske[G * TILE + tid] += (double)Mres * sq3(Vs.x, Vs.y, Vs.z);
-            }
-            if (KIND == KIND_KE) {
-                if (doScale && active && massive) {
-                    if (!isPair) nv = make_float3(rv.x + Vs.x, rv.y + Vs.y, rv.z + Vs.z);
-                    else nv = iAmDrude ? make_float3(cmv.x - relv.x * f2 + Vs.x, cmv.y - relv.y * f2 + Vs.y, cmv.z - relv.z * f2 + Vs.z)
-                                       : make_float3(cmv.x + relv.x * f1 + Vs.x, cmv.y + relv.y * f1 + Vs.y, cmv.z + relv.z * f1 + Vs.z);
-                    st_stream(a.velm + start + tid, make_float4(nv.x, nv.y, nv.z, v.w));
-                }
-            } else if (active) {
-                // ---- half kick + drift (+ hard wall) (drudeTGNH.cu:314-364, 438-465, 474-573) ----
-                const float4 x = sx[tid];
-                const float fx = load_force<FFMT>(sF, 0, fo + tid), fy = load_force<FFMT>(sF, 1, fo + tid), fz = load_force<FFMT>(sF, 2, fo + tid);
-                if (!isPair) {
-                    if (massive) {
-                        nv.x = rv.x + Vs.x + a.fscale * v.w * fx;
-                        nv.y = rv.y + Vs.y + a.fscale * v.w * fy;
-                        nv.z = rv.z + Vs.z + a.fscale * v.w * fz;
-                        st_stream(a.velm + start + tid, make_float4(nv.x, nv.y, nv.z, v.w));
-                        st_stream(a.posq + start + tid, make_float4(x.x + a.dt * nv.x, x.y + a.dt * nv.y, x.z + a.dt * nv.z, x.w));
-                    }
+        if (USE_COM && active && KIND != KIND_BU) {
+            const int j0 = tid - desc_off_first(d), j1 = tid + desc_off_last(d);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = j0; j <= j1; j++) {
+                const float4 q = sv[j];
+                const bool mass = q.w != 0.0f;
+                const float mq = mass ? rcp_fast(q.w) : 0.0f;
+                if (KIND == KIND_B) {
+                    const float3 Fq = load_force3<FFMT>(sF, fo + j);
+                    const float fs = mass ? a.fscale : 0.0f;
+                    acc.x += fmaf(q.x, mq, fs * Fq.x); acc.y += fmaf(q.y, mq, fs * Fq.y); acc.z += fmaf(q.z, mq, fs * Fq.z);
                 } else {
-                    const float ox = load_force<FFMT>(sF, 0, fo + pj), oy = load_force<FFMT>(sF, 1, fo + pj), oz = load_force<FFMT>(sF, 2, fo + pj);
-                    const float4 xo = sx[pj];
-                    const float3 F1 = iAmDrude ? make_float3(fx, fy, fz) : make_float3(ox, oy, oz);
-                    const float3 F2 = iAmDrude ? make_float3(ox, oy, oz) : make_float3(fx, fy, fz);
-                    const float invTot = 1.0f / (m1 + m2);
-                    const float invRed = (m1 + m2) * w1 * w2;
-                    // pair centre of mass in the lab frame: scaled relative part + scaled residue COM
-                    float3 cm = make_float3(cmv.x + Vs.x, cmv.y + Vs.y, cmv.z + Vs.z);
-                    cm.x += a.fscale * invTot * (F1.x + F2.x); cm.y += a.fscale * invTot * (F1.y + F2.y); cm.z += a.fscale * invTot * (F1.z + F2.z);
-                    relv.x += a.fscale * invRed * (F2.x * f1 - F1.x * f2);
-                    relv.y += a.fscale * invRed * (F2.y * f1 - F1.y * f2);
-                    relv.z += a.fscale * invRed * (F2.z * f1 - F1.z * f2);
-                    float3 nv1 = make_float3(cm.x - relv.x * f2, cm.y - relv.y * f2, cm.z - relv.z * f2);
-                    float3 nv2 = make_float3(cm.x + relv.x * f1, cm.y + relv.y * f1, cm.z + relv.z * f1);
-                    const float4 x1o = iAmDrude ? x : xo, x2o = iAmDrude ? xo : x;
-                    float3 x1 = make_float3(x1o.x + a.dt * nv1.x, x1o.y + a.dt * nv1.y, x1o.z + a.dt * nv1.z);
-                    float3 x2 = make_float3(x2o.x + a.dt * nv2.x, x2o.y + a.dt * nv2.y, x2o.z + a.dt * nv2.z);
-                    if (HARDWALL) {
-                        // Drude displacement from the exact difference of the old positions plus the relative drift:
-                        // avoids the cancellation of two rounded ~box-sized coordinates in the wall test
-                        const float3 delta = make_float3((x1o.x - x2o.x) - a.dt * relv.x, (x1o.y - x2o.y) - a.dt * relv.y, (x1o.z - x2o.z) - a.dt * relv.z);
-                        bool moved;
-                        hard_wall(delta, x1, x2, nv1, nv2, w1, w2, a.rmax, a.hardwallScale, a.dt, moved);
-                    }
-                    const float3 mv = iAmDrude ? nv1 : nv2;
-                    const float3 mx = iAmDrude ? x1 : x2;
-                    if (massive) {
-                        st_stream(a.velm + start + tid, make_float4(mv.x, mv.y, mv.z, v.w));
-                        st_stream(a.posq + start + tid, make_float4(mx.x, mx.y, mx.z, x.w));
-                    }
+                    acc.x = fmaf(q.x, mq, acc.x); acc.y = fmaf(q.y, mq, acc.y); acc.z = fmaf(q.z, mq, acc.z);
+                }
+                acc.w += mq;
+            }
+            Mres = acc.w;
+            const float inv = rcp_fast(acc.w);
+            V = make_float3(acc.x * inv, acc.y * inv, acc.z * inv);
+        }
+
+        float3 vn;                                    // this particle's new velocity
+        float3 r;                                     // ... relative to the residue (after scaling / kick)
+        if (KIND == KIND_BU) {
+            // kick (drudeTGNH.cu:314-364); kinetic energies in the lab frame, the residues' M |V|^2 is removed below
+            vn = kicked(make_float3(v.x, v.y, v.z), fw, F);
+            if (active && massive) st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
+            const float3 vjn = kicked(make_float3(vj.x, vj.y, vj.z), fwj, Fj);
+            rel = make_float3(vjn.x - vn.x, vjn.y - vn.y, vjn.z - vn.z);
+            r = vn;
+            // one thread per residue of the tile; the duty rotates over the warps from tile to tile so that no warp is
+            // always the slow one (a stage is recycled only when all 16 warps have left it)
+            const int ridx = (tid - it * 128) & (TILE - 1);
+            if (USE_COM && ridx < hdr.w) {
+                // P = sum_j (m_j v_j + fscale F_j), M = sum_j m_j over the residue's massive members
+                const int* sr = reinterpret_cast<const int*>(st + St::OFF_R) + (hdr.z & 3);
+                const int j0 = sr[ridx] - start, j1 = sr[ridx + 1] - start;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = j0; j < j1; j++) {
+                    const float4 q = sv[j];
+                    const float3 Fq = load_force3<FFMT>(sF, fo + j);
+                    const bool mass = q.w != 0.0f;
+                    const float mq = mass ? rcp_fast(q.w) : 0.0f;
+                    const float fs = mass ? a.fscale : 0.0f;
+                    acc.x += fmaf(q.x, mq, fs * Fq.x); acc.y += fmaf(q.y, mq, fs * Fq.y); acc.z += fmaf(q.z, mq, fs * Fq.z);
+                    acc.w += mq;
+                }
+                const double keC = (double)(dot3(make_float3(acc.x, acc.y, acc.z)) * rcp_fast(acc.w));   // M |V|^2 = |P|^2 / M
+                accCOM += keC;
+                ske[desc_tg(sd[fo + j0]) * TILE + tid] -= keC;
+            }
+        } else if (KIND == KIND_B) {
+            // integrateDrudeTGNHVelocities (drudeTGNH.cu:314-364), updatePosDelta = false
+            vn = kicked(make_float3(v.x, v.y, v.z), fw, F);
+            if (active && massive) st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
+            rel = make_float3(rel.x + fwj * Fj.x - fw * F.x, rel.y + fwj * Fj.y - fw * F.y, rel.z + fwj * Fj.z - fw * F.z);
+            r = make_float3(vn.x - V.x, vn.y - V.y, vn.z - V.z);
+        } else {
+            // thermostat scaling (integrateDrudeTGNHChain, drudeTGNH.cu:255-300) in the unified form of the header comment
+            r = make_float3(v.x - V.x, v.y - V.y, v.z - V.z);
+            vn = scaled_velocity(sT, r, sCOM, V, coef * fj, rel);
+        }
+
+        if (L::HAS_KE) {
+            // computeNormalizedKineticEnergies (drudeTGNH.cu:152-188), branch-free: an ordinary particle is its own
+            // "pair centre of mass" (rel = 0); the Drude particle of a pair carries the pair's two terms
+            const float3 cm = make_float3(r.x + fj * rel.x, r.y + fj * rel.y, r.z + fj * rel.z);    // pair COM relative to the residue
+            const bool isDrude = role == ROLE_DRUDE;
+            const float massT = isDrude ? (m + mj) : (role == ROLE_NORMAL ? m : 0.0f);
+            const float s2T = sT * sT, s2D = sDrude * sDrude, s2C = sCOM * sCOM;                     // all 1 unless scaling
+            const float keT = massT * s2T * dot3(cm);
+            const float keD = isDrude ? m * fj * s2D * dot3(rel) : 0.0f;                              // reduced mass m*mj/(m+mj)
+            const float keC = (USE_COM && KIND != KIND_BU && active && desc_off_first(d) == 0) ? Mres * s2C * dot3(V) : 0.0f;
+            if (active && massT != 0.0f) ske[tg * TILE + tid] += (double)keT;
+            accDrude += (double)keD;
+            accCOM += (double)keC;
+        }
+
+        if (KIND == KIND_KE) {
+            if (doScale && active && massive) st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
+        } else if (KIND == KIND_A && active) {
+            // half kick + drift (+ hard wall) (drudeTGNH.cu:314-364, 438-465, 474-573)
+            vn = kicked(vn, fw, F);
+            const float4 x = sx[tid];
+            float3 xn = make_float3(x.x + a.dt * vn.x, x.y + a.dt * vn.y, x.z + a.dt * vn.z);
+            if (HARDWALL && role != ROLE_NORMAL) {
+                // the partner's update, recomputed here so that both threads of a pair see the same wall test;
+                // seen from the partner, rel changes sign and the mass fraction is this particle's
+                const float3 rj = make_float3(vj.x - V.x, vj.y - V.y, vj.z - V.z);
+                float3 vjn = kicked(scaled_velocity(sT, rj, sCOM, V, coef * fi, make_float3(-rel.x, -rel.y, -rel.z)), fwj, Fj);
+                const float4 xj = sx[pj];
+                // displacement from the exact difference of the old positions plus the relative drift: avoids the
+                // cancellation of two rounded box-sized coordinates in the wall test
+                float3 delta = make_float3((x.x - xj.x) + a.dt * (vn.x - vjn.x), (x.y - xj.y) + a.dt * (vn.y - vjn.y), (x.z - xj.z) + a.dt * (vn.z - vjn.z));
+                const float r2 = dot3(delta);
+                if (r2 > rmax2) {                     // rInv*maxDrudeDistance < 1  (drudeTGNH.cu:490)
+                    float3 xjn = make_float3(xj.x + a.dt * vjn.x, xj.y + a.dt * vjn.y, xj.z + a.dt * vjn.z);
+                    if (role == ROLE_DRUDE) hard_wall(delta, r2, xn, xjn, vn, vjn, v.w, vj.w, a.rmax, a.hardwallScale, a.dt);
+                    else hard_wall(make_float3(-delta.x, -delta.y, -delta.z), r2, xjn, xn, vjn, vn, vj.w, v.w, a.rmax, a.hardwallScale, a.dt);
                 }
             }
-        } else {
-            // KIND_B: kinetic energies of the kicked velocities relative to the residue COM
-            if (active) {
-                if (!isPair) {
-                    if (massive) ske[tg * TILE + tid] += (double)m * sq3(nv.x - V.x, nv.y - V.y, nv.z - V.z);
-                } else if (iAmDrude) {
-                    ske[tg * TILE + tid] += (double)(m1 + m2) * sq3(cmv.x - V.x, cmv.y - V.y, cmv.z - V.z);
-                    ske[(G + 1) * TILE + tid] += (double)(m1 * m2 / (m1 + m2)) * sq3(relv.x, relv.y, relv.z);
-                }
-                if (USE_COM && desc_off_first(d) == 0) ske[G * TILE + tid] += (double)Mres * sq3(V.x, V.y, V.z);
+            if (massive) {
+                st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
+                st_stream(a.posq + start + tid, make_float4(xn.x, xn.y, xn.z, x.w));
             }
         }
 
-        __syncthreads();                               // every read of this stage (and of smom) is done
-        if (tid == 0 && it + NS < myTiles) issue(it + NS);
+        // hand the stage back: one arrival per warp; the producer refills it once all 16 warps are done with it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stg]);
+        if (tid == 0 && it + NS < myTiles) {
+            prefetch(it + NS + PF_DIST);
+            mbar_wait(&empty[stg], phase);
+            issue(it + NS);
+        }
     }
-
+    pdl_launch_dependents();
     if (!L::HAS_KE) return;
 
-    // ---- deterministic reduction: thread columns -> warp -> CTA -> (last CTA) grid -> chain ----
-    const int lane = tid & 31, warp = tid >> 5;
+    // ---- deterministic reduction: thread columns -> warp -> CTA -> (last CTA) grid ----
+    ske[G * TILE + tid] += accCOM;
+    ske[(G + 1) * TILE + tid] += accDrude;
     for (int g = 0; g < T; g++) {
         double x = ske[g * TILE + tid];
 #pragma unroll
@@ -380,7 +432,7 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
     __syncthreads();
     if (tid < T) {
         double x = 0.0;
-        for (int w = 0; w < TILE / 32; w++) x += swarp[tid * 16 + w];
+        for (int w = 0; w < NWARPS; w++) x += swarp[tid * 16 + w];
         a.partials[(size_t)blockIdx.x * T + tid] = x;
     }
     __threadfence();
@@ -393,8 +445,8 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
     if (!smisc[0]) return;
     __threadfence();
     // last CTA: warp g sums column g of the partials over all CTAs in a fixed order
-    double* out = (a.chainMode == CHAIN_NONE && a.chain.ke2Local) ? a.chain.ke2Local : a.chain.ke2;
-    for (int g = warp; g < T; g += TILE / 32) {
+    double* out = a.useLocalKE ? a.chain.ke2Local : a.chain.ke2;
+    for (int g = warp; g < T; g += NWARPS) {
         double x = 0.0;
         for (int b = lane; b < (int)gridDim.x; b += 32) x += __ldcg(a.partials + (size_t)b * T + g);
 #pragma unroll
@@ -403,11 +455,13 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
     }
     if (tid == 0) *a.ticket = 0u;
     if (KIND == KIND_KE && a.applyScale && tid < T) a.chain.pending[tid] = 1.0;   // the deferred scaling is now applied
-    __syncthreads();
-    if (a.chainMode != CHAIN_NONE && warp == 0) chain_phase(a.chain, a.chainMode, lane);
 }
 
-// stand-alone chain update (sharded runs after the all-reduce; first step of a tgnh_step batch)
-__global__ void tgnh_chain_kernel(ChainView c, int mode) { chain_phase(c, mode, threadIdx.x); }
+// The Nose-Hoover chain update(s) between two streaming launches: one warp, lane g = thermostat g.
+__global__ void __launch_bounds__(32, 1) tgnh_chain_kernel(ChainView c, int mode) {
+    pdl_launch_dependents();      // the next streaming launch may start its prologue; it waits for our results
+    pdl_wait();
+    chain_phase(c, mode, threadIdx.x);
+}
 
 }  // namespace tgnh
