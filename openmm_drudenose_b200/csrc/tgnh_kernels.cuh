@@ -25,6 +25,9 @@
 // Arithmetic: the reference transforms each Drude pair to (centre of mass, relative) coordinates and
 // back in every kernel.  Algebraically, with f_j = m_j / (m_i + m_j) and rel = v_j - v_i,
 //     scaling:  v_i <- sT (v_i - V) + sCOM V + (sT - sDrude) f_j rel        (drudeTGNH.cu:270-300)
+//               evaluated as v_i + [(sT-1)(v_i - V) + (sCOM-1) V + (sT - sDrude) f_j rel]: the thermostat factors are
+//               1 + O(1e-4), and a factor rounded to fp32 would put the SAME 3e-8 relative error on every particle of
+//               the group (6e-8 on its kinetic energy, every step); the differences s-1 are taken in double
 //     kick:     v_i <- v_i + fscale w_i F_i                                 (drudeTGNH.cu:330-364; the cm/rel
 //                                                                            form reduces to the direct kick)
 // which holds for both members of a pair and, with "partner = self" (rel = 0), for ordinary particles:
@@ -83,8 +86,8 @@ struct SmemLayout {
     static constexpr int NSTAGE = (KIND == KIND_A) ? 3 : 4;
     static constexpr int OFF_BAR = NSTAGE * Stage::BYTES;         // full[NS], empty[NS] mbarriers
     static constexpr int OFF_TLIST = OFF_BAR + 128;               // int4[TLIST_CAP] bounds of this CTA's first tiles
-    static constexpr int OFF_SCALE = OFF_TLIST + TLIST_CAP * 16;  // float[MAX_T]
-    static constexpr int OFF_MISC = OFF_SCALE + MAX_T * 4;        // int[4]
+    static constexpr int OFF_SCALE = OFF_TLIST + TLIST_CAP * 16;  // double[MAX_T] s^2, float[MAX_T] s - 1
+    static constexpr int OFF_MISC = OFF_SCALE + MAX_T * 12;       // int[4]
     static constexpr int OFF_WARP = OFF_MISC + 16;                // double[T][16]   (HAS_KE)
     static constexpr int OFF_KE = OFF_WARP + (HAS_KE ? MAX_T * 16 * 8 : 0);
     static int bytes(int T) { return OFF_KE + (HAS_KE ? T * TILE * 8 : 0); }
@@ -106,6 +109,18 @@ __device__ __forceinline__ float rcp_fast(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+}
+// second-order term of the reciprocal: 1/w = r + rcp_lo(w, r) to ~1e-14 for r = rcp_fast(w)
+__device__ __forceinline__ float rcp_lo(float w, float r) { return r * fmaf(-w, r, 1.0f); }
+// Masses that weight the kinetic-energy sums are formed in double from that pair.  A species' rounded fp32
+// mass (all oxygens share one w) would otherwise shift its thermostat's energy by up to 6e-8 — systematically,
+// so it does not average out over particles, and the Nose-Hoover chain integrates it.
+__device__ __forceinline__ double mass_d(float w, float r) { return (double)r + (double)rcp_lo(w, r); }
+// 1/x in double from a float seed: two Newton steps (1e-7 -> 1e-14 -> rounding)
+__device__ __forceinline__ double rcp_d(double x, float seed) {
+    double r = (double)seed;
+    r = r * fma(-x, r, 2.0);
+    return r * fma(-x, r, 2.0);
 }
 __device__ __forceinline__ float rsqrt_fast(float x) {
     float r;
@@ -159,11 +174,11 @@ __device__ __forceinline__ void hard_wall(float3 delta, float r2, float3& x1, fl
 
 __device__ __forceinline__ float dot3(float3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
 
-// sT*r + sCOM*V + c*rel with a fixed evaluation order, so that the two threads of a Drude pair compute
+// v + eT*r + eCOM*V + c*rel (e = s - 1) with a fixed evaluation order, so that the two threads of a Drude pair compute
 // bit-identical values for each other's particle (both must take the same side of the hard-wall test)
-__device__ __forceinline__ float3 scaled_velocity(float sT, float3 r, float sCOM, float3 V, float c, float3 rel) {
-    return make_float3(fmaf(c, rel.x, fmaf(sT, r.x, sCOM * V.x)), fmaf(c, rel.y, fmaf(sT, r.y, sCOM * V.y)),
-                       fmaf(c, rel.z, fmaf(sT, r.z, sCOM * V.z)));
+__device__ __forceinline__ float3 scaled_velocity(float3 v, float eT, float3 r, float eCOM, float3 V, float c, float3 rel) {
+    return make_float3(v.x + fmaf(c, rel.x, fmaf(eT, r.x, eCOM * V.x)), v.y + fmaf(c, rel.y, fmaf(eT, r.y, eCOM * V.y)),
+                       v.z + fmaf(c, rel.z, fmaf(eT, r.z, eCOM * V.z)));
 }
 __device__ __forceinline__ float3 kicked(float3 v, float fw, float3 F) {
     return make_float3(fmaf(fw, F.x, v.x), fmaf(fw, F.y, v.y), fmaf(fw, F.z, v.z));
@@ -183,7 +198,8 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* empty = full + NS;
     int4* tlist = reinterpret_cast<int4*>(smem + L::OFF_TLIST);
-    float* sscale = reinterpret_cast<float*>(smem + L::OFF_SCALE);
+    double* ssq = reinterpret_cast<double*>(smem + L::OFF_SCALE);         // s_g^2
+    float* seps = reinterpret_cast<float*>(ssq + MAX_T);                  // s_g - 1
     int* smisc = reinterpret_cast<int*>(smem + L::OFF_MISC);
     double* ske = reinterpret_cast<double*>(smem + L::OFF_KE);
     double* swarp = reinterpret_cast<double*>(smem + L::OFF_WARP);
@@ -206,7 +222,11 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
     if (L::HAS_KE)
         for (int g = 0; g < T; g++) ske[g * TILE + tid] = 0.0;
     pdl_wait();                                         // everything below reads what earlier launches wrote
-    if (tid < T) sscale[tid] = (KIND == KIND_B || KIND == KIND_BU) ? 1.0f : (float)a.chain.scaleA[tid];
+    if (tid < T) {
+        const double sg = (KIND == KIND_B || KIND == KIND_BU) ? 1.0 : a.chain.scaleA[tid];
+        ssq[tid] = sg * sg;
+        seps[tid] = (float)(sg - 1.0);
+    }
     __syncthreads();
 
     const uint64_t polOnce = policy_evict_first();
@@ -257,8 +277,8 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
     }
 
     const bool doScale = (KIND == KIND_A) || (KIND == KIND_KE && a.applyScale);
-    const float sCOM = doScale ? sscale[G] : 1.0f;
-    const float sDrude = doScale ? sscale[G + 1] : 1.0f;
+    const float eCOM = doScale ? seps[G] : 0.0f;
+    const float eDrude = doScale ? seps[G + 1] : 0.0f;
     const float rmax2 = a.rmax * a.rmax;
     double accCOM = 0.0, accDrude = 0.0;               // this thread's share of the COM-group and Drude-group sums
 
@@ -290,8 +310,8 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
         const float invTot = rcp_fast(m + mj);
         const float fi = m * invTot, fj = mj * invTot;        // mass fractions of this particle and of its partner
         float3 rel = make_float3(vj.x - v.x, vj.y - v.y, vj.z - v.z);   // partner minus me (0 for ordinary particles)
-        const float sT = doScale ? sscale[tg] : 1.0f;
-        const float coef = (sT - sDrude);
+        const float eT = doScale ? seps[tg] : 0.0f;
+        const float coef = (eT - eDrude);            // sT - sDrude
 
         float3 F = make_float3(0.f, 0.f, 0.f), Fj = F;
         if (St::HAS_F && active) { F = load_force3<FFMT>(sF, fo + tid); Fj = load_force3<FFMT>(sF, fo + pj); }
@@ -300,26 +320,38 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
         // residue centre-of-mass velocity (calcCOMVelocities, drudeTGNH.cu:86-105); for the second half it is taken
         // after the kick: sum_j m_j (v_j + fscale w_j F_j) = sum_j (m_j v_j + fscale F_j) over the massive members
         float3 V = make_float3(0.f, 0.f, 0.f);
-        float Mres = 0.f;
+        double keC = 0.0;                             // M |V|^2 of this particle's residue (kinds that reduce energies)
         if (USE_COM && active && KIND != KIND_BU) {
             const int j0 = tid - desc_off_first(d), j1 = tid + desc_off_last(d);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int j = j0; j <= j1; j++) {
-                const float4 q = sv[j];
-                const bool mass = q.w != 0.0f;
-                const float mq = mass ? rcp_fast(q.w) : 0.0f;
-                if (KIND == KIND_B) {
-                    const float3 Fq = load_force3<FFMT>(sF, fo + j);
-                    const float fs = mass ? a.fscale : 0.0f;
-                    acc.x += fmaf(q.x, mq, fs * Fq.x); acc.y += fmaf(q.y, mq, fs * Fq.y); acc.z += fmaf(q.z, mq, fs * Fq.z);
-                } else {
+            if (!L::HAS_KE) {
+                // first half: V only feeds the small corrections (sT-1)(v - V) and (sCOM-1) V, fp32 sums are ample
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = j0; j <= j1; j++) {
+                    const float4 q = sv[j];
+                    const float mq = q.w != 0.0f ? rcp_fast(q.w) : 0.0f;
                     acc.x = fmaf(q.x, mq, acc.x); acc.y = fmaf(q.y, mq, acc.y); acc.z = fmaf(q.z, mq, acc.z);
+                    acc.w += mq;
                 }
-                acc.w += mq;
+                const float inv = rcp_fast(acc.w);
+                V = make_float3(acc.x * inv, acc.y * inv, acc.z * inv);
+            } else {
+                // kinds that reduce energies: momentum and mass of the residue in double (see mass_d)
+                double Px = 0.0, Py = 0.0, Pz = 0.0, M = 0.0;
+                for (int j = j0; j <= j1; j++) {
+                    const float4 q = sv[j];
+                    const bool mass = q.w != 0.0f;
+                    const float mq = mass ? rcp_fast(q.w) : 0.0f;
+                    const double mqd = mass ? mass_d(q.w, mq) : 0.0;
+                    float3 vq = make_float3(q.x, q.y, q.z);
+                    if (KIND == KIND_B) vq = kicked(vq, a.fscale * q.w, load_force3<FFMT>(sF, fo + j));   // what member j stores
+                    Px = fma(mqd, (double)vq.x, Px); Py = fma(mqd, (double)vq.y, Py); Pz = fma(mqd, (double)vq.z, Pz);
+                    M += mqd;
+                }
+                const double invM = rcp_d(M, rcp_fast((float)M));
+                const double Vx = Px * invM, Vy = Py * invM, Vz = Pz * invM;
+                V = make_float3((float)Vx, (float)Vy, (float)Vz);
+                keC = M * fma(Vx, Vx, fma(Vy, Vy, Vz * Vz));
             }
-            Mres = acc.w;
-            const float inv = rcp_fast(acc.w);
-            V = make_float3(acc.x * inv, acc.y * inv, acc.z * inv);
         }
 
         float3 vn;                                    // this particle's new velocity
@@ -335,20 +367,20 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
             // always the slow one (a stage is recycled only when all 16 warps have left it)
             const int ridx = (tid - it * 128) & (TILE - 1);
             if (USE_COM && ridx < hdr.w) {
-                // P = sum_j (m_j v_j + fscale F_j), M = sum_j m_j over the residue's massive members
+                // P = sum_j m_j v_j (kicked velocities), M = sum_j m_j over the residue's massive members
                 const int* sr = reinterpret_cast<const int*>(st + St::OFF_R) + (hdr.z & 3);
                 const int j0 = sr[ridx] - start, j1 = sr[ridx + 1] - start;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                double Px = 0.0, Py = 0.0, Pz = 0.0, M = 0.0;
                 for (int j = j0; j < j1; j++) {
                     const float4 q = sv[j];
-                    const float3 Fq = load_force3<FFMT>(sF, fo + j);
                     const bool mass = q.w != 0.0f;
                     const float mq = mass ? rcp_fast(q.w) : 0.0f;
-                    const float fs = mass ? a.fscale : 0.0f;
-                    acc.x += fmaf(q.x, mq, fs * Fq.x); acc.y += fmaf(q.y, mq, fs * Fq.y); acc.z += fmaf(q.z, mq, fs * Fq.z);
-                    acc.w += mq;
+                    const double mqd = mass ? mass_d(q.w, mq) : 0.0;
+                    const float3 vq = kicked(make_float3(q.x, q.y, q.z), a.fscale * q.w, load_force3<FFMT>(sF, fo + j));   // what member j stores
+                    Px = fma(mqd, (double)vq.x, Px); Py = fma(mqd, (double)vq.y, Py); Pz = fma(mqd, (double)vq.z, Pz);
+                    M += mqd;
                 }
-                const double keC = (double)(dot3(make_float3(acc.x, acc.y, acc.z)) * rcp_fast(acc.w));   // M |V|^2 = |P|^2 / M
+                const double keC = fma(Px, Px, fma(Py, Py, Pz * Pz)) * rcp_d(M, rcp_fast((float)M));   // M |V|^2 = |P|^2 / M
                 accCOM += keC;
                 ske[desc_tg(sd[fo + j0]) * TILE + tid] -= keC;
             }
@@ -361,7 +393,7 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
         } else {
             // thermostat scaling (integrateDrudeTGNHChain, drudeTGNH.cu:255-300) in the unified form of the header comment
             r = make_float3(v.x - V.x, v.y - V.y, v.z - V.z);
-            vn = scaled_velocity(sT, r, sCOM, V, coef * fj, rel);
+            vn = scaled_velocity(make_float3(v.x, v.y, v.z), eT, r, eCOM, V, coef * fj, rel);
         }
 
         if (L::HAS_KE) {
@@ -369,14 +401,17 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
             // "pair centre of mass" (rel = 0); the Drude particle of a pair carries the pair's two terms
             const float3 cm = make_float3(r.x + fj * rel.x, r.y + fj * rel.y, r.z + fj * rel.z);    // pair COM relative to the residue
             const bool isDrude = role == ROLE_DRUDE;
-            const float massT = isDrude ? (m + mj) : (role == ROLE_NORMAL ? m : 0.0f);
-            const float s2T = sT * sT, s2D = sDrude * sDrude, s2C = sCOM * sCOM;                     // all 1 unless scaling
-            const float keT = massT * s2T * dot3(cm);
-            const float keD = isDrude ? m * fj * s2D * dot3(rel) : 0.0f;                              // reduced mass m*mj/(m+mj)
-            const float keC = (USE_COM && KIND != KIND_BU && active && desc_off_first(d) == 0) ? Mres * s2C * dot3(V) : 0.0f;
-            if (active && massT != 0.0f) ske[tg * TILE + tid] += (double)keT;
-            accDrude += (double)keD;
-            accCOM += (double)keC;
+            const double md = massive ? mass_d(v.w, m) : 0.0, mjd = mass_d(vj.w, mj);
+            const double Mp = md + mjd;
+            const double massT = isDrude ? Mp : (role == ROLE_NORMAL ? md : 0.0);
+            const double s2T = doScale ? ssq[tg] : 1.0, s2D = doScale ? ssq[G + 1] : 1.0, s2C = doScale ? ssq[G] : 1.0;
+            const double keT = massT * s2T * (double)dot3(cm);
+            const double keD = isDrude ? md * mjd * rcp_d(Mp, invTot) * s2D * (double)dot3(rel) : 0.0;   // reduced mass
+            if (!(USE_COM && KIND != KIND_BU && active && desc_off_first(d) == 0)) keC = 0.0;        // the residue's first particle carries M |V|^2
+            keC *= s2C;
+            if (active && massT != 0.0) ske[tg * TILE + tid] += keT;
+            accDrude += keD;
+            accCOM += keC;
         }
 
         if (KIND == KIND_KE) {
@@ -390,7 +425,7 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
                 // the partner's update, recomputed here so that both threads of a pair see the same wall test;
                 // seen from the partner, rel changes sign and the mass fraction is this particle's
                 const float3 rj = make_float3(vj.x - V.x, vj.y - V.y, vj.z - V.z);
-                float3 vjn = kicked(scaled_velocity(sT, rj, sCOM, V, coef * fi, make_float3(-rel.x, -rel.y, -rel.z)), fwj, Fj);
+                float3 vjn = kicked(scaled_velocity(make_float3(vj.x, vj.y, vj.z), eT, rj, eCOM, V, coef * fi, make_float3(-rel.x, -rel.y, -rel.z)), fwj, Fj);
                 const float4 xj = sx[pj];
                 // displacement from the exact difference of the old positions plus the relative drift: avoids the
                 // cancellation of two rounded box-sized coordinates in the wall test

@@ -146,7 +146,8 @@ def _ionic_templates():
 
 def build(templates, mol_types, mol_groups, num_temp_groups, *, seed=SEED, first_molecule=0,
           density=33.4, box_molecules=None, drude_sigma=0.005, force_sigma=200.0,
-          k_spring=100000 * 4.184, temperature=300.0, pair_force="common", **params):
+          k_spring=100000 * 4.184, temperature=300.0, pair_force="common", cold_drudes=False,
+          quantize_masses=False, **params):
     """Assemble a system from per-molecule template ids / temperature groups.
 
     mol_types[j], mol_groups[j] describe global molecule first_molecule + j.  Random data for a
@@ -162,6 +163,11 @@ def build(templates, mol_types, mol_groups, num_temp_groups, *, seed=SEED, first
                        on every step (measured: hit fraction 1.000 after ~30 steps, Drude temperature 318 K for a
                        1 K target); kept as the hard-wall stress workload;
       "none"           zero force on pair members (for tests that recompute harmonic forces every step).
+
+    cold_drudes: draw each pair's centre-of-mass velocity at `temperature` and its relative velocity at
+    drude_temperature (an equilibrated dual-thermostat state) instead of independent thermal velocities.
+    quantize_masses: replace every mass m by 1 / float32(1 / m), so that the fp32 inverse masses of the device
+    layout and the fp64 masses given to a CPU oracle describe exactly the same system.
     """
     mol_types = np.asarray(mol_types, np.int32)
     mol_groups = np.asarray(mol_groups, np.int32)
@@ -222,7 +228,19 @@ def build(templates, mol_types, mol_groups, num_temp_groups, *, seed=SEED, first
     positions[pair_drude] = positions[pair_parent] + drude_sigma * nrm[pair_drude, 0:3]
     with np.errstate(divide="ignore", invalid="ignore"):
         vsig = np.where(masses > 0, np.sqrt(BOLTZ * temperature / np.where(masses > 0, masses, 1.0)), 0.0)
+    if quantize_masses:
+        with np.errstate(divide="ignore"):
+            w32 = np.where(masses > 0, 1.0 / np.where(masses > 0, masses, 1.0), 0.0).astype(np.float32).astype(np.float64)
+            masses = np.where(w32 > 0, 1.0 / np.where(w32 > 0, w32, 1.0), 0.0)
     velocities = vsig[:, None] * nrm[:, 3:6]
+    if cold_drudes and len(pair_drude):
+        md, mp = masses[pair_drude], masses[pair_parent]
+        mt, mu = md + mp, md * mp / (md + mp)
+        t_d = params.get("drude_temperature", 1.0)
+        vcm = np.sqrt(BOLTZ * temperature / mt)[:, None] * nrm[pair_parent, 3:6]
+        vrel = np.sqrt(BOLTZ * t_d / mu)[:, None] * nrm[pair_drude, 3:6]          # v_parent - v_drude
+        velocities[pair_drude] = vcm - vrel * (mp / mt)[:, None]
+        velocities[pair_parent] = vcm + vrel * (md / mt)[:, None]
     positions = _f32(positions); velocities = _f32(velocities)
     forces = force_sigma * nrm[:, 6:9]
     forces[masses == 0] = 0.0

@@ -1,0 +1,129 @@
+"""CPU tests of the host side: generator, C-ABI library loading / validation, shard logic (gloo, world_size 2)."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from openmm_drudenose_b200 import capi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_generator_is_shard_invariant():
+    whole = synth.water_box(70000, 4)
+    lo = synth.water_box(30000, 4, first_molecule=0, box_molecules=70000)
+    hi = synth.water_box(40000, 4, first_molecule=30000, box_molecules=70000)
+    n = lo.num_particles
+    for name in ("positions", "velocities", "forces", "masses", "temp_group"):
+        np.testing.assert_array_equal(getattr(whole, name)[:n], getattr(lo, name))
+        np.testing.assert_array_equal(getattr(whole, name)[n:], getattr(hi, name))
+    assert whole.num_pairs == lo.num_pairs + hi.num_pairs
+
+
+def test_config_shapes():
+    c1 = synth.nacl_box()
+    assert (c1.num_particles, c1.num_pairs, c1.num_residues, c1.num_temp_groups) == (2500, 512, 512, 2)
+    assert (c1.masses == 0).sum() == 492 and len(c1.constraints) == 1476
+    c2 = synth.swm4_box(10000)
+    assert (c2.num_particles, c2.num_pairs, len(c2.constraints)) == (50000, 10000, 30000)
+    c3 = synth.ionic_liquid(1000)
+    assert (c3.num_particles, c3.num_pairs, c3.num_residues, c3.num_temp_groups) == (45000, 15000, 2000, 3)
+    v = c1.velm_f32(); f = c1.force_i64_soa(2528)
+    assert v.shape == (2500, 4) and v.dtype == np.float32 and f.shape == (3, 2528) and f.dtype == np.int64
+
+
+def test_library_exports_every_declared_symbol():
+    """include/tgnh.h <-> libtgnh.so: every declared function is exported (no compute calls without a GPU)."""
+    hdr = open(os.path.join(ROOT, "include", "tgnh.h")).read()
+    import re
+    declared = set(re.findall(r"\b(tgnh_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"tgnh_params", "tgnh_handle", "tgnh_comm"}
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(capi.SYMBOLS)
+    assert b"sm_100a" in capi.lib().tgnh_build_info()
+
+
+def test_sass_is_blackwell_native():
+    """The streaming kernels use TMA bulk copies (UBLKCP) and mbarriers (SYNCS) and are built for sm_100a only."""
+    out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+    sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "SYNCS" in sass
+
+
+def _params_error(**kw):
+    s = synth.water_box(8, 2)
+    for k, v in list(kw.items()):
+        if hasattr(s, k):
+            setattr(s, k, v); kw.pop(k)
+    with pytest.raises(capi.TgnhError) as e:
+        capi.Handle(s, **kw)
+    return e.value
+
+
+def test_create_validates_before_touching_the_device():
+    """Argument errors are reported even without a GPU; a valid request without a GPU fails loudly (no CPU fallback)."""
+    assert _params_error(num_nh_chains=0).code == capi.ERR_UNSUPPORTED
+    assert _params_error(padded=30).code == capi.ERR_INVALID_ARGUMENT           # not a multiple of 4 / < N
+    assert _params_error(max_drude_distance=-1.0).code == capi.ERR_INVALID_ARGUMENT
+    assert _params_error(num_temp_groups=40).code == capi.ERR_UNSUPPORTED
+    assert _params_error(force_format=7).code == capi.ERR_INVALID_ARGUMENT
+    import torch
+    if not torch.cuda.is_available():
+        s = synth.water_box(8, 2)
+        with pytest.raises(capi.TgnhError) as e:
+            capi.Handle(s)
+        assert e.value.code == capi.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from openmm_drudenose_b200 import synth
+from oracle import oracle as O
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+mol = 600
+per = mol // world
+shard = synth.water_box(per, 3, first_molecule=rank * per, box_molecules=mol, quantize_masses=True)
+# what tgnh_create does when sharded: local DOF contributions summed over ranks
+o_local = O.Oracle(shard, O.TG)
+# the per-step collective: local 2*KE vectors summed (stands in for ncclAllReduce(double[G+2]))
+ke = torch.from_numpy(o_local.compute_ke2(shard.velocities.copy()))
+dist.all_reduce(ke)
+if rank == 0:
+    whole = synth.water_box(mol, 3, quantize_masses=True)
+    ref = O.Oracle(whole, O.TG).compute_ke2(whole.velocities.copy())
+    np.testing.assert_allclose(ke.numpy(), ref, rtol=1e-12)
+    print("OK")
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_kinetic_energy_reduction_gloo(tmp_path):
+    """world_size 2 on CPU (gloo): molecule-aligned shards + a sum all-reduce of the double[G+2] vector reproduce
+    the single-process kinetic energies — the host-side logic of the sharded path."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "OK" in out.stdout
