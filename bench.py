@@ -112,6 +112,19 @@ def make_system(workload, rank, world):
 # CPU legs (the only place besides tests/ and smoke() that touches oracle/)
 # ---------------------------------------------------------------------------------------------------
 def cpu_run(system, steps, warmup, threads):
+    """Times the reference algorithm on the host.  Preferred: oracle/_ref — the reference's OWN reference-platform
+    sources compiled unmodified against the OpenMM API shim (serial like the original; it implements the dual
+    Nose-Hoover part only and ignores temperature groups, SURVEY.md finding 1).  Otherwise the oracle port
+    (temperature groups + COM group, OpenMP over `threads`).  Returns (seconds, kind, cores)."""
+    from oracle import ref as R
+    if R.available() and not os.environ.get("TGNH_BENCH_FORCE_PORT"):
+        sim = R.ReferenceSim(system)
+        p, v, f = system.positions.copy(), system.velocities.copy(), system.forces.copy()
+        if warmup:
+            sim.step(p, v, f, warmup)
+        t0 = time.perf_counter()
+        sim.step(p, v, f, steps)
+        return time.perf_counter() - t0, "reference", 1
     from oracle import oracle as O
     O.lib().tgnh_oracle_set_threads(threads)
     o = O.Oracle(system, O.TG, constraints=system.constraints)
@@ -122,26 +135,33 @@ def cpu_run(system, steps, warmup, threads):
     o.step(p, v, f, steps)
     dt = time.perf_counter() - t0
     O.lib().tgnh_oracle_set_threads(1)
-    return dt
+    return dt, "port", threads
+
+
+def cpu_sample_system(workload):
+    """Bounded sample of the workload for the CPU legs: 1M particles of the same generator (C4/C5), else the config itself."""
+    if workload in ("c4", "c4-wall", "c5"):
+        return synth.water_box(250_000, 4, box_molecules=C4_MOLECULES, pair_force="frozen_spring" if workload == "c4-wall" else "common")
+    return make_system(workload, 0, 1)
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm on the host cores, all threads, bounded sample."""
+    """--impl reference: the reference's own CPU implementation on the host cores, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    sample_mol = 250_000                       # 1M particles of the C4 generator per step
-    system = synth.water_box(sample_mol, 4, box_molecules=C4_MOLECULES) if args.workload in ("c4", "c4-wall", "c5") else make_system(args.workload, 0, 1)
-    dt = cpu_run(system, args.steps, args.warmup, cores)
+    system = cpu_sample_system(args.workload)
+    dt, kind, cores = cpu_run(system, args.steps, args.warmup, os.cpu_count() or 1)
     value = system.num_particles * args.steps / dt
-    sample = f"{system.num_particles} particles of the same generator x {args.steps} steps ({dt:.2f} s)"
+    what = ("/root/reference platforms/reference + openmmapi sources built against the OpenMM API shim (oracle/_ref), serial"
+            if kind == "reference" else "oracle port (fp64 restatement, OpenMP)")
+    sample = f"{system.num_particles} particles of the same generator x {args.steps} steps ({dt:.2f} s); {what}"
     out = {
         "impl": "reference", "metric": "TGNH step particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -267,12 +287,13 @@ def run_ours(args):
         # CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same generator, 1 core (the
         # reference platform is serial)
         if world == 1 and not args.no_cpu_baseline:
-            sample_mol = 250_000 if args.workload in ("c4", "c4-wall", "c5") else None
-            sysb = synth.water_box(sample_mol, 4, box_molecules=C4_MOLECULES) if sample_mol else system
+            sysb = cpu_sample_system(args.workload)
             bsteps = 20
-            dt = cpu_run(sysb, bsteps, 2, 1)
-            out["cpu_baseline"] = {"value": sysb.num_particles * bsteps / dt, "unit": "particle-steps/s", "cores": 1,
-                                   "kind": "port", "sample": f"{sysb.num_particles} particles of the same generator x {bsteps} steps ({dt:.1f} s), oracle-tg fp64 serial"}
+            dt, kind, cores = cpu_run(sysb, bsteps, 2, 1)
+            out["cpu_baseline"] = {"value": sysb.num_particles * bsteps / dt, "unit": "particle-steps/s", "cores": cores, "kind": kind,
+                                   "sample": f"{sysb.num_particles} particles of the same generator x {bsteps} steps ({dt:.1f} s), "
+                                             + ("the reference platform's own sources (oracle/_ref), serial fp64" if kind == "reference"
+                                                else "oracle-tg port, serial fp64")}
         print(json.dumps(out))
     h.close()
     if comm is not None:

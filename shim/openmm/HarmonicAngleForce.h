@@ -1,0 +1,4 @@
+#ifndef SHIM_OPENMM_FWD_HarmonicAngleForce_H_
+#define SHIM_OPENMM_FWD_HarmonicAngleForce_H_
+#include "openmm/shim_core.h"
+#endif
