@@ -125,6 +125,8 @@ int tgnh_invalidate(tgnh_handle* h);
 /* ---- thermostat state (blocking; they synchronise `stream`) -------------------------------- */
 /* sizes: T = G+2 thermostats (G relative groups, COM group at G, Drude group at G+1) */
 int tgnh_num_thermostats(const tgnh_handle* h);
+/* M, the Nose-Hoover chain length the handle was created with */
+int tgnh_num_nh_chains(const tgnh_handle* h);
 /* 2*KE per thermostat as consumed by the most recent chain update (kineticEnergiesVec, :490) */
 int tgnh_get_kinetic_energies(tgnh_handle* h, void* stream, double* ke2 /*[T]*/);
 /* 0.5 * sum(2KE) cached by the last chain update (KESum, :493-497 / :654-658) */

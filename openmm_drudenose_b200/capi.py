@@ -19,7 +19,7 @@ BOLTZ = 1.380649e-23 * 6.02214076e23 / 1000.0
 # every symbol include/tgnh.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "tgnh_create", "tgnh_destroy", "tgnh_last_error", "tgnh_build_info", "tgnh_half1", "tgnh_half2", "tgnh_flush",
-    "tgnh_step", "tgnh_step_host", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_get_kinetic_energies",
+    "tgnh_step", "tgnh_step_host", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
     "tgnh_kinetic_energy", "tgnh_compute_kinetic_energies", "tgnh_get_chain_state", "tgnh_set_chain_state",
     "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
     "tgnh_comm_create", "tgnh_comm_destroy",
@@ -68,6 +68,7 @@ def lib():
         L.tgnh_step_host.argtypes = [vp, vp, vp, vp, C.c_int, dp]
         L.tgnh_invalidate.argtypes = [vp]
         L.tgnh_num_thermostats.argtypes = [vp]
+        L.tgnh_num_nh_chains.argtypes = [vp]
         L.tgnh_get_kinetic_energies.argtypes = [vp, vp, dp]
         L.tgnh_kinetic_energy.argtypes = [vp, vp, dp]
         L.tgnh_compute_kinetic_energies.argtypes = [vp, vp, vp, dp]

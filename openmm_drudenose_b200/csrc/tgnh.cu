@@ -658,6 +658,7 @@ extern "C" int tgnh_step_host(tgnh_handle* h, void* velm_host, void* posq_host, 
 // thermostat state
 // ------------------------------------------------------------------------------------------------
 extern "C" int tgnh_num_thermostats(const tgnh_handle* h) { return h ? h->T : 0; }
+extern "C" int tgnh_num_nh_chains(const tgnh_handle* h) { return h ? h->M : 0; }
 extern "C" int64_t tgnh_launch_count(const tgnh_handle* h) { return h ? h->launches : 0; }
 
 static int d2h(tgnh_handle* h, void* stream, double* dst, const double* src, size_t n) {

@@ -1,0 +1,24 @@
+#ifndef TGNH_B200_DRUDETGNH_INTEGRATOR_PROXY_H_
+#define TGNH_B200_DRUDETGNH_INTEGRATOR_PROXY_H_
+#include "openmm/internal/windowsExportDrude.h"
+#include "openmm/serialization/SerializationProxy.h"
+
+namespace OpenMM {
+
+/**
+ * XML proxy of DrudeTGNHIntegrator.  Type name and the version-1 properties are the reference's
+ * (/root/reference/serialization/src/DrudeTGNHIntegratorProxy.cpp:40-67).  Version 2 additionally persists what
+ * version 1 silently drops (maxDrudeDistance, useCOMTempGroup, the temperature-group tables); both versions load.
+ */
+class OPENMM_EXPORT_DRUDE DrudeTGNHIntegratorProxy : public SerializationProxy {
+public:
+    DrudeTGNHIntegratorProxy();
+    void serialize(const void* object, SerializationNode& node) const;
+    void* deserialize(const SerializationNode& node) const;
+    /** 1 = byte-compatible with the reference's files; 2 (default) = complete */
+    static int writeVersion;
+};
+
+}  // namespace OpenMM
+
+#endif

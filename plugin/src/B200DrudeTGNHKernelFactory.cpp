@@ -1,0 +1,72 @@
+// Plugin entry points OpenMM's plugin loader looks for, with the names and behaviour of the reference's
+// /root/reference/platforms/cuda/src/CudaDrudeTGNHKernelFactory.cpp:37-66.
+#include "B200DrudeTGNHKernelFactory.h"
+
+#include <exception>
+
+#include "B200DrudeTGNHKernels.h"
+#include "openmm/OpenMMException.h"
+#include "openmm/internal/ContextImpl.h"
+#include "openmm/internal/windowsExport.h"
+
+#ifdef TGNH_WITH_OPENMM
+// Real OpenMM: device arrays come from the CUDA platform's CudaContext (not compilable in this repo's container)
+#include "CudaContext.h"
+#include "CudaPlatform.h"
+namespace OpenMM {
+class CudaContextAccess : public TgnhDeviceAccess {
+public:
+    explicit CudaContextAccess(CudaContext& cu) : cu(cu) {}
+    TgnhDeviceView view() {
+        cu.setAsCurrent();
+        if (cu.getUseDoublePrecision() || cu.getUseMixedPrecision())
+            throw OpenMMException("DrudeTGNH (libtgnh): only the single-precision CUDA layout is implemented; create the Context with Precision=single");
+        TgnhDeviceView v;
+        v.velm = (void*)cu.getVelm().getDevicePointer();
+        v.posq = (void*)cu.getPosq().getDevicePointer();
+        v.force = (const void*)cu.getForce().getDevicePointer();
+        v.paddedNumAtoms = cu.getPaddedNumAtoms();
+        v.forceFormat = TGNH_FORCE_I64_SOA;
+        v.stream = (void*)cu.getCurrentStream();
+        v.device = cu.getDeviceIndex();
+        return v;
+    }
+    void advanceTime(double dt) {
+        cu.setTime(cu.getTime() + dt);
+        cu.setStepCount(cu.getStepCount() + 1);
+        cu.reorderAtoms();
+    }
+private:
+    CudaContext& cu;
+};
+}  // namespace OpenMM
+#endif
+
+using namespace OpenMM;
+
+extern "C" OPENMM_EXPORT void registerPlatforms() {}
+
+extern "C" OPENMM_EXPORT void registerKernelFactories() {
+    try {
+        Platform& platform = Platform::getPlatformByName("CUDA");
+        platform.registerKernelFactory(IntegrateDrudeTGNHStepKernel::Name(), new B200DrudeTGNHKernelFactory());
+    } catch (const std::exception&) {
+        // no CUDA platform in this process: nothing to register (the reference swallows this too, :44-48)
+    }
+}
+
+extern "C" OPENMM_EXPORT void registerDrudeTGNHCudaKernelFactories() { registerKernelFactories(); }
+
+KernelImpl* B200DrudeTGNHKernelFactory::createKernelImpl(std::string name, const Platform& platform, ContextImpl& context) const {
+    if (name != IntegrateDrudeTGNHStepKernel::Name())
+        throw OpenMMException((std::string("Tried to create kernel with illegal kernel name '") + name + "'").c_str());
+#ifdef TGNH_WITH_OPENMM
+    CudaContext& cu = *static_cast<CudaPlatform::PlatformData*>(context.getPlatformData())->contexts[0];
+    return new B200IntegrateDrudeTGNHStepKernel(name, platform, *new CudaContextAccess(cu));   // lives as long as the context
+#else
+    // shim build: the platform data IS the device access object (plugin/tests/ShimCudaPlatform.h)
+    TgnhDeviceAccess* access = static_cast<TgnhDeviceAccess*>(context.getPlatformData());
+    if (access == NULL) throw OpenMMException("DrudeTGNH: the CUDA platform holds no device arrays for this context");
+    return new B200IntegrateDrudeTGNHStepKernel(name, platform, *access);
+#endif
+}

@@ -1,0 +1,60 @@
+#ifndef TGNH_B200_KERNELS_H_
+#define TGNH_B200_KERNELS_H_
+/*
+ * IntegrateDrudeTGNHStepKernel on B200: the KernelImpl OpenMM's CUDA platform instantiates for
+ * "IntegrateDrudeTGNHStep".  It replaces CudaIntegrateDrudeTGNHStepKernel
+ * (/root/reference/platforms/cuda/src/CudaDrudeTGNHKernels.{h,cpp}): no runtime-compiled kernel strings, no host
+ * chain, no per-step D2H/H2D — every call below forwards to the C-ABI of libtgnh.so (include/tgnh.h).
+ */
+#include <vector>
+
+#include "../../include/tgnh.h"
+#include "openmm/DrudeTGNHKernels.h"
+
+namespace OpenMM {
+
+/** Device arrays of the platform the kernel runs on, in OpenMM's CUDA layouts. */
+struct TgnhDeviceView {
+    void* velm;          // float4[paddedNumAtoms]   cu.getVelm()
+    void* posq;          // float4[paddedNumAtoms]   cu.getPosq()
+    const void* force;   // SoA [3][paddedNumAtoms]  cu.getForce()
+    int paddedNumAtoms;  // cu.getPaddedNumAtoms()
+    int forceFormat;     // TGNH_FORCE_I64_SOA for OpenMM's fixed-point buffer
+    void* stream;        // cudaStream_t the platform launches on
+    int device;          // CUDA device ordinal
+};
+
+/** How the kernel reaches the platform: implemented over CudaContext with a real OpenMM, over the shim platform in tests. */
+class TgnhDeviceAccess {
+public:
+    virtual ~TgnhDeviceAccess() {}
+    virtual TgnhDeviceView view() = 0;
+    virtual void advanceTime(double dt) = 0;     // cu.setTime / cu.setStepCount (CudaDrudeTGNHKernels.cpp:405-406)
+};
+
+class B200IntegrateDrudeTGNHStepKernel : public IntegrateDrudeTGNHStepKernel {
+public:
+    B200IntegrateDrudeTGNHStepKernel(std::string name, const Platform& platform, TgnhDeviceAccess& device)
+        : IntegrateDrudeTGNHStepKernel(name, platform), device(device), handle(NULL), deferScale(false) {}
+    ~B200IntegrateDrudeTGNHStepKernel();
+    void initialize(const System& system, const DrudeTGNHIntegrator& integrator, const DrudeForce& force);
+    void execute(ContextImpl& context, const DrudeTGNHIntegrator& integrator);
+    double computeKineticEnergy(ContextImpl& context, const DrudeTGNHIntegrator& integrator, bool isKESumValid);
+    void stateChanged();
+    void finishSteps(ContextImpl& context);
+    /** thermostat state for checkpointing (the reference keeps it in host vectors and never saves it) */
+    void getChainState(std::vector<double>& eta, std::vector<double>& etaDot, std::vector<double>& etaDotDot);
+    void setChainState(const std::vector<double>& eta, const std::vector<double>& etaDot, const std::vector<double>& etaDotDot);
+    /** Leave the second half-step's scaling pending between the steps of one step(n) call.  Only safe when nothing else
+     *  (barostat, CMMotionRemover, reporters) touches velocities between steps; off by default. */
+    void setDeferScaling(bool on) { deferScale = on; }
+private:
+    void check(int rc) const;
+    TgnhDeviceAccess& device;
+    tgnh_handle* handle;
+    bool deferScale;
+};
+
+}  // namespace OpenMM
+
+#endif

@@ -1,0 +1,94 @@
+// TEST INFRASTRUCTURE — a "CUDA" platform for the OpenMM API shim: owns device arrays in OpenMM's CUDA layouts
+// (float4 velm / posq, SoA forces), moves state between them and the Context's host copies, and evaluates the shim's
+// host force model into the device force buffer.  It lets the real plugin stack (DrudeTGNHIntegrator -> KernelImpl ->
+// C-ABI -> sm_100a kernels) run end to end without OpenMM.
+#ifndef TGNH_SHIM_CUDA_PLATFORM_H_
+#define TGNH_SHIM_CUDA_PLATFORM_H_
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <vector>
+
+#include "../src/B200DrudeTGNHKernels.h"
+#include "openmm/OpenMMException.h"
+#include "openmm/internal/ContextImpl.h"
+
+namespace OpenMM {
+
+class ShimCudaPlatform : public Platform {
+public:
+    class Data : public TgnhDeviceAccess {
+    public:
+        Data(ContextImpl& c, int forceFormat) : ctx(c), n(c.getSystem().getNumParticles()), padded(((n + 31) / 32) * 32), forceFormat(forceFormat),
+              velm(NULL), posq(NULL), force(NULL), time(0.0), steps(0) {
+            int count = 0;
+            if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw OpenMMException("ShimCudaPlatform: no CUDA device");
+            const size_t fbytes = (size_t)3 * padded * (forceFormat == TGNH_FORCE_I64_SOA ? 8 : 4);
+            if (cudaMalloc(&velm, (size_t)padded * 16) || cudaMalloc(&posq, (size_t)padded * 16) || cudaMalloc(&force, fbytes))
+                throw OpenMMException("ShimCudaPlatform: cudaMalloc failed");
+            cudaMemset(velm, 0, (size_t)padded * 16); cudaMemset(posq, 0, (size_t)padded * 16); cudaMemset(force, 0, fbytes);
+            hv.assign((size_t)padded * 4, 0.f); hx.assign((size_t)padded * 4, 0.f);
+        }
+        ~Data() { cudaFree(velm); cudaFree(posq); cudaFree(force); }
+        TgnhDeviceView view() {
+            TgnhDeviceView v = {velm, posq, force, padded, forceFormat, NULL, 0};
+            return v;
+        }
+        void advanceTime(double dt) { time += dt; steps++; ctx.time = time; }
+        void upload() {
+            for (int i = 0; i < n; i++) {
+                const double m = ctx.getSystem().getParticleMass(i);
+                for (int c = 0; c < 3; c++) { hv[4 * i + c] = (float)ctx.shimVelocities()[i][c]; hx[4 * i + c] = (float)ctx.shimPositions()[i][c]; }
+                hv[4 * i + 3] = m == 0.0 ? 0.f : (float)(1.0 / m);
+            }
+            cudaMemcpy(velm, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(posq, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice);
+        }
+        void download() {
+            cudaMemcpy(hv.data(), velm, hv.size() * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(hx.data(), posq, hx.size() * 4, cudaMemcpyDeviceToHost);
+            for (int i = 0; i < n; i++)
+                for (int c = 0; c < 3; c++) { ctx.shimVelocities()[i][c] = hv[4 * i + c]; ctx.shimPositions()[i][c] = hx[4 * i + c]; }
+        }
+        /** forces: host model on the downloaded positions, written into the device buffer in the platform's format */
+        void forcesOnDevice(const ShimForceModel& model) {
+            download();
+            model(ctx.shimPositions(), ctx.shimForces());
+            if (forceFormat == TGNH_FORCE_I64_SOA) {
+                std::vector<long long> f((size_t)3 * padded, 0);
+                for (int i = 0; i < n; i++) for (int c = 0; c < 3; c++) f[(size_t)c * padded + i] = (long long)llrint(ctx.shimForces()[i][c] * 4294967296.0);
+                cudaMemcpy(force, f.data(), f.size() * 8, cudaMemcpyHostToDevice);
+            } else {
+                std::vector<float> f((size_t)3 * padded, 0.f);
+                for (int i = 0; i < n; i++) for (int c = 0; c < 3; c++) f[(size_t)c * padded + i] = (float)ctx.shimForces()[i][c];
+                cudaMemcpy(force, f.data(), f.size() * 4, cudaMemcpyHostToDevice);
+            }
+        }
+    private:
+        ContextImpl& ctx;
+        int n, padded, forceFormat;
+        void *velm, *posq, *force;
+        double time;
+        int steps;
+        std::vector<float> hv, hx;
+    };
+    explicit ShimCudaPlatform(int forceFormat = TGNH_FORCE_I64_SOA) : forceFormat(forceFormat) {}
+    const std::string& getName() const { static const std::string n = "CUDA"; return n; }
+    void contextCreated(ContextImpl& context, const std::map<std::string, std::string>&) const {
+        Data* d = new Data(context, forceFormat);
+        context.setPlatformData(static_cast<TgnhDeviceAccess*>(d));
+        context.shimUpload = [d]() { d->upload(); };
+        context.shimDownload = [d]() { d->download(); };
+    }
+    void contextDestroyed(ContextImpl& context) const { delete static_cast<Data*>(static_cast<TgnhDeviceAccess*>(context.getPlatformData())); }
+    /** route the context's force model through the device buffers */
+    static void installForceModel(ContextImpl& context, ShimForceModel model) {
+        Data* d = static_cast<Data*>(static_cast<TgnhDeviceAccess*>(context.getPlatformData()));
+        context.shimForcesOnDevice = [d, model]() { d->forcesOnDevice(model); };
+    }
+private:
+    int forceFormat;
+};
+
+}  // namespace OpenMM
+#endif

@@ -226,8 +226,8 @@ typedef std::function<void(const std::vector<Vec3>& positions, std::vector<Vec3>
 class ContextImpl {
 public:
     ContextImpl(Context& owner, const System& system, Integrator& integrator, Platform* platform)
-        : owner(owner), system(system), integrator(integrator), platform(platform), platformData(NULL), lastForceGroups(-1),
-          time(0), forceCalls(0) {
+        : time(0), owner(owner), system(system), integrator(integrator), platform(platform), platformData(NULL), lastForceGroups(-1),
+          forceCalls(0) {
         int n = system.getNumParticles();
         positions.assign(n, Vec3()); velocities.assign(n, Vec3()); forces.assign(n, Vec3());
     }
