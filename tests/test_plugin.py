@@ -74,3 +74,36 @@ def test_plugin_single_pair_hard_wall(cuda):
         sim.step(p, v, f, 10)
         assert np.linalg.norm(p[0] - p[1]) <= sp.max_drude_distance * (1 + 1e-4)
     sim.close()
+
+
+def test_python_module_surface():
+    """`drudetgnhplugin` (pybind11 stand-in for the SWIG module): class, method list, Python-side defaults of
+    python/drudetgnhplugin.i:60-92 — note useDrudeNHChains defaults to True in Python, False in C++ (SURVEY.md finding 3)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "plugin", "python"))
+    import drudetgnhplugin as dp
+    integ = dp.DrudeTGNHIntegrator(300.0, 0.1, 1.0, 0.005, 0.001, 20)          # the README's call: 6th argument = drudeStepsPerRealStep
+    assert float(integ.getTemperature()) == 300.0 and float(integ.getDrudeCouplingTime()) == 0.005
+    assert integ.getDrudeStepsPerRealStep() == 20 and integ.getNumNHChains() == 1
+    assert integ.getUseDrudeNHChains() == 1 and integ.getUseCOMTempGroup() == 1
+    integ.setMaxDrudeDistance(0.02)
+    assert float(integ.getMaxDrudeDistance()) == 0.02
+    with pytest.raises(dp.OpenMMException, match="cannot be negative"):
+        integ.setMaxDrudeDistance(-0.1)
+    methods = ["getTemperature", "setTemperature", "getCouplingTime", "setCouplingTime", "getDrudeTemperature", "setDrudeTemperature",
+               "getDrudeCouplingTime", "setDrudeCouplingTime", "getMaxDrudeDistance", "setMaxDrudeDistance", "step",
+               "getDrudeStepsPerRealStep", "setDrudeStepsPerRealStep", "getNumNHChains", "setNumNHChains", "getUseDrudeNHChains",
+               "setUseDrudeNHChains", "getUseCOMTempGroup", "setUseCOMTempGroup", "getNumTempGroups", "addTempGroup",
+               "addParticleTempGroup", "setParticleTempGroup", "getParticleTempGroup"]
+    assert all(hasattr(integ, m) for m in methods)
+    # temperature groups: the first addTempGroup() returns 0; the README's "default group 0, added group 1" recipe throws (D11)
+    assert integ.addTempGroup() == 0
+    with pytest.raises(dp.OpenMMException, match="Index out of range"):
+        integ.addParticleTempGroup(1)
+    assert integ.addTempGroup() == 1
+    assert integ.addParticleTempGroup(1) == 0 and integ.getParticleTempGroup(0) == 1
+    with pytest.raises(dp.OpenMMException, match="not bound to a context"):
+        integ.step(1)
+    xml = dp.serialize(integ)
+    copy = dp.deserialize(xml)
+    assert copy.getNumTempGroups() == 2 and copy.getParticleTempGroup(0) == 1 and float(copy.getMaxDrudeDistance()) == 0.02
