@@ -159,11 +159,15 @@ class Handle:
         self.T = lib().tgnh_num_thermostats(h)
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().tgnh_destroy(self.h)
-            self.h = None
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.tgnh_destroy(self.h)
+        self.h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown
+            pass
 
     # ---- the step ----
     def half1(self, velm, posq, force, stream=0):
