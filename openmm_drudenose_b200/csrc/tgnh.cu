@@ -517,6 +517,8 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     a.applyScale = applyScale;
     a.useLocalKE = sharded(h) ? 1 : 0;
     a.reverse = (prof == KIND_B) ? 1 : 0;   // first-half and reduce/flush launches walk forward, second-half backward
+    static const int tunePrefetch = getenv("TGNH_TUNE_PREFETCH") ? atoi(getenv("TGNH_TUNE_PREFETCH")) : 0;                  // experiments only
+    a.prologuePrefetch = (prof == KIND_A) ? tunePrefetch : 0;
     static const int tuneReverse = getenv("TGNH_TUNE_REVERSE") ? atoi(getenv("TGNH_TUNE_REVERSE")) : -1;   // experiments only
     if (tuneReverse == 0) a.reverse = 0;
     if (tuneReverse == 2) a.reverse = (prof == KIND_B) ? 0 : 1;

@@ -39,7 +39,6 @@ namespace tgnh {
 
 enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2, KIND_BU = 3 };
 constexpr int NWARPS = TILE / 32;
-constexpr int PF_DIST = 0;         // L2 prefetch distance in tiles (per CTA), 0 = off
 constexpr int TLIST_CAP = 128;     // tile bounds cached in shared memory per CTA (later tiles are looked up in global memory)
 
 struct StreamArgs {
@@ -59,6 +58,7 @@ struct StreamArgs {
     int applyScale;           // KIND_KE: scale velocities by scaleA and write them back
     int useLocalKE;           // sharded: reduce into chain.ke2Local (all-reduced into ke2 afterwards)
     int reverse;              // walk the tiles from the last to the first (see "L2 hand-over" below)
+    int prologuePrefetch;     // tiles per CTA whose read-only inputs are prefetched into L2 before griddepcontrol.wait
     double* partials;         // [gridDim.x][T]
     unsigned int* ticket;     // last-CTA-done counter (self-resetting)
     ChainView chain;
@@ -221,24 +221,16 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
     for (int it = tid; it < myTiles && it < TLIST_CAP; it += TILE) tlist[it] = tile_bounds(it);   // static tables: safe before pdl_wait
     if (L::HAS_KE)
         for (int g = 0; g < T; g++) ske[g * TILE + tid] = 0.0;
-    pdl_wait();                                         // everything below reads what earlier launches wrote
-    if (tid < T) {
-        const double sg = (KIND == KIND_B || KIND == KIND_BU) ? 1.0 : a.chain.scaleA[tid];
-        ssq[tid] = sg * sg;
-        seps[tid] = (float)(sg - 1.0);
-    }
     __syncthreads();
 
     const uint64_t polOnce = policy_evict_first();
-    const uint64_t polKeep = policy_evict_last();
-    // L2 prefetch of the tile this CTA will request PF_DIST requests from now: the HBM latency (2-3 us under load) is
-    // then covered by L2 capacity instead of shared-memory stages, of which only 3-4 fit per CTA
+    // L2 prefetch of a later tile's read-only inputs (posq is only touched by first-half launches, forces and
+    // descriptors are never written by this library): used in the prologue, while HBM is idle during the chain launch
     auto prefetch = [&](int it) {
-        if (PF_DIST == 0 || it >= myTiles) return;
+        if (it >= myTiles) return;
         const int4 b = it < TLIST_CAP ? tlist[it] : tile_bounds(it);
         const int start = b.x, end = b.y;
         const int n = end - start, a0 = start & ~3, na = ((end + 3) & ~3) - a0;
-        if (KIND == KIND_KE) bulk_prefetch_l2(a.velm + start, n * 16);   // velm of the other kinds was just written by the previous launch
         if (St::HAS_X) bulk_prefetch_l2(a.posq + start, n * 16);
         if (St::HAS_F) {
             const unsigned char* f = static_cast<const unsigned char*>(a.force);
@@ -246,35 +238,49 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
         }
         bulk_prefetch_l2(a.desc + a0, na * 4);
     };
-    // Request tile `it` of this CTA into its stage (thread 0 only).
-    auto issue = [&](int it) {
+    // Request tile `it` of this CTA into its stage (thread 0 only).  `parts`: 1 = everything but velm (arms the barrier
+    // with the full byte count), 2 = velm, 3 = both.  The split exists for the prologue: velm is the only input the
+    // previous launch writes, so the rest can be requested before griddepcontrol.wait, while the chain launch that
+    // precedes a first-half launch is still running.
+    auto issue = [&](int it, int parts) {
         const int4 b = it < TLIST_CAP ? tlist[it] : tile_bounds(it);
         const int start = b.x, end = b.y, r0 = b.z, r1 = b.w;
         const int n = end - start, a0 = start & ~3, na = ((end + 3) & ~3) - a0;
         unsigned char* st = smem + (it % NS) * St::BYTES;
         uint64_t* bar = &full[it % NS];
-        *reinterpret_cast<int4*>(st + St::OFF_HDR) = make_int4(start, n, r0, r1 - r0);
-        uint32_t bytes = n * 16 + na * 4;
-        const int ra0 = r0 & ~3, rna = ((r1 + 1 + 3) & ~3) - ra0;     // residues r0..r1 inclusive (r1 = end marker)
-        if (St::HAS_R) bytes += rna * 4;
-        if (St::HAS_X) bytes += n * 16;
-        if (St::HAS_F) bytes += 3 * na * St::FBYTES;
-        mbar_arrive_expect_tx(bar, bytes);
-        bulk_g2s(st + St::OFF_V, a.velm + start, n * 16, bar, polOnce);
-        if (St::HAS_X) bulk_g2s(st + St::OFF_X, a.posq + start, n * 16, bar, polOnce);
-        if (St::HAS_F) {
-            const unsigned char* f = static_cast<const unsigned char*>(a.force);
-            for (int c = 0; c < 3; c++)
-                bulk_g2s(st + St::OFF_F + c * PADW * St::FBYTES, f + ((size_t)c * a.paddedN + a0) * St::FBYTES, na * St::FBYTES, bar,
-                         polOnce);
+        if (parts & 1) {
+            *reinterpret_cast<int4*>(st + St::OFF_HDR) = make_int4(start, n, r0, r1 - r0);
+            uint32_t bytes = n * 16 + na * 4;
+            const int ra0 = r0 & ~3, rna = ((r1 + 1 + 3) & ~3) - ra0;     // residues r0..r1 inclusive (r1 = end marker)
+            if (St::HAS_R) bytes += rna * 4;
+            if (St::HAS_X) bytes += n * 16;
+            if (St::HAS_F) bytes += 3 * na * St::FBYTES;
+            mbar_arrive_expect_tx(bar, bytes);
+            if (St::HAS_X) bulk_g2s(st + St::OFF_X, a.posq + start, n * 16, bar, polOnce);
+            if (St::HAS_F) {
+                const unsigned char* f = static_cast<const unsigned char*>(a.force);
+                for (int c = 0; c < 3; c++)
+                    bulk_g2s(st + St::OFF_F + c * PADW * St::FBYTES, f + ((size_t)c * a.paddedN + a0) * St::FBYTES, na * St::FBYTES, bar,
+                             polOnce);
+            }
+            bulk_g2s(st + St::OFF_D, a.desc + a0, na * 4, bar, polOnce);
+            if (St::HAS_R) bulk_g2s(st + St::OFF_R, a.resStart + ra0, rna * 4, bar, polOnce);
         }
-        bulk_g2s(st + St::OFF_D, a.desc + a0, na * 4, bar, polOnce);
-        if (St::HAS_R) bulk_g2s(st + St::OFF_R, a.resStart + ra0, rna * 4, bar, polOnce);
+        if (parts & 2) bulk_g2s(st + St::OFF_V, a.velm + start, n * 16, bar, polOnce);
     };
     if (tid == 0) {
-        for (int it = 0; it < NS && it < myTiles; it++) issue(it);
-        for (int it = NS; it < NS + PF_DIST; it++) prefetch(it);
+        for (int it = 0; it < NS && it < myTiles; it++) issue(it, 1);
+        for (int it = NS; it < NS + a.prologuePrefetch; it++) prefetch(it);
     }
+    pdl_wait();                                         // everything below reads what earlier launches wrote
+    if (tid == 0)
+        for (int it = 0; it < NS && it < myTiles; it++) issue(it, 2);
+    if (tid < T) {
+        const double sg = (KIND == KIND_B || KIND == KIND_BU) ? 1.0 : a.chain.scaleA[tid];
+        ssq[tid] = sg * sg;
+        seps[tid] = (float)(sg - 1.0);
+    }
+    __syncthreads();
 
     const bool doScale = (KIND == KIND_A) || (KIND == KIND_KE && a.applyScale);
     const float eCOM = doScale ? seps[G] : 0.0f;
@@ -447,9 +453,8 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stg]);
         if (tid == 0 && it + NS < myTiles) {
-            prefetch(it + NS + PF_DIST);
             mbar_wait(&empty[stg], phase);
-            issue(it + NS);
+            issue(it + NS, 3);
         }
     }
     pdl_launch_dependents();

