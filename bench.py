@@ -201,7 +201,9 @@ def run_ours(args):
     h_force[:, :n] = torch.from_numpy(np.ascontiguousarray(system.forces.T, np.float32))
     velm, posq, force = h_velm.to(dev), h_posq.to(dev), h_force.to(dev)
     h = capi.Handle(system, padded=padded, device=local, comm=comm)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(device=dev)            # the step runs on its own (non-default) stream
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     def barrier():
         torch.cuda.synchronize()

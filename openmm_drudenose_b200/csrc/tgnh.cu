@@ -617,8 +617,8 @@ extern "C" int tgnh_step(tgnh_handle* h, void* stream, void* velm, void* posq, c
     if (int rc = ensure_ke(h, s, velm, CHAIN_FIRST)) return rc;
     for (int i = 0; i < nsteps; i++) {
         if (int rc = launch_stream(h, s, KIND_A, velm, posq, force, 1, CHAIN_NONE)) return rc;
-        // the thermostat half-step that ends step i and the one that begins step i+1 run back to back in the
-        // tail of the same launch; their scale factors are applied together by the next KIND_A pass
+        // the thermostat half-step that ends step i and the one that begins step i+1 run back to back in one
+        // chain launch; their scale factors are applied together by the next first-half pass
         const int mode = (i + 1 < nsteps) ? CHAIN_SECOND_FIRST : CHAIN_SECOND;
         if (int rc = launch_stream(h, s, KIND_B, velm, nullptr, force, 0, mode)) return rc;
     }
