@@ -52,6 +52,8 @@ enum { TGNH_FORCE_F32_SOA = 0, TGNH_FORCE_I64_SOA = 1 };
 /* flags for tgnh_half2 */
 enum {
     TGNH_HALF2_DEFAULT = 0,
+    TGNH_HALF2_KICK_ONLY = 2,        /* constrained systems: only the half kick; the caller applies OpenMM's velocity
+                                        constraints and then calls tgnh_thermostat */
     TGNH_HALF2_DEFER_SCALE = 1       /* leave the second thermostat half-step's velocity scaling pending; it is folded
                                         into the next tgnh_half1 (or applied by tgnh_flush).  Only legal when nothing
                                         reads or writes velm in between. */
@@ -108,6 +110,16 @@ const char* tgnh_build_info(void);
 /* First half: thermostat half-step (KE -> chain -> scale), half kick, drift, hard wall.
  * = CudaDrudeTGNHKernels.cpp:336-376 without the OpenMM constraint call at :363. */
 int tgnh_half1(tgnh_handle* h, void* stream, void* velm, void* posq, const void* force);
+/* The first half split around OpenMM's position constraints (systems with SETTLE / SHAKE / CCMA):
+ *   tgnh_half1_kick   thermostat half-step + half kick; writes pos_delta = (dt*v, 0) float4[paddedN], the layout of
+ *                     integration.getPosDelta() in single precision            (= :336-360)
+ *   ... caller: integration.applyConstraints(tol) on pos_delta                 (= :363)
+ *   tgnh_half1_drift  x += pos_delta, v = pos_delta / dt, hard wall            (= :366-376) */
+int tgnh_half1_kick(tgnh_handle* h, void* stream, void* velm, const void* force, void* pos_delta);
+int tgnh_half1_drift(tgnh_handle* h, void* stream, void* velm, void* posq, void* pos_delta);
+/* Thermostat half-step on the velocities as they are (after tgnh_half2(KICK_ONLY) + the caller's velocity constraints):
+ * kinetic energies, chain update, scaling (= :394-402).  flags: TGNH_HALF2_DEFER_SCALE or 0. */
+int tgnh_thermostat(tgnh_handle* h, void* stream, void* velm, int flags);
 /* Second half: half kick with the new forces, thermostat half-step.  = :384-402 without :391. */
 int tgnh_half2(tgnh_handle* h, void* stream, void* velm, const void* force, int flags);
 /* Apply a pending (deferred) velocity scaling so that velm is what the reference would hold. */

@@ -12,13 +12,14 @@ LIB_PATH = os.path.join(_HERE, "libtgnh.so")
 
 OK, ERR_INVALID_ARGUMENT, ERR_TEMP_GROUP, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE = range(7)
 FORCE_F32_SOA, FORCE_I64_SOA = 0, 1
-HALF2_DEFAULT, HALF2_DEFER_SCALE = 0, 1
+HALF2_DEFAULT, HALF2_DEFER_SCALE, HALF2_KICK_ONLY = 0, 1, 2
 UNIQUE_ID_BYTES = 128
 BOLTZ = 1.380649e-23 * 6.02214076e23 / 1000.0
 
 # every symbol include/tgnh.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "tgnh_create", "tgnh_destroy", "tgnh_last_error", "tgnh_build_info", "tgnh_half1", "tgnh_half2", "tgnh_flush",
+    "tgnh_create", "tgnh_destroy", "tgnh_last_error", "tgnh_build_info", "tgnh_half1", "tgnh_half1_kick", "tgnh_half1_drift",
+    "tgnh_thermostat", "tgnh_half2", "tgnh_flush",
     "tgnh_step", "tgnh_step_host", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
     "tgnh_kinetic_energy", "tgnh_compute_kinetic_energies", "tgnh_get_chain_state", "tgnh_set_chain_state",
     "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
@@ -63,6 +64,9 @@ def lib():
         L.tgnh_build_info.restype = C.c_char_p
         L.tgnh_half1.argtypes = [vp, vp, vp, vp, vp]
         L.tgnh_half2.argtypes = [vp, vp, vp, vp, C.c_int]
+        L.tgnh_half1_kick.argtypes = [vp, vp, vp, vp, vp]
+        L.tgnh_half1_drift.argtypes = [vp, vp, vp, vp, vp]
+        L.tgnh_thermostat.argtypes = [vp, vp, vp, C.c_int]
         L.tgnh_flush.argtypes = [vp, vp, vp]
         L.tgnh_step.argtypes = [vp, vp, vp, vp, vp, C.c_int]
         L.tgnh_step_host.argtypes = [vp, vp, vp, vp, C.c_int, dp]
@@ -172,6 +176,15 @@ class Handle:
     # ---- the step ----
     def half1(self, velm, posq, force, stream=0):
         check(lib().tgnh_half1(self.h, stream, velm, posq, force))
+
+    def half1_kick(self, velm, force, pos_delta, stream=0):
+        check(lib().tgnh_half1_kick(self.h, stream, velm, force, pos_delta))
+
+    def half1_drift(self, velm, posq, pos_delta, stream=0):
+        check(lib().tgnh_half1_drift(self.h, stream, velm, posq, pos_delta))
+
+    def thermostat(self, velm, flags=HALF2_DEFAULT, stream=0):
+        check(lib().tgnh_thermostat(self.h, stream, velm, flags))
 
     def half2(self, velm, force, flags=HALF2_DEFAULT, stream=0):
         check(lib().tgnh_half2(self.h, stream, velm, force, flags))

@@ -141,8 +141,8 @@ struct tgnh_handle {
     unsigned int* dTicket = nullptr;
     ChainView chain{};
     size_t chainDoubles = 0;
-    int gridA = 0, gridB = 0, gridKE = 0;
-    int smemA = 0, smemB = 0, smemKE = 0;
+    int gridA = 0, gridB = 0, gridKE = 0, gridA1 = 0, gridA2 = 0;
+    int smemA = 0, smemB = 0, smemKE = 0, smemA1 = 0, smemA2 = 0;
     // host copies of the thermostat parameters
     std::vector<double> dof, nkbt, etaMass;
     // state machine
@@ -176,6 +176,8 @@ static StreamKernel pick(int kind, int ffmt, bool useCOM, bool hardwall) {
         case KIND_A: return ffmt ? pick2<KIND_A, 1>(useCOM, hardwall) : pick2<KIND_A, 0>(useCOM, hardwall);
         case KIND_B: return ffmt ? pick2<KIND_B, 1>(useCOM, false) : pick2<KIND_B, 0>(useCOM, false);
         case KIND_BU: return ffmt ? pick2<KIND_BU, 1>(useCOM, false) : pick2<KIND_BU, 0>(useCOM, false);
+        case KIND_A1: return ffmt ? pick2<KIND_A1, 1>(useCOM, false) : pick2<KIND_A1, 0>(useCOM, false);
+        case KIND_A2: return hardwall ? tgnh_stream_kernel<KIND_A2, 0, false, true> : tgnh_stream_kernel<KIND_A2, 0, false, false>;
         default: return pick2<KIND_KE, 0>(useCOM, false);
     }
 }
@@ -188,6 +190,11 @@ static int smem_bytes(int kind, int ffmt, bool useCOM, int T) {
         case KIND_B:
             if (ffmt) return useCOM ? SmemLayout<KIND_B, 1, true>::bytes(T) : SmemLayout<KIND_B, 1, false>::bytes(T);
             return useCOM ? SmemLayout<KIND_B, 0, true>::bytes(T) : SmemLayout<KIND_B, 0, false>::bytes(T);
+        case KIND_A1:
+            if (ffmt) return useCOM ? SmemLayout<KIND_A1, 1, true>::bytes(T) : SmemLayout<KIND_A1, 1, false>::bytes(T);
+            return useCOM ? SmemLayout<KIND_A1, 0, true>::bytes(T) : SmemLayout<KIND_A1, 0, false>::bytes(T);
+        case KIND_A2:
+            return SmemLayout<KIND_A2, 0, false>::bytes(T);
         case KIND_BU:
             if (ffmt) return useCOM ? SmemLayout<KIND_BU, 1, true>::bytes(T) : SmemLayout<KIND_BU, 1, false>::bytes(T);
             return useCOM ? SmemLayout<KIND_BU, 0, true>::bytes(T) : SmemLayout<KIND_BU, 0, false>::bytes(T);
@@ -449,10 +456,13 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
 
     int rc;
     if ((rc = configure_kernel(h, KIND_A, &h->gridA, &h->smemA)) || (rc = configure_kernel(h, h->kindB, &h->gridB, &h->smemB)) ||
-        (rc = configure_kernel(h, KIND_KE, &h->gridKE, &h->smemKE)))
+        (rc = configure_kernel(h, KIND_KE, &h->gridKE, &h->smemKE)) || (rc = configure_kernel(h, KIND_A1, &h->gridA1, &h->smemA1)) ||
+        (rc = configure_kernel(h, KIND_A2, &h->gridA2, &h->smemA2)))
         return bail(rc);
     int maxGrid = h->gridA > h->gridB ? h->gridA : h->gridB;
     if (h->gridKE > maxGrid) maxGrid = h->gridKE;
+    if (h->gridA1 > maxGrid) maxGrid = h->gridA1;
+    if (h->gridA2 > maxGrid) maxGrid = h->gridA2;
     if (!dmalloc((void**)&h->dPartials, (size_t)maxGrid * T * 8)) return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the partial sums failed"));
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(TGNH_ERR_CUDA, "device error during tgnh_create: %s", cudaGetErrorString(cudaGetLastError())));
     *out = h;
@@ -503,12 +513,14 @@ static int launch_chain(tgnh_handle* h, cudaStream_t s, int mode) {
 
 // one streaming launch; for the reducing kinds (KIND_B / KIND_KE) followed by the all-reduce of the
 // kinetic-energy vector when sharded and by the chain update `chainMode` asks for
-static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, void* posq, const void* force, int applyScale, int chainMode) {
+static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, void* posq, const void* force, int applyScale, int chainMode,
+                         void* posDelta = nullptr) {
     StreamArgs a;
-    a.velm = (float4*)velm; a.posq = (float4*)posq; a.force = force;
+    a.velm = (float4*)velm; a.posq = (float4*)posq; a.force = force; a.posDelta = (float4*)posDelta;
     a.desc = h->dDesc; a.tileStart = h->dTileStart; a.numTiles = h->numTiles; a.paddedN = h->paddedN;
     a.resStart = h->dResStart; a.tileFirstRes = h->dTileFirstRes;
-    const int prof = kind;               // profiling slot (first half / second half / reduce)
+    const bool firstHalf = kind == KIND_A || kind == KIND_A1 || kind == KIND_A2;
+    const int prof = firstHalf ? KIND_A : kind;      // profiling slot (first half / second half / reduce)
     if (kind == KIND_B) kind = h->kindB;
     a.dt = (float)h->dt;
     a.fscale = (float)(h->ffmt == TGNH_FORCE_I64_SOA ? 0.5 * h->dt / 4294967296.0 : 0.5 * h->dt);   // CudaDrudeTGNHKernels.cpp:295
@@ -523,8 +535,8 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     if (tuneReverse == 0) a.reverse = 0;
     if (tuneReverse == 2) a.reverse = (prof == KIND_B) ? 0 : 1;
     a.partials = h->dPartials; a.ticket = h->dTicket; a.chain = h->chain;
-    const int grid = prof == KIND_A ? h->gridA : prof == KIND_B ? h->gridB : h->gridKE;
-    const int smem = prof == KIND_A ? h->smemA : prof == KIND_B ? h->smemB : h->smemKE;
+    const int grid = kind == KIND_A1 ? h->gridA1 : kind == KIND_A2 ? h->gridA2 : prof == KIND_A ? h->gridA : prof == KIND_B ? h->gridB : h->gridKE;
+    const int smem = kind == KIND_A1 ? h->smemA1 : kind == KIND_A2 ? h->smemA2 : prof == KIND_A ? h->smemA : prof == KIND_B ? h->smemB : h->smemKE;
     StreamKernel k = pick(kind, h->ffmt, h->useCOM, h->hardwall);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
@@ -584,10 +596,46 @@ extern "C" int tgnh_half1(tgnh_handle* h, void* stream, void* velm, void* posq, 
     return launch_stream(h, s, KIND_A, velm, posq, force, 1, CHAIN_NONE);   // :351-376
 }
 
+extern "C" int tgnh_half1_kick(tgnh_handle* h, void* stream, void* velm, const void* force, void* pos_delta) {
+    if (int rc = check_ptrs(h, velm, pos_delta, force, true, true)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (int rc = ensure_ke(h, s, velm, CHAIN_FIRST)) return rc;
+    h->scalePending = false;
+    h->keValid = false;
+    return launch_stream(h, s, KIND_A1, velm, nullptr, force, 1, CHAIN_NONE, pos_delta);
+}
+
+extern "C" int tgnh_half1_drift(tgnh_handle* h, void* stream, void* velm, void* posq, void* pos_delta) {
+    if (int rc = check_ptrs(h, velm, posq, pos_delta, true, true)) return rc;
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->keValid = false;
+    return launch_stream(h, (cudaStream_t)stream, KIND_A2, velm, posq, nullptr, 0, CHAIN_NONE, pos_delta);
+}
+
+extern "C" int tgnh_thermostat(tgnh_handle* h, void* stream, void* velm, int flags) {
+    if (int rc = check_ptrs(h, velm, nullptr, nullptr, false, false)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->scalePending) return fail(TGNH_ERR_INVALID_ARGUMENT, "a deferred velocity scaling is pending; call tgnh_flush first");
+    h->keValid = false;                                              // the caller's velocity constraints changed velm
+    if (int rc = ensure_ke(h, s, velm, CHAIN_SECOND)) return rc;
+    h->scalePending = true;
+    if ((flags & TGNH_HALF2_DEFER_SCALE) && h->uniformGroups) return TGNH_OK;
+    return flush_scale(h, s, velm);
+}
+
 extern "C" int tgnh_half2(tgnh_handle* h, void* stream, void* velm, const void* force, int flags) {
     if (int rc = check_ptrs(h, velm, nullptr, force, false, true)) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(h->device));
+    if (flags & TGNH_HALF2_KICK_ONLY) {
+        // constrained systems: OpenMM's velocity constraints (:391) come between the kick and the thermostat half-step;
+        // the kinetic energies this launch reduces are discarded and tgnh_thermostat recomputes them
+        if (int rc = launch_stream(h, s, KIND_B, velm, nullptr, force, 0, CHAIN_NONE)) return rc;
+        h->keValid = false;
+        return TGNH_OK;
+    }
     if (int rc = launch_stream(h, s, KIND_B, velm, nullptr, force, 0, CHAIN_SECOND)) return rc;   // :384-395
     h->keValid = true;
     h->scalePending = true;

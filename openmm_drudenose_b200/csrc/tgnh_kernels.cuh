@@ -10,6 +10,10 @@
 //                            case): sum_u m_u |v_u - V|^2 = sum_u m_u |v_u|^2 - M |V|^2 per residue, so particles
 //                            never need their residue's COM velocity; one thread per RESIDUE (densely packed
 //                            lanes instead of every member redoing the residue sum) adds the M |V|^2 terms
+//   KIND_A1 / KIND_A2      = the first half split around OpenMM's position constraints (CudaDrudeTGNHKernels.cpp:356-376):
+//                            A1 = scaling + kick, emits posDelta = dt * v (drudeTGNH.cu:249-365); the caller runs
+//                            integration.applyConstraints on posDelta; A2 = x += posDelta, v = posDelta / dt, hard wall
+//                            (drudeTGNH.cu:435-574)
 //   KIND_KE (reduce/flush) = the kinetic-energy reduction alone, optionally applying a pending scaling
 //                            (drudeTGNH.cu:82-242, 249-301)
 //
@@ -37,13 +41,14 @@
 
 namespace tgnh {
 
-enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2, KIND_BU = 3 };
+enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2, KIND_BU = 3, KIND_A1 = 4, KIND_A2 = 5 };
 constexpr int NWARPS = TILE / 32;
 constexpr int TLIST_CAP = 128;     // tile bounds cached in shared memory per CTA (later tiles are looked up in global memory)
 
 struct StreamArgs {
     float4* velm;
     float4* posq;
+    float4* posDelta;         // float4[paddedN] (dt*v, 0): integration.getPosDelta() (KIND_A1 writes, KIND_A2 reads)
     const void* force;        // SoA [3][paddedN], float or long long
     const uint32_t* desc;     // [roundup4(N)]
     const int* tileStart;     // [numTiles + 1]
@@ -66,8 +71,9 @@ struct StreamArgs {
 
 template <int KIND, int FFMT>
 struct StageLayout {
-    static constexpr bool HAS_X = (KIND == KIND_A);
-    static constexpr bool HAS_F = (KIND != KIND_KE);
+    static constexpr bool HAS_X = (KIND == KIND_A || KIND == KIND_A2);
+    static constexpr bool HAS_F = (KIND != KIND_KE && KIND != KIND_A2);
+    static constexpr bool HAS_P = (KIND == KIND_A2);             // posDelta tile
     static constexpr int FBYTES = FFMT == 1 ? 8 : 4;
     static constexpr int OFF_V = 0;
     static constexpr int OFF_X = OFF_V + TILE * 16;
@@ -75,15 +81,16 @@ struct StageLayout {
     static constexpr int OFF_D = OFF_F + (HAS_F ? 3 * PADW * FBYTES : 0);
     static constexpr bool HAS_R = (KIND == KIND_BU);
     static constexpr int OFF_R = OFF_D + PADW * 4;              // residue starts of the tile (KIND_BU)
-    static constexpr int OFF_HDR = OFF_R + (HAS_R ? PADW * 4 : 0);   // int4 {first particle, count, first residue, residues}
+    static constexpr int OFF_P = OFF_R + (HAS_R ? PADW * 4 : 0);
+    static constexpr int OFF_HDR = OFF_P + (HAS_P ? TILE * 16 : 0);  // int4 {first particle, count, first residue, residues}
     static constexpr int BYTES = OFF_HDR + 16;
 };
 
 template <int KIND, int FFMT, bool USE_COM>
 struct SmemLayout {
     using Stage = StageLayout<KIND, FFMT>;
-    static constexpr bool HAS_KE = (KIND != KIND_A);
-    static constexpr int NSTAGE = (KIND == KIND_A) ? 3 : 4;
+    static constexpr bool HAS_KE = (KIND == KIND_B || KIND == KIND_BU || KIND == KIND_KE);
+    static constexpr int NSTAGE = (KIND == KIND_A || KIND == KIND_A2) ? 3 : 4;
     static constexpr int OFF_BAR = NSTAGE * Stage::BYTES;         // full[NS], empty[NS] mbarriers
     static constexpr int OFF_TLIST = OFF_BAR + 128;               // int4[TLIST_CAP] bounds of this CTA's first tiles
     static constexpr int OFF_SCALE = OFF_TLIST + TLIST_CAP * 16;  // double[MAX_T] s^2, float[MAX_T] s - 1
@@ -254,6 +261,7 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
             const int ra0 = r0 & ~3, rna = ((r1 + 1 + 3) & ~3) - ra0;     // residues r0..r1 inclusive (r1 = end marker)
             if (St::HAS_R) bytes += rna * 4;
             if (St::HAS_X) bytes += n * 16;
+            if (St::HAS_P) bytes += n * 16;
             if (St::HAS_F) bytes += 3 * na * St::FBYTES;
             mbar_arrive_expect_tx(bar, bytes);
             if (St::HAS_X) bulk_g2s(st + St::OFF_X, a.posq + start, n * 16, bar, polOnce);
@@ -266,7 +274,10 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
             bulk_g2s(st + St::OFF_D, a.desc + a0, na * 4, bar, polOnce);
             if (St::HAS_R) bulk_g2s(st + St::OFF_R, a.resStart + ra0, rna * 4, bar, polOnce);
         }
-        if (parts & 2) bulk_g2s(st + St::OFF_V, a.velm + start, n * 16, bar, polOnce);
+        if (parts & 2) {
+            bulk_g2s(st + St::OFF_V, a.velm + start, n * 16, bar, polOnce);
+            if (St::HAS_P) bulk_g2s(st + St::OFF_P, a.posDelta + start, n * 16, bar, polOnce);   // written by the caller's constraint kernels
+        }
     };
     if (tid == 0) {
         for (int it = 0; it < NS && it < myTiles; it++) issue(it, 1);
@@ -276,13 +287,13 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
     if (tid == 0)
         for (int it = 0; it < NS && it < myTiles; it++) issue(it, 2);
     if (tid < T) {
-        const double sg = (KIND == KIND_B || KIND == KIND_BU) ? 1.0 : a.chain.scaleA[tid];
+        const double sg = (KIND == KIND_B || KIND == KIND_BU || KIND == KIND_A2) ? 1.0 : a.chain.scaleA[tid];
         ssq[tid] = sg * sg;
         seps[tid] = (float)(sg - 1.0);
     }
     __syncthreads();
 
-    const bool doScale = (KIND == KIND_A) || (KIND == KIND_KE && a.applyScale);
+    const bool doScale = (KIND == KIND_A || KIND == KIND_A1) || (KIND == KIND_KE && a.applyScale);
     const float eCOM = doScale ? seps[G] : 0.0f;
     const float eDrude = doScale ? seps[G + 1] : 0.0f;
     const float rmax2 = a.rmax * a.rmax;
@@ -327,7 +338,7 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
         // after the kick: sum_j m_j (v_j + fscale w_j F_j) = sum_j (m_j v_j + fscale F_j) over the massive members
         float3 V = make_float3(0.f, 0.f, 0.f);
         double keC = 0.0;                             // M |V|^2 of this particle's residue (kinds that reduce energies)
-        if (USE_COM && active && KIND != KIND_BU) {
+        if (USE_COM && active && KIND != KIND_BU && KIND != KIND_A2) {
             const int j0 = tid - desc_off_first(d), j1 = tid + desc_off_last(d);
             if (!L::HAS_KE) {
                 // first half: V only feeds the small corrections (sT-1)(v - V) and (sCOM-1) V, fp32 sums are ample
@@ -422,6 +433,35 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
 
         if (KIND == KIND_KE) {
             if (doScale && active && massive) st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
+        } else if (KIND == KIND_A1) {
+            // scaling + half kick; posDelta = dt * v for OpenMM's constraint kernels (drudeTGNH.cu:322-324, 360-363)
+            vn = kicked(vn, fw, F);
+            if (active && massive) {
+                st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
+                st_global(a.posDelta + start + tid, make_float4(a.dt * vn.x, a.dt * vn.y, a.dt * vn.z, 0.0f));
+            }
+        } else if (KIND == KIND_A2 && active) {
+            // integrateDrudeTGNHPositions (drudeTGNH.cu:438-465): x += delta, v = delta / dt; then the hard wall (:474-573)
+            const float4* sp = reinterpret_cast<const float4*>(st + St::OFF_P);
+            const float invDt = 1.0f / a.dt;
+            const float4 dl = sp[tid], x = sx[tid];
+            float3 xn = make_float3(x.x + dl.x, x.y + dl.y, x.z + dl.z);
+            vn = make_float3(dl.x * invDt, dl.y * invDt, dl.z * invDt);
+            if (HARDWALL && role != ROLE_NORMAL) {
+                const float4 dj = sp[pj], xj = sx[pj];
+                float3 vjn = make_float3(dj.x * invDt, dj.y * invDt, dj.z * invDt);
+                float3 delta = make_float3((x.x - xj.x) + (dl.x - dj.x), (x.y - xj.y) + (dl.y - dj.y), (x.z - xj.z) + (dl.z - dj.z));
+                const float r2 = dot3(delta);
+                if (r2 > rmax2) {
+                    float3 xjn = make_float3(xj.x + dj.x, xj.y + dj.y, xj.z + dj.z);
+                    if (role == ROLE_DRUDE) hard_wall(delta, r2, xn, xjn, vn, vjn, v.w, vj.w, a.rmax, a.hardwallScale, a.dt);
+                    else hard_wall(make_float3(-delta.x, -delta.y, -delta.z), r2, xjn, xn, vjn, vn, vj.w, v.w, a.rmax, a.hardwallScale, a.dt);
+                }
+            }
+            if (massive) {
+                st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
+                st_stream(a.posq + start + tid, make_float4(xn.x, xn.y, xn.z, x.w));
+            }
         } else if (KIND == KIND_A && active) {
             // half kick + drift (+ hard wall) (drudeTGNH.cu:314-364, 438-465, 474-573)
             vn = kicked(vn, fw, F);

@@ -25,12 +25,16 @@ public:
         v.velm = (void*)cu.getVelm().getDevicePointer();
         v.posq = (void*)cu.getPosq().getDevicePointer();
         v.force = (const void*)cu.getForce().getDevicePointer();
+        v.posDelta = (void*)cu.getIntegrationUtilities().getPosDelta().getDevicePointer();
         v.paddedNumAtoms = cu.getPaddedNumAtoms();
         v.forceFormat = TGNH_FORCE_I64_SOA;
         v.stream = (void*)cu.getCurrentStream();
         v.device = cu.getDeviceIndex();
         return v;
     }
+    void applyConstraints(double tol) { cu.getIntegrationUtilities().applyConstraints(tol); }
+    void computeVirtualSites() { cu.getIntegrationUtilities().computeVirtualSites(); }
+    void applyVelocityConstraints(double tol) { cu.getIntegrationUtilities().applyVelocityConstraints(tol); }
     void advanceTime(double dt) {
         cu.setTime(cu.getTime() + dt);
         cu.setStepCount(cu.getStepCount() + 1);

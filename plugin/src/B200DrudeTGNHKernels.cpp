@@ -72,6 +72,7 @@ void B200IntegrateDrudeTGNHStepKernel::initialize(const System& system, const Dr
     p.particle_res_id = resId.data();
     p.constraint_p = consA.data();
     p.constraint_p1 = consB.data();
+    constrained = system.getNumConstraints() > 0;
     tgnh_destroy(handle);
     handle = NULL;
     check(tgnh_create(&p, &handle));
@@ -80,12 +81,27 @@ void B200IntegrateDrudeTGNHStepKernel::initialize(const System& system, const Dr
 // CudaIntegrateDrudeTGNHStepKernel::execute (CudaDrudeTGNHKernels.cpp:284-408)
 void B200IntegrateDrudeTGNHStepKernel::execute(ContextImpl& context, const DrudeTGNHIntegrator& integrator) {
     const TgnhDeviceView dv = device.view();
-    // thermostat half-step, half kick, drift, hard wall (:336-376); OpenMM's constraint kernels would run in between
-    // for constrained systems ("constraints")
-    check(tgnh_half1(handle, dv.stream, dv.velm, dv.posq, dv.force));
-    context.calcForcesAndEnergy(true, false);                                                           // :380
-    const TgnhDeviceView dv2 = device.view();                                                           // force buffer may have moved
-    check(tgnh_half2(handle, dv2.stream, dv2.velm, dv2.force, deferScale ? TGNH_HALF2_DEFER_SCALE : TGNH_HALF2_DEFAULT));   // :384-402
+    const double tol = integrator.getConstraintTolerance();
+    if (!constrained) {
+        // thermostat half-step, half kick, drift, hard wall in one launch (:336-376)
+        check(tgnh_half1(handle, dv.stream, dv.velm, dv.posq, dv.force));
+        device.computeVirtualSites();                                                                   // :377
+        context.calcForcesAndEnergy(true, false);                                                       // :380
+        const TgnhDeviceView dv2 = device.view();                                                       // the force buffer may have moved
+        check(tgnh_half2(handle, dv2.stream, dv2.velm, dv2.force, deferScale ? TGNH_HALF2_DEFER_SCALE : TGNH_HALF2_DEFAULT));   // :384-402
+    } else {
+        // same step with OpenMM's SETTLE / SHAKE / CCMA kernels where the reference calls them
+        if (dv.posDelta == NULL) throw OpenMMException("DrudeTGNH: the platform provides no posDelta buffer for a constrained system");
+        check(tgnh_half1_kick(handle, dv.stream, dv.velm, dv.force, dv.posDelta));                      // :336-360
+        device.applyConstraints(tol);                                                                   // :363
+        check(tgnh_half1_drift(handle, dv.stream, dv.velm, dv.posq, dv.posDelta));                      // :366-376
+        device.computeVirtualSites();                                                                   // :377
+        context.calcForcesAndEnergy(true, false);                                                       // :380
+        const TgnhDeviceView dv2 = device.view();
+        check(tgnh_half2(handle, dv2.stream, dv2.velm, dv2.force, TGNH_HALF2_KICK_ONLY));               // :384-388
+        device.applyVelocityConstraints(tol);                                                           // :391
+        check(tgnh_thermostat(handle, dv2.stream, dv2.velm, deferScale ? TGNH_HALF2_DEFER_SCALE : TGNH_HALF2_DEFAULT));   // :394-402
+    }
     device.advanceTime(integrator.getStepSize());                                                       // :405-406
 }
 

@@ -18,6 +18,7 @@ struct TgnhDeviceView {
     void* velm;          // float4[paddedNumAtoms]   cu.getVelm()
     void* posq;          // float4[paddedNumAtoms]   cu.getPosq()
     const void* force;   // SoA [3][paddedNumAtoms]  cu.getForce()
+    void* posDelta;      // float4[paddedNumAtoms]   integration.getPosDelta() (constrained systems only, may be NULL otherwise)
     int paddedNumAtoms;  // cu.getPaddedNumAtoms()
     int forceFormat;     // TGNH_FORCE_I64_SOA for OpenMM's fixed-point buffer
     void* stream;        // cudaStream_t the platform launches on
@@ -30,12 +31,16 @@ public:
     virtual ~TgnhDeviceAccess() {}
     virtual TgnhDeviceView view() = 0;
     virtual void advanceTime(double dt) = 0;     // cu.setTime / cu.setStepCount (CudaDrudeTGNHKernels.cpp:405-406)
+    // OpenMM's own kernels the step calls between ours (CudaDrudeTGNHKernels.cpp:363, 377, 391); no-ops by default
+    virtual void applyConstraints(double tol) {}          // integration.applyConstraints: acts on posDelta
+    virtual void computeVirtualSites() {}                 // integration.computeVirtualSites
+    virtual void applyVelocityConstraints(double tol) {}  // integration.applyVelocityConstraints: acts on velm
 };
 
 class B200IntegrateDrudeTGNHStepKernel : public IntegrateDrudeTGNHStepKernel {
 public:
     B200IntegrateDrudeTGNHStepKernel(std::string name, const Platform& platform, TgnhDeviceAccess& device)
-        : IntegrateDrudeTGNHStepKernel(name, platform), device(device), handle(NULL), deferScale(false) {}
+        : IntegrateDrudeTGNHStepKernel(name, platform), device(device), handle(NULL), deferScale(false), constrained(false) {}
     ~B200IntegrateDrudeTGNHStepKernel();
     void initialize(const System& system, const DrudeTGNHIntegrator& integrator, const DrudeForce& force);
     void execute(ContextImpl& context, const DrudeTGNHIntegrator& integrator);
@@ -53,6 +58,7 @@ private:
     TgnhDeviceAccess& device;
     tgnh_handle* handle;
     bool deferScale;
+    bool constrained;    // the System has constraints: the split call sequence leaves room for OpenMM's constraint kernels
 };
 
 }  // namespace OpenMM

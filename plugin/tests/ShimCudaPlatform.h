@@ -20,21 +20,25 @@ public:
     class Data : public TgnhDeviceAccess {
     public:
         Data(ContextImpl& c, int forceFormat) : ctx(c), n(c.getSystem().getNumParticles()), padded(((n + 31) / 32) * 32), forceFormat(forceFormat),
-              velm(NULL), posq(NULL), force(NULL), time(0.0), steps(0) {
+              velm(NULL), posq(NULL), force(NULL), posDelta(NULL), time(0.0), steps(0), constraintCalls(0) {
             int count = 0;
             if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw OpenMMException("ShimCudaPlatform: no CUDA device");
             const size_t fbytes = (size_t)3 * padded * (forceFormat == TGNH_FORCE_I64_SOA ? 8 : 4);
-            if (cudaMalloc(&velm, (size_t)padded * 16) || cudaMalloc(&posq, (size_t)padded * 16) || cudaMalloc(&force, fbytes))
+            if (cudaMalloc(&velm, (size_t)padded * 16) || cudaMalloc(&posq, (size_t)padded * 16) || cudaMalloc(&force, fbytes) || cudaMalloc(&posDelta, (size_t)padded * 16))
                 throw OpenMMException("ShimCudaPlatform: cudaMalloc failed");
             cudaMemset(velm, 0, (size_t)padded * 16); cudaMemset(posq, 0, (size_t)padded * 16); cudaMemset(force, 0, fbytes);
             hv.assign((size_t)padded * 4, 0.f); hx.assign((size_t)padded * 4, 0.f);
         }
-        ~Data() { cudaFree(velm); cudaFree(posq); cudaFree(force); }
+        ~Data() { cudaFree(velm); cudaFree(posq); cudaFree(force); cudaFree(posDelta); }
         TgnhDeviceView view() {
-            TgnhDeviceView v = {velm, posq, force, padded, forceFormat, NULL, 0};
+            TgnhDeviceView v = {velm, posq, force, posDelta, padded, forceFormat, NULL, 0};
             return v;
         }
         void advanceTime(double dt) { time += dt; steps++; ctx.time = time; }
+        // the shim has no constraint solver: the calls are counted so that tests can see the split sequence ran
+        void applyConstraints(double) { constraintCalls++; }
+        void applyVelocityConstraints(double) { constraintCalls++; }
+        int constraintCalls;
         void upload() {
             for (int i = 0; i < n; i++) {
                 const double m = ctx.getSystem().getParticleMass(i);
@@ -67,7 +71,7 @@ public:
     private:
         ContextImpl& ctx;
         int n, padded, forceFormat;
-        void *velm, *posq, *force;
+        void *velm, *posq, *force, *posDelta;
         double time;
         int steps;
         std::vector<float> hv, hx;

@@ -32,6 +32,7 @@ struct Sim {
     Sim() : integrator(NULL), context(NULL), forceModel(0) {}
     ~Sim() { delete context; delete integrator; }
 };
+std::vector<std::pair<int, int> > g_nextConstraints;   // consumed by the next ref_create
 Platform* g_platform[2] = {NULL, NULL};
 Platform& platform_for(int forceFormat) {
     // one "CUDA" platform per force format; the kernel factory is registered on whichever is current
@@ -65,6 +66,8 @@ void* ref_create(int n, const double* masses, int npairs, const int* pairDrude, 
         for (int i = 1; i < n; i++) if (resId[i] == resId[i - 1]) bonds->addBond(i - 1, i);
         s->system.addForce(bonds);
         if (hasCMMotionRemover) s->system.addForce(new CMMotionRemover());
+        for (size_t i = 0; i < g_nextConstraints.size(); i++) s->system.addConstraint(g_nextConstraints[i].first, g_nextConstraints[i].second, 0.1);
+        g_nextConstraints.clear();
         s->integrator = new DrudeTGNHIntegrator(temperature, couplingTime, drudeTemperature, drudeCouplingTime, stepSize, drudeSteps, numNHChains,
                                                 useDrudeNHChains != 0, useCOMTempGroup != 0);
         s->integrator->setMaxDrudeDistance(maxDrudeDistance);
@@ -121,6 +124,18 @@ int ref_step(void* h, double* pos, double* vel, double* force, int nsteps, const
         g_error = e.what();
         return 1;
     }
+}
+
+// constraints of the System the next ref_create builds (the shim never applies them: they only switch the kernel to
+// the split call sequence and enter the DOF bookkeeping)
+void plugin_set_next_constraints(int n, const int* a, const int* b) {
+    g_nextConstraints.clear();
+    for (int i = 0; i < n; i++) g_nextConstraints.push_back(std::make_pair(a[i], b[i]));
+}
+
+int plugin_constraint_calls(void* h) {
+    Sim* s = (Sim*)h;
+    return static_cast<ShimCudaPlatform::Data*>(static_cast<TgnhDeviceAccess*>(s->context->getImpl().getPlatformData()))->constraintCalls;
 }
 
 double plugin_kinetic_energy(void* h) {

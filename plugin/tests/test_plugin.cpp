@@ -112,7 +112,7 @@ class FakeCudaPlatform : public Platform, public TgnhDeviceAccess {
 public:
     const string& getName() const { static const string n = "CUDA"; return n; }
     void contextCreated(ContextImpl& c, const map<string, string>&) const { c.setPlatformData(static_cast<TgnhDeviceAccess*>(const_cast<FakeCudaPlatform*>(this))); }
-    TgnhDeviceView view() { TgnhDeviceView v = {NULL, NULL, NULL, 32, TGNH_FORCE_I64_SOA, NULL, 0}; return v; }
+    TgnhDeviceView view() { TgnhDeviceView v = {NULL, NULL, NULL, NULL, 32, TGNH_FORCE_I64_SOA, NULL, 0}; return v; }
     void advanceTime(double) {}
 };
 

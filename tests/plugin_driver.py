@@ -21,6 +21,8 @@ def lib():
         L.ref_destroy.argtypes = [C.c_void_p]
         L.ref_num_residues.argtypes = [C.c_void_p]
         L.ref_step.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp]
+        L.plugin_set_next_constraints.argtypes = [C.c_int, ip, ip]
+        L.plugin_constraint_calls.argtypes = [C.c_void_p]
         L.plugin_kinetic_energy.argtypes = [C.c_void_p]
         L.plugin_kinetic_energy.restype = C.c_double
         _lib = L
@@ -36,9 +38,13 @@ def _ip(a):
 
 
 class PluginSim:
-    def __init__(self, system, force_model=0, has_cm_motion_remover=False):
+    def __init__(self, system, force_model=0, has_cm_motion_remover=False, with_constraints=False):
         s = system
         L = lib()
+        if with_constraints and len(s.constraints):
+            c = np.ascontiguousarray(s.constraints, np.int32)
+            a, b = np.ascontiguousarray(c[:, 0]), np.ascontiguousarray(c[:, 1])
+            L.plugin_set_next_constraints(len(c), _ip(a), _ip(b))
         self._keep = [np.ascontiguousarray(s.masses, np.float64), np.ascontiguousarray(s.pair_drude, np.int32),
                       np.ascontiguousarray(s.pair_parent, np.int32), np.ascontiguousarray(s.res_id, np.int32),
                       np.ascontiguousarray(s.temp_group, np.int32), np.ascontiguousarray(s.k_spring, np.float64)]
@@ -53,6 +59,9 @@ class PluginSim:
     def step(self, pos, vel, force, nsteps=1, ext_force=None):
         if lib().ref_step(self.h, _dp(pos), _dp(vel), _dp(force), nsteps, _dp(ext_force)):
             raise RuntimeError(lib().ref_last_error().decode())
+
+    def constraint_calls(self):
+        return lib().plugin_constraint_calls(self.h)
 
     def kinetic_energy(self):
         return lib().plugin_kinetic_energy(self.h)

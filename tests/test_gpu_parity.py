@@ -349,3 +349,52 @@ def test_error_reporting(cuda):
     with pytest.raises(capi.TgnhError):
         h.step(0, st.posq.data_ptr(), st.force.data_ptr(), 1)
     h.close()
+
+
+def test_constraint_split_equals_fused_step(cuda):
+    """tgnh_half1_kick + tgnh_half1_drift and tgnh_half2(KICK_ONLY) + tgnh_thermostat — the call sequence for systems whose
+    constraints OpenMM applies between them (CudaDrudeTGNHKernels.cpp:363, :391) — reproduce the fused calls when the
+    constraint step is the identity, and the oracle within the per-step tolerance."""
+    import torch
+    s = synth.water_box(3000, 3, quantize_masses=True)
+    a, b = DeviceState(s, cuda), DeviceState(s, cuda)
+    ha, hb = capi.Handle(s), capi.Handle(s)
+    pos_delta = torch.zeros_like(b.velm)
+    o = O.Oracle(s, O.TG)
+    p, v, f = s.positions.copy(), s.velocities.copy(), s.forces.copy()
+    for _ in range(3):
+        ha.half1(*a.ptrs)
+        ha.half2(a.velm.data_ptr(), a.force.data_ptr())
+        hb.half1_kick(b.velm.data_ptr(), b.force.data_ptr(), pos_delta.data_ptr())
+        hb.half1_drift(b.velm.data_ptr(), b.posq.data_ptr(), pos_delta.data_ptr())
+        hb.half2(b.velm.data_ptr(), b.force.data_ptr(), capi.HALF2_KICK_ONLY)
+        hb.thermostat(b.velm.data_ptr())
+    o.step(p, v, f, 3)
+    assert rel_err(b.vel(), a.vel()) < 1e-6 and rel_err(b.pos(), a.pos()) < 1e-6      # v = (dt v) / dt costs one rounding
+    assert rel_err(b.vel(), v) < 3 * TOL_STEP and rel_err(b.pos(), p) < TOL_STEP
+    np.testing.assert_allclose(hb.vscale(), o.vscale, rtol=TOL_THERMO)
+    assert ke_err(hb.kinetic_energies(), o.ke2, o.thermostat_params()[1]) < TOL_THERMO
+    ha.close(); hb.close()
+
+
+def test_constraint_split_uses_the_constrained_displacement(cuda):
+    """Whatever the caller's constraint kernels leave in posDelta is what moves the particles: x += delta, v = delta / dt
+    (integrateDrudeTGNHPositions, drudeTGNH.cu:438-465); massless particles are untouched."""
+    import torch
+    s = synth.swm4_box(500, quantize_masses=True, max_drude_distance=0.0)
+    st = DeviceState(s, cuda)
+    h = capi.Handle(s)
+    n = s.num_particles
+    pos_delta = torch.zeros_like(st.velm)
+    x0 = st.posq.clone()
+    h.half1_kick(st.velm.data_ptr(), st.force.data_ptr(), pos_delta.data_ptr())
+    v1 = st.velm.clone()
+    massive = torch.from_numpy(s.masses != 0).to(cuda)
+    np.testing.assert_allclose(pos_delta[:n, :3][massive].cpu().numpy(), (v1[:n, :3][massive] * np.float32(s.step_size)).cpu().numpy(), rtol=2e-7)
+    pos_delta[:n, :3] *= 0.5                                  # stand-in for a constraint solver shortening every displacement
+    h.half1_drift(st.velm.data_ptr(), st.posq.data_ptr(), pos_delta.data_ptr())
+    np.testing.assert_allclose(st.posq[:n, :3][massive].cpu().numpy(), (x0[:n, :3] + pos_delta[:n, :3])[massive].cpu().numpy(), rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(st.velm[:n, :3][massive].cpu().numpy(), (pos_delta[:n, :3][massive] / np.float32(s.step_size)).cpu().numpy(), rtol=3e-7)
+    assert torch.equal(st.posq[:n][~massive], x0[:n][~massive])
+    assert torch.equal(st.posq[:n, 3], x0[:n, 3]) and torch.equal(st.velm[:n, 3], v1[:n, 3])
+    h.close()

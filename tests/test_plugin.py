@@ -63,6 +63,28 @@ def test_plugin_stack_against_oracle(cuda, model):
 
 
 @pytest.mark.gpu
+def test_plugin_constrained_system_takes_the_split_sequence(cuda):
+    """A System with constraints (C2 shape: SWM4 waters, 3 constraints each, massless M site, CMMotionRemover): the KernelImpl
+    calls kick -> applyConstraints -> drift -> forces -> kick -> applyVelocityConstraints -> thermostat
+    (CudaDrudeTGNHKernels.cpp:356-402).  The shim's constraint calls are identities, so the result equals the oracle with
+    the constraints entering only the DOF bookkeeping."""
+    from plugin_driver import PluginSim
+    s = synth.swm4_box(800, quantize_masses=True)
+    s.positions = (s.positions - s.positions.mean(0)).astype(np.float32).astype(np.float64)
+    sim = PluginSim(s, has_cm_motion_remover=True, with_constraints=True)
+    o = O.Oracle(s, O.TG, constraints=s.constraints, has_cm_motion_remover=True)
+    ext = np.rint(s.forces * 4294967296.0) / 4294967296.0
+    pa, va, fa = s.positions.copy(), s.velocities.copy(), ext.copy()
+    pb, vb, fb = pa.copy(), va.copy(), ext.copy()
+    sim.step(pa, va, fa, 10)
+    o.step(pb, vb, fb, 10)
+    assert sim.constraint_calls() == 20
+    assert rel_err(va, vb) < 2e-5 and rel_err(pa, pb) < 1e-5
+    assert abs(sim.kinetic_energy() - o.ke_sum) / o.ke_sum < 1e-6
+    sim.close()
+
+
+@pytest.mark.gpu
 def test_plugin_single_pair_hard_wall(cuda):
     """The reference tests' 2-particle system (testSinglePair): the hard wall bound holds at every sample."""
     from plugin_driver import PluginSim
