@@ -15,8 +15,8 @@
  * torch types cross it.  Every function returns TGNH_OK or an error code; the message is
  * available from tgnh_last_error() (thread-local).
  *
- * Buffers handed to the step functions are DEVICE pointers owned by the caller, in the layout
- * OpenMM's CudaContext uses in single precision:
+ * Buffers handed to the step functions are DEVICE pointers owned by the caller, in the layouts
+ * OpenMM's CudaContext uses; shown for single precision, see TGNH_PRECISION_MIXED below:
  *     velm   float4[paddedN]   (vx, vy, vz, 1/m)   cu.getVelm();  w == 0 marks an immovable particle
  *     posq   float4[paddedN]   (x, y, z, q)        cu.getPosq();  w is preserved
  *     force  SoA [3][paddedN]  force[i + k*paddedN]                cu.getForce()
@@ -49,6 +49,12 @@ enum {
 
 enum { TGNH_FORCE_F32_SOA = 0, TGNH_FORCE_I64_SOA = 1 };
 
+/* OpenMM CUDA precision modes (cu.getUseMixedPrecision()):
+ *   SINGLE  velm float4,  posq float4,                         posDelta float4;  fp32 arithmetic, fp64 energy sums + chain
+ *   MIXED   velm double4, posq float4 + posqCorrection float4, posDelta double4; fp64 arithmetic ("mixed" = double in
+ *           drudeTGNH.cu); register cu.getPosqCorrection() once with tgnh_set_posq_correction */
+enum { TGNH_PRECISION_SINGLE = 0, TGNH_PRECISION_MIXED = 1 };
+
 /* flags for tgnh_half2 */
 enum {
     TGNH_HALF2_DEFAULT = 0,
@@ -78,7 +84,7 @@ typedef struct {
     int32_t has_cm_motion_remover;   /* System contains a CMMotionRemover (CudaDrudeTGNHKernels.cpp:204-212) */
     int32_t force_format;            /* TGNH_FORCE_* */
     int32_t device;                  /* CUDA device ordinal; -1 = current device */
-    int32_t reserved;
+    int32_t precision;               /* TGNH_PRECISION_* */
     double temperature;
     double coupling_time;
     double drude_temperature;
@@ -130,6 +136,8 @@ int tgnh_step(tgnh_handle* h, void* stream, void* velm, void* posq, const void* 
 /* Host-buffer convenience (end-to-end path): copies velm/posq/force from pinned or pageable HOST memory,
  * runs nsteps, copies velm/posq back and the 2*KE vector into ke2_host ([G+2], may be NULL). Blocking. */
 int tgnh_step_host(tgnh_handle* h, void* velm_host, void* posq_host, const void* force_host, int nsteps, double* ke2_host);
+/* Mixed precision: the float4[paddedN] residual array of the positions (cu.getPosqCorrection()). */
+int tgnh_set_posq_correction(tgnh_handle* h, void* posq_correction);
 /* The velocities were changed behind the integrator's back (DrudeTGNHIntegrator::stateChanged,
  * openmmapi/src/DrudeTGNHIntegrator.cpp:166-170): cached kinetic energies are dropped. */
 int tgnh_invalidate(tgnh_handle* h);

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libtgnh.so")
 
 OK, ERR_INVALID_ARGUMENT, ERR_TEMP_GROUP, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE = range(7)
 FORCE_F32_SOA, FORCE_I64_SOA = 0, 1
+PRECISION_SINGLE, PRECISION_MIXED = 0, 1
 HALF2_DEFAULT, HALF2_DEFER_SCALE, HALF2_KICK_ONLY = 0, 1, 2
 UNIQUE_ID_BYTES = 128
 BOLTZ = 1.380649e-23 * 6.02214076e23 / 1000.0
@@ -20,7 +21,7 @@ BOLTZ = 1.380649e-23 * 6.02214076e23 / 1000.0
 SYMBOLS = [
     "tgnh_create", "tgnh_destroy", "tgnh_last_error", "tgnh_build_info", "tgnh_half1", "tgnh_half1_kick", "tgnh_half1_drift",
     "tgnh_thermostat", "tgnh_half2", "tgnh_flush",
-    "tgnh_step", "tgnh_step_host", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
+    "tgnh_step", "tgnh_step_host", "tgnh_set_posq_correction", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
     "tgnh_kinetic_energy", "tgnh_compute_kinetic_energies", "tgnh_get_chain_state", "tgnh_set_chain_state",
     "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
     "tgnh_comm_create", "tgnh_comm_destroy",
@@ -37,7 +38,7 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "num_particles", "padded_num_particles", "num_pairs", "num_residues", "num_temp_groups", "num_constraints",
         "num_nh_chains", "drude_steps_per_real_step", "use_drude_nh_chains", "use_com_temp_group",
-        "has_cm_motion_remover", "force_format", "device", "reserved")] + [(n, C.c_double) for n in (
+        "has_cm_motion_remover", "force_format", "device", "precision")] + [(n, C.c_double) for n in (
         "temperature", "coupling_time", "drude_temperature", "drude_coupling_time", "step_size",
         "max_drude_distance")] + [
         ("masses", C.POINTER(C.c_double)), ("pair_drude", C.POINTER(C.c_int32)), ("pair_parent", C.POINTER(C.c_int32)),
@@ -70,6 +71,7 @@ def lib():
         L.tgnh_flush.argtypes = [vp, vp, vp]
         L.tgnh_step.argtypes = [vp, vp, vp, vp, vp, C.c_int]
         L.tgnh_step_host.argtypes = [vp, vp, vp, vp, C.c_int, dp]
+        L.tgnh_set_posq_correction.argtypes = [vp, vp]
         L.tgnh_invalidate.argtypes = [vp]
         L.tgnh_num_thermostats.argtypes = [vp]
         L.tgnh_num_nh_chains.argtypes = [vp]
@@ -129,7 +131,7 @@ class Comm:
 class Handle:
     """Owns one tgnh_handle.  Buffers are passed as raw device pointers (ints), e.g. tensor.data_ptr()."""
 
-    def __init__(self, system, *, force_format=FORCE_F32_SOA, padded=None, device=-1, comm=None,
+    def __init__(self, system, *, force_format=FORCE_F32_SOA, precision=PRECISION_SINGLE, padded=None, device=-1, comm=None,
                  has_cm_motion_remover=False, constraints=None, **overrides):
         s = system
         n = s.num_particles
@@ -147,7 +149,7 @@ class Handle:
             num_temp_groups=s.num_temp_groups, num_constraints=len(cons), num_nh_chains=s.num_nh_chains,
             drude_steps_per_real_step=s.drude_steps, use_drude_nh_chains=int(s.use_drude_nh_chains),
             use_com_temp_group=int(s.use_com_temp_group), has_cm_motion_remover=int(has_cm_motion_remover),
-            force_format=force_format, device=device, temperature=s.temperature, coupling_time=s.coupling_time,
+            force_format=force_format, device=device, precision=precision, temperature=s.temperature, coupling_time=s.coupling_time,
             drude_temperature=s.drude_temperature, drude_coupling_time=s.drude_coupling_time, step_size=s.step_size,
             max_drude_distance=s.max_drude_distance, masses=_dp(k["masses"]), pair_drude=_ip(k["pd"]),
             pair_parent=_ip(k["pp"]), particle_temp_group=_ip(k["tg"]), particle_res_id=_ip(k["res"]),
@@ -201,6 +203,9 @@ class Handle:
         as_ptr = lambda a: a if isinstance(a, int) else a.ctypes.data
         check(lib().tgnh_step_host(self.h, as_ptr(velm_host), as_ptr(posq_host), as_ptr(force_host), nsteps, _dp(ke2)))
         return ke2
+
+    def set_posq_correction(self, ptr):
+        check(lib().tgnh_set_posq_correction(self.h, ptr))
 
     def invalidate(self):
         check(lib().tgnh_invalidate(self.h))

@@ -126,7 +126,8 @@ extern "C" void tgnh_comm_destroy(tgnh_comm* c) {
 struct tgnh_handle {
     int device = 0, numSMs = 0;
     int N = 0, paddedN = 0, P = 0, R = 0, G = 0, T = 0, M = 0, S = 0;
-    int useDrudeNH = 0, useCOM = 0, ffmt = 0, hardwall = 0;
+    int useDrudeNH = 0, useCOM = 0, ffmt = 0, hardwall = 0, prec = 0;
+    void* posqCorrection = nullptr;   // mixed precision: cu.getPosqCorrection(), registered with tgnh_set_posq_correction
     bool uniformGroups = true;   // every residue lies in one temperature group (folding / KE carry-over legal)
     double dt = 0, rmax = 0, kT = 0, kTD = 0;
     int numTiles = 0;
@@ -162,50 +163,61 @@ struct tgnh_handle {
 
 typedef void (*StreamKernel)(const StreamArgs);
 
-template <int KIND, int FFMT>
+template <int KIND, int FFMT, int PREC>
 static StreamKernel pick2(bool useCOM, bool hardwall) {
-    if (KIND == KIND_A) {   // only the first-half kernel contains the hard wall
-        if (useCOM) return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, true, true> : tgnh_stream_kernel<KIND_A, FFMT, true, false>;
-        return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, false, true> : tgnh_stream_kernel<KIND_A, FFMT, false, false>;
+    if (KIND == KIND_A) {   // only the kernels that move positions contain the hard wall
+        if (useCOM) return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, true, true, PREC> : tgnh_stream_kernel<KIND_A, FFMT, true, false, PREC>;
+        return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, false, true, PREC> : tgnh_stream_kernel<KIND_A, FFMT, false, false, PREC>;
     }
-    return useCOM ? tgnh_stream_kernel<KIND, FFMT, true, false> : tgnh_stream_kernel<KIND, FFMT, false, false>;
+    if (KIND == KIND_A2) return hardwall ? tgnh_stream_kernel<KIND_A2, 0, false, true, PREC> : tgnh_stream_kernel<KIND_A2, 0, false, false, PREC>;
+    if (KIND == KIND_KE) return useCOM ? tgnh_stream_kernel<KIND_KE, 0, true, false, PREC> : tgnh_stream_kernel<KIND_KE, 0, false, false, PREC>;
+    return useCOM ? tgnh_stream_kernel<KIND, FFMT, true, false, PREC> : tgnh_stream_kernel<KIND, FFMT, false, false, PREC>;
 }
 
-static StreamKernel pick(int kind, int ffmt, bool useCOM, bool hardwall) {
+template <int KIND>
+static StreamKernel pick1(int ffmt, int prec, bool useCOM, bool hardwall) {
+    if (prec) return ffmt ? pick2<KIND, 1, 1>(useCOM, hardwall) : pick2<KIND, 0, 1>(useCOM, hardwall);
+    return ffmt ? pick2<KIND, 1, 0>(useCOM, hardwall) : pick2<KIND, 0, 0>(useCOM, hardwall);
+}
+
+static StreamKernel pick(int kind, int ffmt, int prec, bool useCOM, bool hardwall) {
     switch (kind) {
-        case KIND_A: return ffmt ? pick2<KIND_A, 1>(useCOM, hardwall) : pick2<KIND_A, 0>(useCOM, hardwall);
-        case KIND_B: return ffmt ? pick2<KIND_B, 1>(useCOM, false) : pick2<KIND_B, 0>(useCOM, false);
-        case KIND_BU: return ffmt ? pick2<KIND_BU, 1>(useCOM, false) : pick2<KIND_BU, 0>(useCOM, false);
-        case KIND_A1: return ffmt ? pick2<KIND_A1, 1>(useCOM, false) : pick2<KIND_A1, 0>(useCOM, false);
-        case KIND_A2: return hardwall ? tgnh_stream_kernel<KIND_A2, 0, false, true> : tgnh_stream_kernel<KIND_A2, 0, false, false>;
-        default: return pick2<KIND_KE, 0>(useCOM, false);
+        case KIND_A: return pick1<KIND_A>(ffmt, prec, useCOM, hardwall);
+        case KIND_B: return pick1<KIND_B>(ffmt, prec, useCOM, hardwall);
+        case KIND_BU: return pick1<KIND_BU>(ffmt, prec, useCOM, hardwall);
+        case KIND_A1: return pick1<KIND_A1>(ffmt, prec, useCOM, hardwall);
+        case KIND_A2: return pick1<KIND_A2>(ffmt, prec, useCOM, hardwall);
+        default: return pick1<KIND_KE>(ffmt, prec, useCOM, hardwall);
     }
 }
 
-static int smem_bytes(int kind, int ffmt, bool useCOM, int T) {
+template <int KIND, int FFMT, int PREC>
+static int smem2(bool useCOM, int T) {
+    if (KIND == KIND_A2) return SmemLayout<KIND_A2, 0, false, PREC>::bytes(T);
+    if (KIND == KIND_KE) return useCOM ? SmemLayout<KIND_KE, 0, true, PREC>::bytes(T) : SmemLayout<KIND_KE, 0, false, PREC>::bytes(T);
+    return useCOM ? SmemLayout<KIND, FFMT, true, PREC>::bytes(T) : SmemLayout<KIND, FFMT, false, PREC>::bytes(T);
+}
+
+template <int KIND>
+static int smem1(int ffmt, int prec, bool useCOM, int T) {
+    if (prec) return ffmt ? smem2<KIND, 1, 1>(useCOM, T) : smem2<KIND, 0, 1>(useCOM, T);
+    return ffmt ? smem2<KIND, 1, 0>(useCOM, T) : smem2<KIND, 0, 0>(useCOM, T);
+}
+
+static int smem_bytes(int kind, int ffmt, int prec, bool useCOM, int T) {
     switch (kind) {
-        case KIND_A:
-            if (ffmt) return useCOM ? SmemLayout<KIND_A, 1, true>::bytes(T) : SmemLayout<KIND_A, 1, false>::bytes(T);
-            return useCOM ? SmemLayout<KIND_A, 0, true>::bytes(T) : SmemLayout<KIND_A, 0, false>::bytes(T);
-        case KIND_B:
-            if (ffmt) return useCOM ? SmemLayout<KIND_B, 1, true>::bytes(T) : SmemLayout<KIND_B, 1, false>::bytes(T);
-            return useCOM ? SmemLayout<KIND_B, 0, true>::bytes(T) : SmemLayout<KIND_B, 0, false>::bytes(T);
-        case KIND_A1:
-            if (ffmt) return useCOM ? SmemLayout<KIND_A1, 1, true>::bytes(T) : SmemLayout<KIND_A1, 1, false>::bytes(T);
-            return useCOM ? SmemLayout<KIND_A1, 0, true>::bytes(T) : SmemLayout<KIND_A1, 0, false>::bytes(T);
-        case KIND_A2:
-            return SmemLayout<KIND_A2, 0, false>::bytes(T);
-        case KIND_BU:
-            if (ffmt) return useCOM ? SmemLayout<KIND_BU, 1, true>::bytes(T) : SmemLayout<KIND_BU, 1, false>::bytes(T);
-            return useCOM ? SmemLayout<KIND_BU, 0, true>::bytes(T) : SmemLayout<KIND_BU, 0, false>::bytes(T);
-        default:
-            return useCOM ? SmemLayout<KIND_KE, 0, true>::bytes(T) : SmemLayout<KIND_KE, 0, false>::bytes(T);
+        case KIND_A: return smem1<KIND_A>(ffmt, prec, useCOM, T);
+        case KIND_B: return smem1<KIND_B>(ffmt, prec, useCOM, T);
+        case KIND_BU: return smem1<KIND_BU>(ffmt, prec, useCOM, T);
+        case KIND_A1: return smem1<KIND_A1>(ffmt, prec, useCOM, T);
+        case KIND_A2: return smem1<KIND_A2>(ffmt, prec, useCOM, T);
+        default: return smem1<KIND_KE>(ffmt, prec, useCOM, T);
     }
 }
 
 static int configure_kernel(tgnh_handle* h, int kind, int* grid, int* smem) {
-    StreamKernel k = pick(kind, h->ffmt, h->useCOM, h->hardwall);
-    *smem = smem_bytes(kind, h->ffmt, h->useCOM, h->T);
+    StreamKernel k = pick(kind, h->ffmt, h->prec, h->useCOM, h->hardwall);
+    *smem = smem_bytes(kind, h->ffmt, h->prec, h->useCOM, h->T);
     if (*smem > 227 * 1024)
         return fail(TGNH_ERR_UNSUPPORTED, "%d temperature groups need %d bytes of shared memory per CTA (limit 232448)", h->G, *smem);
     CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem));
@@ -240,6 +252,8 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         return fail(TGNH_ERR_INVALID_ARGUMENT, "padded_num_particles must be a multiple of 4 and >= num_particles");
     if (p->force_format != TGNH_FORCE_F32_SOA && p->force_format != TGNH_FORCE_I64_SOA)
         return fail(TGNH_ERR_INVALID_ARGUMENT, "unknown force_format %d", p->force_format);
+    if (p->precision != TGNH_PRECISION_SINGLE && p->precision != TGNH_PRECISION_MIXED)
+        return fail(TGNH_ERR_INVALID_ARGUMENT, "unknown precision %d", p->precision);
     if (p->max_drude_distance < 0) return fail(TGNH_ERR_INVALID_ARGUMENT, "setMaxDrudeDistance: Distance cannot be negative");
     if (!(p->step_size > 0)) return fail(TGNH_ERR_INVALID_ARGUMENT, "step_size must be positive");
 
@@ -320,7 +334,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
     h->N = N; h->paddedN = p->padded_num_particles; h->P = P; h->R = R; h->G = G; h->T = T; h->M = M;
     h->S = p->drude_steps_per_real_step;
     h->useDrudeNH = p->use_drude_nh_chains != 0; h->useCOM = p->use_com_temp_group != 0;
-    h->ffmt = p->force_format; h->hardwall = p->max_drude_distance > 0;
+    h->ffmt = p->force_format; h->hardwall = p->max_drude_distance > 0; h->prec = p->precision;
     h->uniformGroups = uniform;
     h->dt = p->step_size; h->rmax = p->max_drude_distance;
     h->kT = TGNH_BOLTZ * p->temperature; h->kTD = TGNH_BOLTZ * p->drude_temperature;
@@ -516,16 +530,18 @@ static int launch_chain(tgnh_handle* h, cudaStream_t s, int mode) {
 static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, void* posq, const void* force, int applyScale, int chainMode,
                          void* posDelta = nullptr) {
     StreamArgs a;
-    a.velm = (float4*)velm; a.posq = (float4*)posq; a.force = force; a.posDelta = (float4*)posDelta;
+    a.velm = velm; a.posq = (float4*)posq; a.posqCorrection = (float4*)h->posqCorrection; a.force = force; a.posDelta = posDelta;
+    if (h->prec && posq != nullptr && h->posqCorrection == nullptr)
+        return fail(TGNH_ERR_INVALID_ARGUMENT, "mixed precision: register the posqCorrection array with tgnh_set_posq_correction first");
     a.desc = h->dDesc; a.tileStart = h->dTileStart; a.numTiles = h->numTiles; a.paddedN = h->paddedN;
     a.resStart = h->dResStart; a.tileFirstRes = h->dTileFirstRes;
     const bool firstHalf = kind == KIND_A || kind == KIND_A1 || kind == KIND_A2;
     const int prof = firstHalf ? KIND_A : kind;      // profiling slot (first half / second half / reduce)
     if (kind == KIND_B) kind = h->kindB;
-    a.dt = (float)h->dt;
-    a.fscale = (float)(h->ffmt == TGNH_FORCE_I64_SOA ? 0.5 * h->dt / 4294967296.0 : 0.5 * h->dt);   // CudaDrudeTGNHKernels.cpp:295
-    a.rmax = (float)h->rmax;
-    a.hardwallScale = (float)std::sqrt(h->kTD);                                                       // :299
+    a.dt = h->dt;
+    a.fscale = h->ffmt == TGNH_FORCE_I64_SOA ? 0.5 * h->dt / 4294967296.0 : 0.5 * h->dt;             // CudaDrudeTGNHKernels.cpp:295
+    a.rmax = h->rmax;
+    a.hardwallScale = std::sqrt(h->kTD);                                                              // :299
     a.applyScale = applyScale;
     a.useLocalKE = sharded(h) ? 1 : 0;
     a.reverse = (prof == KIND_B) ? 1 : 0;   // first-half and reduce/flush launches walk forward, second-half backward
@@ -537,7 +553,7 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     a.partials = h->dPartials; a.ticket = h->dTicket; a.chain = h->chain;
     const int grid = kind == KIND_A1 ? h->gridA1 : kind == KIND_A2 ? h->gridA2 : prof == KIND_A ? h->gridA : prof == KIND_B ? h->gridB : h->gridKE;
     const int smem = kind == KIND_A1 ? h->smemA1 : kind == KIND_A2 ? h->smemA2 : prof == KIND_A ? h->smemA : prof == KIND_B ? h->smemB : h->smemKE;
-    StreamKernel k = pick(kind, h->ffmt, h->useCOM, h->hardwall);
+    StreamKernel k = pick(kind, h->ffmt, h->prec, h->useCOM, h->hardwall);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
         if (h->evUsed + 2 > h->evPool.size()) {
@@ -675,6 +691,14 @@ extern "C" int tgnh_step(tgnh_handle* h, void* stream, void* velm, void* posq, c
     return flush_scale(h, s, velm);
 }
 
+extern "C" int tgnh_set_posq_correction(tgnh_handle* h, void* posq_correction) {
+    if (!h) return fail(TGNH_ERR_INVALID_ARGUMENT, "null handle");
+    if (!h->prec) return fail(TGNH_ERR_INVALID_ARGUMENT, "posqCorrection exists in mixed precision only");
+    if (!posq_correction || ((uintptr_t)posq_correction & 15)) return fail(TGNH_ERR_INVALID_ARGUMENT, "posq_correction must be a 16-byte aligned device pointer");
+    h->posqCorrection = posq_correction;
+    return TGNH_OK;
+}
+
 extern "C" int tgnh_invalidate(tgnh_handle* h) {
     if (!h) return fail(TGNH_ERR_INVALID_ARGUMENT, "null handle");
     h->keValid = false;
@@ -687,6 +711,7 @@ extern "C" int tgnh_step_host(tgnh_handle* h, void* velm_host, void* posq_host, 
     const size_t fbytes = (size_t)3 * h->paddedN * (h->ffmt == TGNH_FORCE_I64_SOA ? 8 : 4);
     if (!h->hsStream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->hsStream, cudaStreamNonBlocking));
+        if (h->prec) return fail(TGNH_ERR_UNSUPPORTED, "tgnh_step_host covers the single-precision layout only");
         CUDA_TRY(cudaMalloc(&h->hsVelm, (size_t)h->paddedN * 16));
         CUDA_TRY(cudaMalloc(&h->hsPosq, (size_t)h->paddedN * 16));
         CUDA_TRY(cudaMalloc(&h->hsForce, fbytes));

@@ -36,6 +36,10 @@
 //                                                                            form reduces to the direct kick)
 // which holds for both members of a pair and, with "partner = self" (rel = 0), for ordinary particles:
 // one branch-free code path, and no (f_i + f_j != 1) round-trip error in fp32.
+//
+// Precision (template parameter PREC): 0 = OpenMM's single-precision layout (float4 velm, float4 posq), fp32 arithmetic
+// with fp64 energy sums; 1 = OpenMM's mixed-precision layout (double4 velm, float4 posq + float4 posqCorrection, double4
+// posDelta; `mixed` = double in drudeTGNH.cu), all arithmetic in double.
 #pragma once
 #include "tgnh_device.cuh"
 
@@ -45,10 +49,15 @@ enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2, KIND_BU = 3, KIND_A1 = 4, KIND_A2 = 
 constexpr int NWARPS = TILE / 32;
 constexpr int TLIST_CAP = 128;     // tile bounds cached in shared memory per CTA (later tiles are looked up in global memory)
 
+template <int PREC> struct Prec;
+template <> struct Prec<0> { typedef float real; typedef float4 real4; };
+template <> struct Prec<1> { typedef double real; typedef double4 real4; };
+
 struct StreamArgs {
-    float4* velm;
-    float4* posq;
-    float4* posDelta;         // float4[paddedN] (dt*v, 0): integration.getPosDelta() (KIND_A1 writes, KIND_A2 reads)
+    void* velm;               // real4[paddedN]
+    float4* posq;             // float4[paddedN]
+    float4* posqCorrection;   // float4[paddedN], mixed precision only (cu.getPosqCorrection())
+    void* posDelta;           // real4[paddedN] (dt*v, 0): integration.getPosDelta() (KIND_A1 writes, KIND_A2 reads)
     const void* force;        // SoA [3][paddedN], float or long long
     const uint32_t* desc;     // [roundup4(N)]
     const int* tileStart;     // [numTiles + 1]
@@ -56,10 +65,10 @@ struct StreamArgs {
     const int* tileFirstRes;  // [numTiles + 1] index into resStart of each tile's first residue      (KIND_BU)
     int numTiles;
     int paddedN;
-    float dt;                 // step size
-    float fscale;             // 0.5*dt (f32 forces) or 0.5*dt/2^32 (i64 forces)
-    float rmax;               // maxDrudeDistance
-    float hardwallScale;      // sqrt(kB * T_drude)
+    double dt;                // step size
+    double fscale;            // 0.5*dt (f32 forces) or 0.5*dt/2^32 (i64 forces)
+    double rmax;              // maxDrudeDistance
+    double hardwallScale;     // sqrt(kB * T_drude)
     int applyScale;           // KIND_KE: scale velocities by scaleA and write them back
     int useLocalKE;           // sharded: reduce into chain.ke2Local (all-reduced into ke2 afterwards)
     int reverse;              // walk the tiles from the last to the first (see "L2 hand-over" below)
@@ -69,45 +78,69 @@ struct StreamArgs {
     ChainView chain;
 };
 
-template <int KIND, int FFMT>
+template <int KIND, int FFMT, int PREC>
 struct StageLayout {
     static constexpr bool HAS_X = (KIND == KIND_A || KIND == KIND_A2);
     static constexpr bool HAS_F = (KIND != KIND_KE && KIND != KIND_A2);
     static constexpr bool HAS_P = (KIND == KIND_A2);             // posDelta tile
-    static constexpr int FBYTES = FFMT == 1 ? 8 : 4;
-    static constexpr int OFF_V = 0;
-    static constexpr int OFF_X = OFF_V + TILE * 16;
-    static constexpr int OFF_F = OFF_X + (HAS_X ? TILE * 16 : 0);
-    static constexpr int OFF_D = OFF_F + (HAS_F ? 3 * PADW * FBYTES : 0);
     static constexpr bool HAS_R = (KIND == KIND_BU);
+    static constexpr int FBYTES = FFMT == 1 ? 8 : 4;
+    static constexpr int VB = PREC ? 32 : 16;                    // bytes of one velm / posDelta element
+    static constexpr int OFF_V = 0;
+    static constexpr int OFF_X = OFF_V + TILE * VB;
+    static constexpr int OFF_XC = OFF_X + (HAS_X ? TILE * 16 : 0);             // posqCorrection tile (mixed)
+    static constexpr int OFF_F = OFF_XC + ((HAS_X && PREC) ? TILE * 16 : 0);
+    static constexpr int OFF_D = OFF_F + (HAS_F ? 3 * PADW * FBYTES : 0);
     static constexpr int OFF_R = OFF_D + PADW * 4;              // residue starts of the tile (KIND_BU)
     static constexpr int OFF_P = OFF_R + (HAS_R ? PADW * 4 : 0);
-    static constexpr int OFF_HDR = OFF_P + (HAS_P ? TILE * 16 : 0);  // int4 {first particle, count, first residue, residues}
+    static constexpr int OFF_HDR = OFF_P + (HAS_P ? TILE * VB : 0);   // int4 {first particle, count, first residue, residues}
     static constexpr int BYTES = OFF_HDR + 16;
 };
 
-template <int KIND, int FFMT, bool USE_COM>
+template <int KIND, int FFMT, bool USE_COM, int PREC>
 struct SmemLayout {
-    using Stage = StageLayout<KIND, FFMT>;
+    using Stage = StageLayout<KIND, FFMT, PREC>;
     static constexpr bool HAS_KE = (KIND == KIND_B || KIND == KIND_BU || KIND == KIND_KE);
     static constexpr int NSTAGE = (KIND == KIND_A || KIND == KIND_A2) ? 3 : 4;
     static constexpr int OFF_BAR = NSTAGE * Stage::BYTES;         // full[NS], empty[NS] mbarriers
     static constexpr int OFF_TLIST = OFF_BAR + 128;               // int4[TLIST_CAP] bounds of this CTA's first tiles
-    static constexpr int OFF_SCALE = OFF_TLIST + TLIST_CAP * 16;  // double[MAX_T] s^2, float[MAX_T] s - 1
-    static constexpr int OFF_MISC = OFF_SCALE + MAX_T * 12;       // int[4]
+    static constexpr int OFF_SCALE = OFF_TLIST + TLIST_CAP * 16;  // double[MAX_T] s^2, double[MAX_T] s - 1
+    static constexpr int OFF_MISC = OFF_SCALE + MAX_T * 16;       // int[4]
     static constexpr int OFF_WARP = OFF_MISC + 16;                // double[T][16]   (HAS_KE)
     static constexpr int OFF_KE = OFF_WARP + (HAS_KE ? MAX_T * 16 * 8 : 0);
     static int bytes(int T) { return OFF_KE + (HAS_KE ? T * TILE * 8 : 0); }
 };
 
-template <int FFMT>
-__device__ __forceinline__ float3 load_force3(const unsigned char* sF, int idx) {
+// ---- small vector helpers, generic in the arithmetic type ------------------------------------------------------
+template <typename T> struct V3 { T x, y, z; };
+template <typename T> __device__ __forceinline__ V3<T> v3(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
+template <typename T> __device__ __forceinline__ V3<T> operator+(V3<T> a, V3<T> b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> __device__ __forceinline__ V3<T> operator-(V3<T> a, V3<T> b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> __device__ __forceinline__ V3<T> operator-(V3<T> a) { return v3(-a.x, -a.y, -a.z); }
+template <typename T> __device__ __forceinline__ V3<T> operator*(T s, V3<T> a) { return v3(s * a.x, s * a.y, s * a.z); }
+template <typename T> __device__ __forceinline__ T dot3(V3<T> a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+template <typename T> __device__ __forceinline__ T dot3(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// a + s*b with one rounding per component
+template <typename T> __device__ __forceinline__ V3<T> axpy(T s, V3<T> b, V3<T> a) { return v3(fma(s, b.x, a.x), fma(s, b.y, a.y), fma(s, b.z, a.z)); }
+__device__ __forceinline__ V3<float> xyz(float4 q) { return v3(q.x, q.y, q.z); }
+__device__ __forceinline__ V3<double> xyz(double4 q) { return v3(q.x, q.y, q.z); }
+__device__ __forceinline__ float4 pack4(V3<float> a, float w) { return make_float4(a.x, a.y, a.z, w); }
+__device__ __forceinline__ double4 pack4(V3<double> a, double w) { return make_double4(a.x, a.y, a.z, w); }
+template <typename T> __device__ __forceinline__ V3<double> to_double(V3<T> a) { return v3((double)a.x, (double)a.y, (double)a.z); }
+
+__device__ __forceinline__ void st_global(double4* p, double4 v) {
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(reinterpret_cast<double2*>(p) + 1), "d"(v.z), "d"(v.w) : "memory");
+}
+
+template <int FFMT, typename T>
+__device__ __forceinline__ V3<T> load_force3(const unsigned char* sF, int idx) {
     if (FFMT == 1) {
         const long long* f = reinterpret_cast<const long long*>(sF);
-        return make_float3((float)f[idx], (float)f[PADW + idx], (float)f[2 * PADW + idx]);
+        return v3((T)f[idx], (T)f[PADW + idx], (T)f[2 * PADW + idx]);
     }
     const float* f = reinterpret_cast<const float*>(sF);
-    return make_float3(f[idx], f[PADW + idx], f[2 * PADW + idx]);
+    return v3((T)f[idx], (T)f[PADW + idx], (T)f[2 * PADW + idx]);
 }
 
 // approximate reciprocal / rsqrt: 1 MUFU each, <= 1 ulp-class error; exact IEEE division would cost ~10
@@ -119,97 +152,130 @@ __device__ __forceinline__ float rcp_fast(float x) {
 }
 // second-order term of the reciprocal: 1/w = r + rcp_lo(w, r) to ~1e-14 for r = rcp_fast(w)
 __device__ __forceinline__ float rcp_lo(float w, float r) { return r * fmaf(-w, r, 1.0f); }
-// Masses that weight the kinetic-energy sums are formed in double from that pair.  A species' rounded fp32
-// mass (all oxygens share one w) would otherwise shift its thermostat's energy by up to 6e-8 — systematically,
-// so it does not average out over particles, and the Nose-Hoover chain integrates it.
-__device__ __forceinline__ double mass_d(float w, float r) { return (double)r + (double)rcp_lo(w, r); }
 // 1/x in double from a float seed: two Newton steps (1e-7 -> 1e-14 -> rounding)
 __device__ __forceinline__ double rcp_d(double x, float seed) {
     double r = (double)seed;
     r = r * fma(-x, r, 2.0);
     return r * fma(-x, r, 2.0);
 }
+__device__ __forceinline__ double rcp_fast(double x) { return rcp_d(x, rcp_fast((float)x)); }
+// Masses that weight the kinetic-energy sums are formed in double.  In the fp32 layout a species' rounded mass (all
+// oxygens share one w) would otherwise shift its thermostat's energy by up to 6e-8 — systematically, so it does not
+// average out over particles, and the Nose-Hoover chain integrates it.
+__device__ __forceinline__ double mass_d(float w, float r) { return (double)r + (double)rcp_lo(w, r); }
+__device__ __forceinline__ double mass_d(double w, double r) { return r; }
 __device__ __forceinline__ float rsqrt_fast(float x) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ double rsqrt_fast(double x) { return rsqrt(x); }
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double fast_div(double a, double b) { return a / b; }
 
 // applyHardWallConstraints (drudeTGNH.cu:487-572) for one pair that is beyond the wall.
 // 1 = Drude particle, 2 = parent.  `delta` is x1 - x2, r2 its squared length.
-__device__ __forceinline__ void hard_wall(float3 delta, float r2, float3& x1, float3& x2, float3& v1, float3& v2, float w1, float w2,
-                                       float rmax, float hardwallScale, float dt) {
-    const float rInv = rsqrt_fast(r2);
-    const float r = r2 * rInv;
-    const float3 bondDir = make_float3(delta.x * rInv, delta.y * rInv, delta.z * rInv);
-    const float mass1 = rcp_fast(w1);
-    const float deltaR = r - rmax;
-    float deltaT = dt;
-    float dotvr1 = v1.x * bondDir.x + v1.y * bondDir.y + v1.z * bondDir.z;
-    const float3 vp1 = make_float3(v1.x - bondDir.x * dotvr1, v1.y - bondDir.y * dotvr1, v1.z - bondDir.z * dotvr1);
-    const float vBond = hardwallScale * sqrtf(w1);                    // hardwallscaleDrude / SQRT(mass1)
-    if (w2 == 0.0f) {
+template <typename T>
+__device__ __forceinline__ void hard_wall(V3<T> delta, T r2, V3<T>& x1, V3<T>& x2, V3<T>& v1, V3<T>& v2, T w1, T w2, T rmax, T hardwallScale, T dt) {
+    const T rInv = rsqrt_fast(r2);
+    const T r = r2 * rInv;
+    const V3<T> bondDir = rInv * delta;
+    const T mass1 = rcp_fast(w1);
+    const T deltaR = r - rmax;
+    T deltaT = dt;
+    T dotvr1 = dot3(v1, bondDir);
+    const V3<T> vp1 = axpy(-dotvr1, bondDir, v1);
+    const T vBond = hardwallScale * sqrt(w1);                         // hardwallscaleDrude / SQRT(mass1)
+    if (w2 == T(0)) {
         // massless parent: only the Drude particle moves (:504-526)
-        if (dotvr1 != 0.0f) deltaT = __fdividef(deltaR, fabsf(dotvr1));
+        if (dotvr1 != T(0)) deltaT = fast_div(deltaR, fabs(dotvr1));
         if (deltaT > dt) deltaT = dt;
-        dotvr1 = -copysignf(vBond, dotvr1);                           // -dotvr1*scale/(|dotvr1|*sqrt(m1))
-        const float dr = -deltaR + deltaT * dotvr1;
-        x1.x += bondDir.x * dr; x1.y += bondDir.y * dr; x1.z += bondDir.z * dr;
-        v1 = make_float3(vp1.x + bondDir.x * dotvr1, vp1.y + bondDir.y * dotvr1, vp1.z + bondDir.z * dotvr1);
+        dotvr1 = -copysign(vBond, dotvr1);                            // -dotvr1*scale/(|dotvr1|*sqrt(m1))
+        const T dr = -deltaR + deltaT * dotvr1;
+        x1 = axpy(dr, bondDir, x1);
+        v1 = axpy(dotvr1, bondDir, vp1);
     } else {
-        const float mass2 = rcp_fast(w2);
-        const float invTotalMass = rcp_fast(mass1 + mass2);
-        float dotvr2 = v2.x * bondDir.x + v2.y * bondDir.y + v2.z * bondDir.z;
-        const float3 vp2 = make_float3(v2.x - bondDir.x * dotvr2, v2.y - bondDir.y * dotvr2, v2.z - bondDir.z * dotvr2);
-        const float vbCMass = (mass1 * dotvr1 + mass2 * dotvr2) * invTotalMass;
+        const T mass2 = rcp_fast(w2);
+        const T invTotalMass = rcp_fast(mass1 + mass2);
+        T dotvr2 = dot3(v2, bondDir);
+        const V3<T> vp2 = axpy(-dotvr2, bondDir, v2);
+        const T vbCMass = (mass1 * dotvr1 + mass2 * dotvr2) * invTotalMass;
         dotvr1 -= vbCMass;
         dotvr2 -= vbCMass;
-        if (dotvr1 != dotvr2) deltaT = __fdividef(deltaR, fabsf(dotvr1 - dotvr2));
+        if (dotvr1 != dotvr2) deltaT = fast_div(deltaR, fabs(dotvr1 - dotvr2));
         if (deltaT > dt) deltaT = dt;
-        dotvr1 = -copysignf(vBond * mass2 * invTotalMass, dotvr1);    // :542  (-dotvr1*vBond*m2/M/|dotvr1|)
-        dotvr2 = -copysignf(vBond * mass1 * invTotalMass, dotvr2);    // :543
-        const float dr1 = -deltaR * mass2 * invTotalMass + deltaT * dotvr1;
-        const float dr2 = deltaR * mass1 * invTotalMass + deltaT * dotvr2;
+        dotvr1 = -copysign(vBond * mass2 * invTotalMass, dotvr1);    // :542  (-dotvr1*vBond*m2/M/|dotvr1|)
+        dotvr2 = -copysign(vBond * mass1 * invTotalMass, dotvr2);    // :543
+        const T dr1 = -deltaR * mass2 * invTotalMass + deltaT * dotvr1;
+        const T dr2 = deltaR * mass1 * invTotalMass + deltaT * dotvr2;
         dotvr1 += vbCMass;
         dotvr2 += vbCMass;
-        x1.x += bondDir.x * dr1; x1.y += bondDir.y * dr1; x1.z += bondDir.z * dr1;
-        x2.x += bondDir.x * dr2; x2.y += bondDir.y * dr2; x2.z += bondDir.z * dr2;
-        v1 = make_float3(vp1.x + bondDir.x * dotvr1, vp1.y + bondDir.y * dotvr1, vp1.z + bondDir.z * dotvr1);
-        v2 = make_float3(vp2.x + bondDir.x * dotvr2, vp2.y + bondDir.y * dotvr2, vp2.z + bondDir.z * dotvr2);
+        x1 = axpy(dr1, bondDir, x1);
+        x2 = axpy(dr2, bondDir, x2);
+        v1 = axpy(dotvr1, bondDir, vp1);
+        v2 = axpy(dotvr2, bondDir, vp2);
     }
 }
 
-__device__ __forceinline__ float dot3(float3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
-
 // v + eT*r + eCOM*V + c*rel (e = s - 1) with a fixed evaluation order, so that the two threads of a Drude pair compute
 // bit-identical values for each other's particle (both must take the same side of the hard-wall test)
-__device__ __forceinline__ float3 scaled_velocity(float3 v, float eT, float3 r, float eCOM, float3 V, float c, float3 rel) {
-    return make_float3(v.x + fmaf(c, rel.x, fmaf(eT, r.x, eCOM * V.x)), v.y + fmaf(c, rel.y, fmaf(eT, r.y, eCOM * V.y)),
-                       v.z + fmaf(c, rel.z, fmaf(eT, r.z, eCOM * V.z)));
+template <typename T>
+__device__ __forceinline__ V3<T> scaled_velocity(V3<T> v, T eT, V3<T> r, T eCOM, V3<T> V, T c, V3<T> rel) {
+    return v3(v.x + fma(c, rel.x, fma(eT, r.x, eCOM * V.x)), v.y + fma(c, rel.y, fma(eT, r.y, eCOM * V.y)),
+              v.z + fma(c, rel.z, fma(eT, r.z, eCOM * V.z)));
 }
-__device__ __forceinline__ float3 kicked(float3 v, float fw, float3 F) {
-    return make_float3(fmaf(fw, F.x, v.x), fmaf(fw, F.y, v.y), fmaf(fw, F.z, v.z));
-}
+template <typename T> __device__ __forceinline__ V3<T> kicked(V3<T> v, T fw, V3<T> F) { return axpy(fw, F, v); }
+
+// positions: single = posq; mixed = posq + posqCorrection in double (drudeTGNH.cu:441-448, 476-486)
+template <int PREC> struct PosTile;
+template <> struct PosTile<0> {
+    const float4* sx;
+    __device__ __forceinline__ V3<float> load(int i, float& q) const { const float4 p = sx[i]; q = p.w; return v3(p.x, p.y, p.z); }
+    __device__ __forceinline__ static void store(const StreamArgs& a, int gi, V3<float> x, float q) { st_stream(a.posq + gi, make_float4(x.x, x.y, x.z, q)); }
+};
+template <> struct PosTile<1> {
+    const float4* sx;
+    const float4* sc;
+    __device__ __forceinline__ V3<double> load(int i, float& q) const {
+        const float4 p = sx[i], c = sc[i];
+        q = p.w;
+        return v3(p.x + (double)c.x, p.y + (double)c.y, p.z + (double)c.z);
+    }
+    __device__ __forceinline__ static void store(const StreamArgs& a, int gi, V3<double> x, float q) {
+        const float hx = (float)x.x, hy = (float)x.y, hz = (float)x.z;                       // :457-458
+        st_stream(a.posq + gi, make_float4(hx, hy, hz, q));
+        st_stream(a.posqCorrection + gi, make_float4((float)(x.x - hx), (float)(x.y - hy), (float)(x.z - hz), 0.0f));
+    }
+};
+
+template <int PREC> __device__ __forceinline__ PosTile<PREC> make_pos(const float4* sx, const float4* sc);
+template <> __device__ __forceinline__ PosTile<0> make_pos<0>(const float4* sx, const float4*) { PosTile<0> p; p.sx = sx; return p; }
+template <> __device__ __forceinline__ PosTile<1> make_pos<1>(const float4* sx, const float4* sc) { PosTile<1> p; p.sx = sx; p.sc = sc; return p; }
 
 // L2 hand-over: velm is written by one streaming launch and read (then overwritten) by the next.  B200's L2
 // holds 126 MB, so when consecutive launches walk the tiles in opposite directions the tail of what the
 // previous launch wrote is still resident: those reads never reach HBM and the dirty lines are overwritten in
 // L2 before they are evicted.  velm stores therefore use the default L2 policy while everything that is touched
 // once per step (posq, forces, descriptors) is loaded evict-first / stored streaming.
-template <int KIND, int FFMT, bool USE_COM, bool HARDWALL>
-__global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_constant__ StreamArgs a) {
-    using L = SmemLayout<KIND, FFMT, USE_COM>;
+template <int KIND, int FFMT, bool USE_COM, bool HARDWALL, int PREC>
+__global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const __grid_constant__ StreamArgs a) {
+    using L = SmemLayout<KIND, FFMT, USE_COM, PREC>;
     using St = typename L::Stage;
+    using real = typename Prec<PREC>::real;
+    using real4 = typename Prec<PREC>::real4;
+    using R3 = V3<real>;
     constexpr int NS = L::NSTAGE;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* empty = full + NS;
     int4* tlist = reinterpret_cast<int4*>(smem + L::OFF_TLIST);
     double* ssq = reinterpret_cast<double*>(smem + L::OFF_SCALE);         // s_g^2
-    float* seps = reinterpret_cast<float*>(ssq + MAX_T);                  // s_g - 1
+    double* seps = ssq + MAX_T;                                           // s_g - 1
     int* smisc = reinterpret_cast<int*>(smem + L::OFF_MISC);
     double* ske = reinterpret_cast<double*>(smem + L::OFF_KE);
     double* swarp = reinterpret_cast<double*>(smem + L::OFF_WARP);
+    real4* gvelm = static_cast<real4*>(a.velm);
+    real4* gdelta = static_cast<real4*>(a.posDelta);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = a.chain.T, G = a.chain.G;
@@ -245,10 +311,10 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
         }
         bulk_prefetch_l2(a.desc + a0, na * 4);
     };
-    // Request tile `it` of this CTA into its stage (thread 0 only).  `parts`: 1 = everything but velm (arms the barrier
-    // with the full byte count), 2 = velm, 3 = both.  The split exists for the prologue: velm is the only input the
-    // previous launch writes, so the rest can be requested before griddepcontrol.wait, while the chain launch that
-    // precedes a first-half launch is still running.
+    // Request tile `it` of this CTA into its stage (thread 0 only).  `parts`: 1 = everything but velm / posDelta (arms
+    // the barrier with the full byte count), 2 = velm (+ posDelta), 3 = both.  The split exists for the prologue: velm
+    // is the only input the previous launch writes, so the rest can be requested before griddepcontrol.wait, while
+    // the chain launch that precedes a first-half launch is still running.
     auto issue = [&](int it, int parts) {
         const int4 b = it < TLIST_CAP ? tlist[it] : tile_bounds(it);
         const int start = b.x, end = b.y, r0 = b.z, r1 = b.w;
@@ -257,14 +323,17 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
         uint64_t* bar = &full[it % NS];
         if (parts & 1) {
             *reinterpret_cast<int4*>(st + St::OFF_HDR) = make_int4(start, n, r0, r1 - r0);
-            uint32_t bytes = n * 16 + na * 4;
+            uint32_t bytes = n * St::VB + na * 4;
             const int ra0 = r0 & ~3, rna = ((r1 + 1 + 3) & ~3) - ra0;     // residues r0..r1 inclusive (r1 = end marker)
             if (St::HAS_R) bytes += rna * 4;
-            if (St::HAS_X) bytes += n * 16;
-            if (St::HAS_P) bytes += n * 16;
+            if (St::HAS_X) bytes += n * (PREC ? 32 : 16);
+            if (St::HAS_P) bytes += n * St::VB;
             if (St::HAS_F) bytes += 3 * na * St::FBYTES;
             mbar_arrive_expect_tx(bar, bytes);
-            if (St::HAS_X) bulk_g2s(st + St::OFF_X, a.posq + start, n * 16, bar, polOnce);
+            if (St::HAS_X) {
+                bulk_g2s(st + St::OFF_X, a.posq + start, n * 16, bar, polOnce);
+                if (PREC) bulk_g2s(st + St::OFF_XC, a.posqCorrection + start, n * 16, bar, polOnce);
+            }
             if (St::HAS_F) {
                 const unsigned char* f = static_cast<const unsigned char*>(a.force);
                 for (int c = 0; c < 3; c++)
@@ -275,8 +344,8 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
             if (St::HAS_R) bulk_g2s(st + St::OFF_R, a.resStart + ra0, rna * 4, bar, polOnce);
         }
         if (parts & 2) {
-            bulk_g2s(st + St::OFF_V, a.velm + start, n * 16, bar, polOnce);
-            if (St::HAS_P) bulk_g2s(st + St::OFF_P, a.posDelta + start, n * 16, bar, polOnce);   // written by the caller's constraint kernels
+            bulk_g2s(st + St::OFF_V, gvelm + start, n * St::VB, bar, polOnce);
+            if (St::HAS_P) bulk_g2s(st + St::OFF_P, gdelta + start, n * St::VB, bar, polOnce);   // written by the caller's constraint kernels
         }
     };
     if (tid == 0) {
@@ -289,22 +358,23 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
     if (tid < T) {
         const double sg = (KIND == KIND_B || KIND == KIND_BU || KIND == KIND_A2) ? 1.0 : a.chain.scaleA[tid];
         ssq[tid] = sg * sg;
-        seps[tid] = (float)(sg - 1.0);
+        seps[tid] = sg - 1.0;
     }
     __syncthreads();
 
     const bool doScale = (KIND == KIND_A || KIND == KIND_A1) || (KIND == KIND_KE && a.applyScale);
-    const float eCOM = doScale ? seps[G] : 0.0f;
-    const float eDrude = doScale ? seps[G + 1] : 0.0f;
-    const float rmax2 = a.rmax * a.rmax;
+    const real eCOM = doScale ? (real)seps[G] : real(0);
+    const real eDrude = doScale ? (real)seps[G + 1] : real(0);
+    const real dt = (real)a.dt, fscale = (real)a.fscale, rmax = (real)a.rmax;
+    const real rmax2 = rmax * rmax;
     double accCOM = 0.0, accDrude = 0.0;               // this thread's share of the COM-group and Drude-group sums
 
     for (int it = 0; it < myTiles; it++) {
         const int stg = it % NS;
         const uint32_t phase = (it / NS) & 1;
         unsigned char* st = smem + stg * St::BYTES;
-        const float4* sv = reinterpret_cast<const float4*>(st + St::OFF_V);
-        const float4* sx = reinterpret_cast<const float4*>(st + St::OFF_X);
+        const real4* sv = reinterpret_cast<const real4*>(st + St::OFF_V);
+        const PosTile<PREC> pos = make_pos<PREC>(reinterpret_cast<const float4*>(st + St::OFF_X), reinterpret_cast<const float4*>(st + St::OFF_XC));
         const unsigned char* sF = st + St::OFF_F;
         const uint32_t* sd = reinterpret_cast<const uint32_t*>(st + St::OFF_D);
 
@@ -314,71 +384,76 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
         const int fo = start & 3;                     // offset of the tile inside its 4-aligned window
 
         const bool active = tid < n;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        real4 v4;
+        v4.x = v4.y = v4.z = v4.w = real(0);
         uint32_t d = 0;                               // inactive lanes: ordinary particle, partner = self, residue = self
-        if (active) { v = sv[tid]; d = sd[fo + tid]; }
+        if (active) { v4 = sv[tid]; d = sd[fo + tid]; }
+        const R3 v = xyz(v4);
+        const real w = v4.w;
         const int tg = desc_tg(d);
         const uint32_t role = desc_role(d);
-        const bool massive = v.w != 0.0f;
+        const bool massive = w != real(0);
         const int pj = tid + desc_partner(d);         // ordinary particles: partner == self
-        const float4 vj = active ? sv[pj] : v;
-        const float m = massive ? rcp_fast(v.w) : 0.0f;
-        const float mj = rcp_fast(vj.w);
-        const float invTot = rcp_fast(m + mj);
-        const float fi = m * invTot, fj = mj * invTot;        // mass fractions of this particle and of its partner
-        float3 rel = make_float3(vj.x - v.x, vj.y - v.y, vj.z - v.z);   // partner minus me (0 for ordinary particles)
-        const float eT = doScale ? seps[tg] : 0.0f;
-        const float coef = (eT - eDrude);            // sT - sDrude
+        const real4 vj4 = active ? sv[pj] : v4;
+        const R3 vj = xyz(vj4);
+        const real wj = vj4.w;
+        const real m = massive ? rcp_fast(w) : real(0);
+        const real mj = rcp_fast(wj);
+        const real invTot = rcp_fast(m + mj);
+        const real fi = m * invTot, fj = mj * invTot;        // mass fractions of this particle and of its partner
+        R3 rel = vj - v;                              // partner minus me (0 for ordinary particles)
+        const real eT = doScale ? (real)seps[tg] : real(0);
+        const real coef = (eT - eDrude);              // sT - sDrude
 
-        float3 F = make_float3(0.f, 0.f, 0.f), Fj = F;
-        if (St::HAS_F && active) { F = load_force3<FFMT>(sF, fo + tid); Fj = load_force3<FFMT>(sF, fo + pj); }
-        const float fw = a.fscale * v.w, fwj = a.fscale * vj.w;
+        R3 F = v3(real(0), real(0), real(0)), Fj = F;
+        if (St::HAS_F && active) { F = load_force3<FFMT, real>(sF, fo + tid); Fj = load_force3<FFMT, real>(sF, fo + pj); }
+        const real fw = fscale * w, fwj = fscale * wj;
 
         // residue centre-of-mass velocity (calcCOMVelocities, drudeTGNH.cu:86-105); for the second half it is taken
-        // after the kick: sum_j m_j (v_j + fscale w_j F_j) = sum_j (m_j v_j + fscale F_j) over the massive members
-        float3 V = make_float3(0.f, 0.f, 0.f);
+        // after the kick
+        R3 V = v3(real(0), real(0), real(0));
         double keC = 0.0;                             // M |V|^2 of this particle's residue (kinds that reduce energies)
         if (USE_COM && active && KIND != KIND_BU && KIND != KIND_A2) {
             const int j0 = tid - desc_off_first(d), j1 = tid + desc_off_last(d);
-            if (!L::HAS_KE) {
-                // first half: V only feeds the small corrections (sT-1)(v - V) and (sCOM-1) V, fp32 sums are ample
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!L::HAS_KE && !PREC) {
+                // first half, fp32 layout: V only feeds the small corrections (sT-1)(v - V) and (sCOM-1) V, fp32 sums are ample
+                R3 P = v3(real(0), real(0), real(0));
+                real M = real(0);
                 for (int j = j0; j <= j1; j++) {
-                    const float4 q = sv[j];
-                    const float mq = q.w != 0.0f ? rcp_fast(q.w) : 0.0f;
-                    acc.x = fmaf(q.x, mq, acc.x); acc.y = fmaf(q.y, mq, acc.y); acc.z = fmaf(q.z, mq, acc.z);
-                    acc.w += mq;
+                    const real4 q = sv[j];
+                    const real mq = q.w != real(0) ? rcp_fast(q.w) : real(0);
+                    P = axpy(mq, xyz(q), P);
+                    M += mq;
                 }
-                const float inv = rcp_fast(acc.w);
-                V = make_float3(acc.x * inv, acc.y * inv, acc.z * inv);
+                V = rcp_fast(M) * P;
             } else {
-                // kinds that reduce energies: momentum and mass of the residue in double (see mass_d)
-                double Px = 0.0, Py = 0.0, Pz = 0.0, M = 0.0;
+                // momentum and mass of the residue in double (see mass_d)
+                V3<double> P = v3(0.0, 0.0, 0.0);
+                double M = 0.0;
                 for (int j = j0; j <= j1; j++) {
-                    const float4 q = sv[j];
-                    const bool mass = q.w != 0.0f;
-                    const float mq = mass ? rcp_fast(q.w) : 0.0f;
+                    const real4 q = sv[j];
+                    const bool mass = q.w != real(0);
+                    const real mq = mass ? rcp_fast(q.w) : real(0);
                     const double mqd = mass ? mass_d(q.w, mq) : 0.0;
-                    float3 vq = make_float3(q.x, q.y, q.z);
-                    if (KIND == KIND_B) vq = kicked(vq, a.fscale * q.w, load_force3<FFMT>(sF, fo + j));   // what member j stores
-                    Px = fma(mqd, (double)vq.x, Px); Py = fma(mqd, (double)vq.y, Py); Pz = fma(mqd, (double)vq.z, Pz);
+                    R3 vq = xyz(q);
+                    if (KIND == KIND_B) vq = kicked(vq, fscale * q.w, load_force3<FFMT, real>(sF, fo + j));   // what member j stores
+                    P = axpy(mqd, to_double(vq), P);
                     M += mqd;
                 }
-                const double invM = rcp_d(M, rcp_fast((float)M));
-                const double Vx = Px * invM, Vy = Py * invM, Vz = Pz * invM;
-                V = make_float3((float)Vx, (float)Vy, (float)Vz);
-                keC = M * fma(Vx, Vx, fma(Vy, Vy, Vz * Vz));
+                const V3<double> Vd = rcp_d(M, rcp_fast((float)M)) * P;
+                V = v3((real)Vd.x, (real)Vd.y, (real)Vd.z);
+                keC = M * dot3(Vd);
             }
         }
 
-        float3 vn;                                    // this particle's new velocity
-        float3 r;                                     // ... relative to the residue (after scaling / kick)
+        R3 vn;                                        // this particle's new velocity
+        R3 r;                                         // ... relative to the residue (after scaling / kick)
         if (KIND == KIND_BU) {
             // kick (drudeTGNH.cu:314-364); kinetic energies in the lab frame, the residues' M |V|^2 is removed below
-            vn = kicked(make_float3(v.x, v.y, v.z), fw, F);
-            if (active && massive) st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
-            const float3 vjn = kicked(make_float3(vj.x, vj.y, vj.z), fwj, Fj);
-            rel = make_float3(vjn.x - vn.x, vjn.y - vn.y, vjn.z - vn.z);
+            vn = kicked(v, fw, F);
+            if (active && massive) st_global(gvelm + start + tid, pack4(vn, w));
+            const R3 vjn = kicked(vj, fwj, Fj);
+            rel = vjn - vn;
             r = vn;
             // one thread per residue of the tile; the duty rotates over the warps from tile to tile so that no warp is
             // always the slow one (a stage is recycled only when all 16 warps have left it)
@@ -387,43 +462,44 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
                 // P = sum_j m_j v_j (kicked velocities), M = sum_j m_j over the residue's massive members
                 const int* sr = reinterpret_cast<const int*>(st + St::OFF_R) + (hdr.z & 3);
                 const int j0 = sr[ridx] - start, j1 = sr[ridx + 1] - start;
-                double Px = 0.0, Py = 0.0, Pz = 0.0, M = 0.0;
+                V3<double> P = v3(0.0, 0.0, 0.0);
+                double M = 0.0;
                 for (int j = j0; j < j1; j++) {
-                    const float4 q = sv[j];
-                    const bool mass = q.w != 0.0f;
-                    const float mq = mass ? rcp_fast(q.w) : 0.0f;
+                    const real4 q = sv[j];
+                    const bool mass = q.w != real(0);
+                    const real mq = mass ? rcp_fast(q.w) : real(0);
                     const double mqd = mass ? mass_d(q.w, mq) : 0.0;
-                    const float3 vq = kicked(make_float3(q.x, q.y, q.z), a.fscale * q.w, load_force3<FFMT>(sF, fo + j));   // what member j stores
-                    Px = fma(mqd, (double)vq.x, Px); Py = fma(mqd, (double)vq.y, Py); Pz = fma(mqd, (double)vq.z, Pz);
+                    const R3 vq = kicked(xyz(q), fscale * q.w, load_force3<FFMT, real>(sF, fo + j));   // what member j stores
+                    P = axpy(mqd, to_double(vq), P);
                     M += mqd;
                 }
-                const double keC = fma(Px, Px, fma(Py, Py, Pz * Pz)) * rcp_d(M, rcp_fast((float)M));   // M |V|^2 = |P|^2 / M
-                accCOM += keC;
-                ske[desc_tg(sd[fo + j0]) * TILE + tid] -= keC;
+                const double keRes = dot3(P) * rcp_d(M, rcp_fast((float)M));   // M |V|^2 = |P|^2 / M
+                accCOM += keRes;
+                ske[desc_tg(sd[fo + j0]) * TILE + tid] -= keRes;
             }
         } else if (KIND == KIND_B) {
             // integrateDrudeTGNHVelocities (drudeTGNH.cu:314-364), updatePosDelta = false
-            vn = kicked(make_float3(v.x, v.y, v.z), fw, F);
-            if (active && massive) st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
-            rel = make_float3(rel.x + fwj * Fj.x - fw * F.x, rel.y + fwj * Fj.y - fw * F.y, rel.z + fwj * Fj.z - fw * F.z);
-            r = make_float3(vn.x - V.x, vn.y - V.y, vn.z - V.z);
+            vn = kicked(v, fw, F);
+            if (active && massive) st_global(gvelm + start + tid, pack4(vn, w));
+            rel = axpy(fwj, Fj, axpy(-fw, F, rel));
+            r = vn - V;
         } else {
             // thermostat scaling (integrateDrudeTGNHChain, drudeTGNH.cu:255-300) in the unified form of the header comment
-            r = make_float3(v.x - V.x, v.y - V.y, v.z - V.z);
-            vn = scaled_velocity(make_float3(v.x, v.y, v.z), eT, r, eCOM, V, coef * fj, rel);
+            r = v - V;
+            vn = scaled_velocity(v, eT, r, eCOM, V, coef * fj, rel);
         }
 
         if (L::HAS_KE) {
             // computeNormalizedKineticEnergies (drudeTGNH.cu:152-188), branch-free: an ordinary particle is its own
             // "pair centre of mass" (rel = 0); the Drude particle of a pair carries the pair's two terms
-            const float3 cm = make_float3(r.x + fj * rel.x, r.y + fj * rel.y, r.z + fj * rel.z);    // pair COM relative to the residue
+            const R3 cm = axpy(fj, rel, r);           // pair COM relative to the residue
             const bool isDrude = role == ROLE_DRUDE;
-            const double md = massive ? mass_d(v.w, m) : 0.0, mjd = mass_d(vj.w, mj);
+            const double md = massive ? mass_d(w, m) : 0.0, mjd = mass_d(wj, mj);
             const double Mp = md + mjd;
             const double massT = isDrude ? Mp : (role == ROLE_NORMAL ? md : 0.0);
             const double s2T = doScale ? ssq[tg] : 1.0, s2D = doScale ? ssq[G + 1] : 1.0, s2C = doScale ? ssq[G] : 1.0;
             const double keT = massT * s2T * (double)dot3(cm);
-            const double keD = isDrude ? md * mjd * rcp_d(Mp, invTot) * s2D * (double)dot3(rel) : 0.0;   // reduced mass
+            const double keD = isDrude ? md * mjd * rcp_d(Mp, (float)invTot) * s2D * (double)dot3(rel) : 0.0;   // reduced mass
             if (!(USE_COM && KIND != KIND_BU && active && desc_off_first(d) == 0)) keC = 0.0;        // the residue's first particle carries M |V|^2
             keC *= s2C;
             if (active && massT != 0.0) ske[tg * TILE + tid] += keT;
@@ -432,60 +508,64 @@ __global__ void __launch_bounds__(TILE, 2) tgnh_stream_kernel(const __grid_const
         }
 
         if (KIND == KIND_KE) {
-            if (doScale && active && massive) st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
+            if (doScale && active && massive) st_global(gvelm + start + tid, pack4(vn, w));
         } else if (KIND == KIND_A1) {
             // scaling + half kick; posDelta = dt * v for OpenMM's constraint kernels (drudeTGNH.cu:322-324, 360-363)
             vn = kicked(vn, fw, F);
             if (active && massive) {
-                st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
-                st_global(a.posDelta + start + tid, make_float4(a.dt * vn.x, a.dt * vn.y, a.dt * vn.z, 0.0f));
+                st_global(gvelm + start + tid, pack4(vn, w));
+                st_global(gdelta + start + tid, pack4(dt * vn, real(0)));
             }
         } else if (KIND == KIND_A2 && active) {
             // integrateDrudeTGNHPositions (drudeTGNH.cu:438-465): x += delta, v = delta / dt; then the hard wall (:474-573)
-            const float4* sp = reinterpret_cast<const float4*>(st + St::OFF_P);
-            const float invDt = 1.0f / a.dt;
-            const float4 dl = sp[tid], x = sx[tid];
-            float3 xn = make_float3(x.x + dl.x, x.y + dl.y, x.z + dl.z);
-            vn = make_float3(dl.x * invDt, dl.y * invDt, dl.z * invDt);
+            const real4* sp = reinterpret_cast<const real4*>(st + St::OFF_P);
+            const real invDt = real(1) / dt;
+            float q;
+            const R3 dl = xyz(sp[tid]), x = pos.load(tid, q);
+            R3 xn = x + dl;
+            vn = invDt * dl;
             if (HARDWALL && role != ROLE_NORMAL) {
-                const float4 dj = sp[pj], xj = sx[pj];
-                float3 vjn = make_float3(dj.x * invDt, dj.y * invDt, dj.z * invDt);
-                float3 delta = make_float3((x.x - xj.x) + (dl.x - dj.x), (x.y - xj.y) + (dl.y - dj.y), (x.z - xj.z) + (dl.z - dj.z));
-                const float r2 = dot3(delta);
+                float qj;
+                const R3 dj = xyz(sp[pj]), xj = pos.load(pj, qj);
+                R3 vjn = invDt * dj;
+                const R3 delta = (x - xj) + (dl - dj);
+                const real r2 = dot3(delta);
                 if (r2 > rmax2) {
-                    float3 xjn = make_float3(xj.x + dj.x, xj.y + dj.y, xj.z + dj.z);
-                    if (role == ROLE_DRUDE) hard_wall(delta, r2, xn, xjn, vn, vjn, v.w, vj.w, a.rmax, a.hardwallScale, a.dt);
-                    else hard_wall(make_float3(-delta.x, -delta.y, -delta.z), r2, xjn, xn, vjn, vn, vj.w, v.w, a.rmax, a.hardwallScale, a.dt);
+                    R3 xjn = xj + dj;
+                    if (role == ROLE_DRUDE) hard_wall(delta, r2, xn, xjn, vn, vjn, w, wj, rmax, (real)a.hardwallScale, dt);
+                    else hard_wall(-delta, r2, xjn, xn, vjn, vn, wj, w, rmax, (real)a.hardwallScale, dt);
                 }
             }
             if (massive) {
-                st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
-                st_stream(a.posq + start + tid, make_float4(xn.x, xn.y, xn.z, x.w));
+                st_global(gvelm + start + tid, pack4(vn, w));
+                PosTile<PREC>::store(a, start + tid, xn, q);
             }
         } else if (KIND == KIND_A && active) {
             // half kick + drift (+ hard wall) (drudeTGNH.cu:314-364, 438-465, 474-573)
             vn = kicked(vn, fw, F);
-            const float4 x = sx[tid];
-            float3 xn = make_float3(x.x + a.dt * vn.x, x.y + a.dt * vn.y, x.z + a.dt * vn.z);
+            float q;
+            const R3 x = pos.load(tid, q);
+            R3 xn = axpy(dt, vn, x);
             if (HARDWALL && role != ROLE_NORMAL) {
                 // the partner's update, recomputed here so that both threads of a pair see the same wall test;
                 // seen from the partner, rel changes sign and the mass fraction is this particle's
-                const float3 rj = make_float3(vj.x - V.x, vj.y - V.y, vj.z - V.z);
-                float3 vjn = kicked(scaled_velocity(make_float3(vj.x, vj.y, vj.z), eT, rj, eCOM, V, coef * fi, make_float3(-rel.x, -rel.y, -rel.z)), fwj, Fj);
-                const float4 xj = sx[pj];
+                const R3 rj = vj - V;
+                R3 vjn = kicked(scaled_velocity(vj, eT, rj, eCOM, V, coef * fi, -rel), fwj, Fj);
+                float qj;
+                const R3 xj = pos.load(pj, qj);
                 // displacement from the exact difference of the old positions plus the relative drift: avoids the
                 // cancellation of two rounded box-sized coordinates in the wall test
-                float3 delta = make_float3((x.x - xj.x) + a.dt * (vn.x - vjn.x), (x.y - xj.y) + a.dt * (vn.y - vjn.y), (x.z - xj.z) + a.dt * (vn.z - vjn.z));
-                const float r2 = dot3(delta);
+                const R3 delta = axpy(dt, vn - vjn, x - xj);
+                const real r2 = dot3(delta);
                 if (r2 > rmax2) {                     // rInv*maxDrudeDistance < 1  (drudeTGNH.cu:490)
-                    float3 xjn = make_float3(xj.x + a.dt * vjn.x, xj.y + a.dt * vjn.y, xj.z + a.dt * vjn.z);
-                    if (role == ROLE_DRUDE) hard_wall(delta, r2, xn, xjn, vn, vjn, v.w, vj.w, a.rmax, a.hardwallScale, a.dt);
-                    else hard_wall(make_float3(-delta.x, -delta.y, -delta.z), r2, xjn, xn, vjn, vn, vj.w, v.w, a.rmax, a.hardwallScale, a.dt);
+                    R3 xjn = axpy(dt, vjn, xj);
+                    if (role == ROLE_DRUDE) hard_wall(delta, r2, xn, xjn, vn, vjn, w, wj, rmax, (real)a.hardwallScale, dt);
+                    else hard_wall(-delta, r2, xjn, xn, vjn, vn, wj, w, rmax, (real)a.hardwallScale, dt);
                 }
             }
             if (massive) {
-                st_global(a.velm + start + tid, make_float4(vn.x, vn.y, vn.z, v.w));
-                st_stream(a.posq + start + tid, make_float4(xn.x, xn.y, xn.z, x.w));
+                st_global(gvelm + start + tid, pack4(vn, w));
+                PosTile<PREC>::store(a, start + tid, xn, q);
             }
         }
 

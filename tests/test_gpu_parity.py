@@ -10,7 +10,7 @@ import pytest
 
 from openmm_drudenose_b200 import capi, synth
 from oracle import oracle as O
-from util import DeviceState, group_temperatures, rel_err
+from util import DeviceState, chain_err, group_temperatures, ke_err, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -36,22 +36,6 @@ def _systems():
 
 
 SYSTEMS = _systems()
-
-
-def ke_err(got, ref, nkbt):
-    """Error of the per-thermostat 2*KE sums in units that matter to the thermostat: relative to the group's own
-    energy scale max(|2KE_g|, N_g kT).  A group without degrees of freedom (N_g kT = 0, e.g. ions whose only
-    relative motion is the Drude pair itself) has 2KE = 0 exactly and no thermostat; there the error is taken
-    relative to the total so that fp32 cancellation noise (1e-9 of the total) is not divided by zero."""
-    scale = np.maximum(np.abs(ref), np.abs(nkbt))
-    scale = np.where(scale > 1e-3 * np.abs(ref).max(), scale, np.abs(ref).max())
-    return float(np.max(np.abs(got - ref) / scale))
-
-
-def chain_err(got, ref):
-    """Chain variables relative to the largest magnitude in the array: eta_dot_0 of a thermostat in equilibrium is a
-    small difference (KE - N kT) / Q of large numbers, so its own magnitude is not a meaningful scale."""
-    return float(np.max(np.abs(got - ref)) / max(np.abs(ref).max(), 1e-300))
 
 
 @pytest.mark.parametrize("name", sorted(SYSTEMS))
