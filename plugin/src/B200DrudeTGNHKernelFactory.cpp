@@ -19,9 +19,11 @@ public:
     explicit CudaContextAccess(CudaContext& cu) : cu(cu) {}
     TgnhDeviceView view() {
         cu.setAsCurrent();
-        if (cu.getUseDoublePrecision() || cu.getUseMixedPrecision())
-            throw OpenMMException("DrudeTGNH (libtgnh): only the single-precision CUDA layout is implemented; create the Context with Precision=single");
+        if (cu.getUseDoublePrecision())
+            throw OpenMMException("DrudeTGNH (libtgnh): the single and mixed CUDA layouts are implemented; create the Context with Precision=single or mixed");
         TgnhDeviceView v;
+        v.precision = cu.getUseMixedPrecision() ? TGNH_PRECISION_MIXED : TGNH_PRECISION_SINGLE;
+        v.posqCorrection = cu.getUseMixedPrecision() ? (void*)cu.getPosqCorrection().getDevicePointer() : NULL;
         v.velm = (void*)cu.getVelm().getDevicePointer();
         v.posq = (void*)cu.getPosq().getDevicePointer();
         v.force = (const void*)cu.getForce().getDevicePointer();

@@ -59,6 +59,7 @@ void B200IntegrateDrudeTGNHStepKernel::initialize(const System& system, const Dr
     p.has_cm_motion_remover = hasCMMotionRemover;
     p.force_format = dv.forceFormat;
     p.device = dv.device;
+    p.precision = dv.precision;
     p.temperature = integrator.getTemperature();
     p.coupling_time = integrator.getCouplingTime();
     p.drude_temperature = integrator.getDrudeTemperature();
@@ -82,6 +83,7 @@ void B200IntegrateDrudeTGNHStepKernel::initialize(const System& system, const Dr
 void B200IntegrateDrudeTGNHStepKernel::execute(ContextImpl& context, const DrudeTGNHIntegrator& integrator) {
     const TgnhDeviceView dv = device.view();
     const double tol = integrator.getConstraintTolerance();
+    if (dv.precision == TGNH_PRECISION_MIXED) check(tgnh_set_posq_correction(handle, dv.posqCorrection));
     if (!constrained) {
         // thermostat half-step, half kick, drift, hard wall in one launch (:336-376)
         check(tgnh_half1(handle, dv.stream, dv.velm, dv.posq, dv.force));

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE — a "CUDA" platform for the OpenMM API shim: owns device arrays in OpenMM's CUDA layouts
-// (float4 velm / posq, SoA forces), moves state between them and the Context's host copies, and evaluates the shim's
+// (single: float4 velm / posq; mixed: double4 velm, float4 posq + float4 posqCorrection; SoA forces), selected with the
+// "Precision" context property like OpenMM's CUDA platform; moves state between them and the Context's host copies, and evaluates the shim's
 // host force model into the device force buffer.  It lets the real plugin stack (DrudeTGNHIntegrator -> KernelImpl ->
 // C-ABI -> sm_100a kernels) run end to end without OpenMM.
 #ifndef TGNH_SHIM_CUDA_PLATFORM_H_
@@ -19,19 +20,21 @@ class ShimCudaPlatform : public Platform {
 public:
     class Data : public TgnhDeviceAccess {
     public:
-        Data(ContextImpl& c, int forceFormat) : ctx(c), n(c.getSystem().getNumParticles()), padded(((n + 31) / 32) * 32), forceFormat(forceFormat),
-              velm(NULL), posq(NULL), force(NULL), posDelta(NULL), time(0.0), steps(0), constraintCalls(0) {
+        Data(ContextImpl& c, int forceFormat, bool mixed) : constraintCalls(0), ctx(c), n(c.getSystem().getNumParticles()), padded(((n + 31) / 32) * 32), forceFormat(forceFormat),
+              mixed(mixed), velm(NULL), posq(NULL), corr(NULL), force(NULL), posDelta(NULL), time(0.0), steps(0) {
             int count = 0;
             if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw OpenMMException("ShimCudaPlatform: no CUDA device");
             const size_t fbytes = (size_t)3 * padded * (forceFormat == TGNH_FORCE_I64_SOA ? 8 : 4);
-            if (cudaMalloc(&velm, (size_t)padded * 16) || cudaMalloc(&posq, (size_t)padded * 16) || cudaMalloc(&force, fbytes) || cudaMalloc(&posDelta, (size_t)padded * 16))
+            const size_t vbytes = (size_t)padded * (mixed ? 32 : 16);
+            if (cudaMalloc(&velm, vbytes) || cudaMalloc(&posq, (size_t)padded * 16) || cudaMalloc(&corr, (size_t)padded * 16) || cudaMalloc(&force, fbytes) ||
+                cudaMalloc(&posDelta, vbytes))
                 throw OpenMMException("ShimCudaPlatform: cudaMalloc failed");
-            cudaMemset(velm, 0, (size_t)padded * 16); cudaMemset(posq, 0, (size_t)padded * 16); cudaMemset(force, 0, fbytes);
-            hv.assign((size_t)padded * 4, 0.f); hx.assign((size_t)padded * 4, 0.f);
+            cudaMemset(velm, 0, vbytes); cudaMemset(posq, 0, (size_t)padded * 16); cudaMemset(corr, 0, (size_t)padded * 16); cudaMemset(force, 0, fbytes);
+            hv.assign((size_t)padded * 4, 0.f); hx.assign((size_t)padded * 4, 0.f); hc.assign((size_t)padded * 4, 0.f); hvd.assign((size_t)padded * 4, 0.0);
         }
-        ~Data() { cudaFree(velm); cudaFree(posq); cudaFree(force); cudaFree(posDelta); }
+        ~Data() { cudaFree(velm); cudaFree(posq); cudaFree(corr); cudaFree(force); cudaFree(posDelta); }
         TgnhDeviceView view() {
-            TgnhDeviceView v = {velm, posq, force, posDelta, padded, forceFormat, NULL, 0};
+            TgnhDeviceView v = {velm, posq, force, posDelta, padded, forceFormat, NULL, 0, mixed ? TGNH_PRECISION_MIXED : TGNH_PRECISION_SINGLE, mixed ? corr : NULL};
             return v;
         }
         void advanceTime(double dt) { time += dt; steps++; ctx.time = time; }
@@ -42,17 +45,33 @@ public:
         void upload() {
             for (int i = 0; i < n; i++) {
                 const double m = ctx.getSystem().getParticleMass(i);
-                for (int c = 0; c < 3; c++) { hv[4 * i + c] = (float)ctx.shimVelocities()[i][c]; hx[4 * i + c] = (float)ctx.shimPositions()[i][c]; }
+                for (int c = 0; c < 3; c++) {
+                    const double x = ctx.shimPositions()[i][c], v = ctx.shimVelocities()[i][c];
+                    hv[4 * i + c] = (float)v; hvd[4 * i + c] = v;
+                    hx[4 * i + c] = (float)x; hc[4 * i + c] = (float)(x - (double)(float)x);
+                }
                 hv[4 * i + 3] = m == 0.0 ? 0.f : (float)(1.0 / m);
+                hvd[4 * i + 3] = m == 0.0 ? 0.0 : 1.0 / m;
             }
-            cudaMemcpy(velm, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice);
+            if (mixed) {
+                cudaMemcpy(velm, hvd.data(), hvd.size() * 8, cudaMemcpyHostToDevice);
+                cudaMemcpy(corr, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
+            } else
+                cudaMemcpy(velm, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice);
             cudaMemcpy(posq, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice);
         }
         void download() {
-            cudaMemcpy(hv.data(), velm, hv.size() * 4, cudaMemcpyDeviceToHost);
             cudaMemcpy(hx.data(), posq, hx.size() * 4, cudaMemcpyDeviceToHost);
+            if (mixed) {
+                cudaMemcpy(hvd.data(), velm, hvd.size() * 8, cudaMemcpyDeviceToHost);
+                cudaMemcpy(hc.data(), corr, hc.size() * 4, cudaMemcpyDeviceToHost);
+            } else
+                cudaMemcpy(hv.data(), velm, hv.size() * 4, cudaMemcpyDeviceToHost);
             for (int i = 0; i < n; i++)
-                for (int c = 0; c < 3; c++) { ctx.shimVelocities()[i][c] = hv[4 * i + c]; ctx.shimPositions()[i][c] = hx[4 * i + c]; }
+                for (int c = 0; c < 3; c++) {
+                    ctx.shimVelocities()[i][c] = mixed ? hvd[4 * i + c] : (double)hv[4 * i + c];
+                    ctx.shimPositions()[i][c] = mixed ? (double)hx[4 * i + c] + (double)hc[4 * i + c] : (double)hx[4 * i + c];
+                }
         }
         /** forces: host model on the downloaded positions, written into the device buffer in the platform's format */
         void forcesOnDevice(const ShimForceModel& model) {
@@ -71,15 +90,20 @@ public:
     private:
         ContextImpl& ctx;
         int n, padded, forceFormat;
-        void *velm, *posq, *force, *posDelta;
+        bool mixed;
+        void *velm, *posq, *corr, *force, *posDelta;
         double time;
         int steps;
-        std::vector<float> hv, hx;
+        std::vector<float> hv, hx, hc;
+        std::vector<double> hvd;
     };
     explicit ShimCudaPlatform(int forceFormat = TGNH_FORCE_I64_SOA) : forceFormat(forceFormat) {}
     const std::string& getName() const { static const std::string n = "CUDA"; return n; }
-    void contextCreated(ContextImpl& context, const std::map<std::string, std::string>&) const {
-        Data* d = new Data(context, forceFormat);
+    void contextCreated(ContextImpl& context, const std::map<std::string, std::string>& properties) const {
+        std::map<std::string, std::string>::const_iterator it = properties.find("Precision");
+        const std::string precision = it == properties.end() ? "single" : it->second;
+        if (precision != "single" && precision != "mixed") throw OpenMMException("ShimCudaPlatform: Precision must be single or mixed");
+        Data* d = new Data(context, forceFormat, precision == "mixed");
         context.setPlatformData(static_cast<TgnhDeviceAccess*>(d));
         context.shimUpload = [d]() { d->upload(); };
         context.shimDownload = [d]() { d->download(); };

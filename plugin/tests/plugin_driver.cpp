@@ -2,6 +2,7 @@
 // plugin/src DrudeTGNHIntegrator -> B200IntegrateDrudeTGNHStepKernel -> libtgnh.so C-ABI -> sm_100a kernels, on the shim's
 // "CUDA" platform.  tests/test_plugin.py compares it with the oracle.
 #include <cstring>
+#include <map>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -33,6 +34,7 @@ struct Sim {
     ~Sim() { delete context; delete integrator; }
 };
 std::vector<std::pair<int, int> > g_nextConstraints;   // consumed by the next ref_create
+std::string g_nextPrecision = "single";                // "Precision" property of the next Context
 Platform* g_platform[2] = {NULL, NULL};
 Platform& platform_for(int forceFormat) {
     // one "CUDA" platform per force format; the kernel factory is registered on whichever is current
@@ -75,7 +77,10 @@ void* ref_create(int n, const double* masses, int npairs, const int* pairDrude, 
         if (tempGroup) for (int i = 0; i < n; i++) s->integrator->addParticleTempGroup(tempGroup[i]);
         s->forceModel = forceModel;
         s->extForce.assign(n, Vec3());
-        s->context = new Context(s->system, *s->integrator, platform_for(1));    // OpenMM's int64 fixed-point force buffer
+        std::map<std::string, std::string> properties;
+        properties["Precision"] = g_nextPrecision;
+        g_nextPrecision = "single";
+        s->context = new Context(s->system, *s->integrator, platform_for(1), properties);    // OpenMM's int64 fixed-point force buffer
         Sim* sp = s;
         ShimCudaPlatform::installForceModel(s->context->getImpl(), [sp](const std::vector<Vec3>& pos, std::vector<Vec3>& f) {
             for (size_t i = 0; i < f.size(); i++) f[i] = sp->extForce[i];
@@ -132,6 +137,8 @@ void plugin_set_next_constraints(int n, const int* a, const int* b) {
     g_nextConstraints.clear();
     for (int i = 0; i < n; i++) g_nextConstraints.push_back(std::make_pair(a[i], b[i]));
 }
+
+void plugin_set_next_precision(const char* precision) { g_nextPrecision = precision; }
 
 int plugin_constraint_calls(void* h) {
     Sim* s = (Sim*)h;

@@ -23,6 +23,7 @@ def lib():
         L.ref_step.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp]
         L.plugin_set_next_constraints.argtypes = [C.c_int, ip, ip]
         L.plugin_constraint_calls.argtypes = [C.c_void_p]
+        L.plugin_set_next_precision.argtypes = [C.c_char_p]
         L.plugin_kinetic_energy.argtypes = [C.c_void_p]
         L.plugin_kinetic_energy.restype = C.c_double
         _lib = L
@@ -38,9 +39,10 @@ def _ip(a):
 
 
 class PluginSim:
-    def __init__(self, system, force_model=0, has_cm_motion_remover=False, with_constraints=False):
+    def __init__(self, system, force_model=0, has_cm_motion_remover=False, with_constraints=False, precision="single"):
         s = system
         L = lib()
+        L.plugin_set_next_precision(precision.encode())      # the Context's "Precision" platform property
         if with_constraints and len(s.constraints):
             c = np.ascontiguousarray(s.constraints, np.int32)
             a, b = np.ascontiguousarray(c[:, 0]), np.ascontiguousarray(c[:, 1])

@@ -85,6 +85,32 @@ def test_plugin_constrained_system_takes_the_split_sequence(cuda):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("constrained", [False, True])
+def test_plugin_stack_mixed_precision(cuda, constrained):
+    """Context created with Precision=mixed (what example/nacl_tg.py:60 asks for): double4 velm, posqCorrection, int64
+    forces recomputed from the positions each step (Drude springs).  100 steps agree with the oracle to 1e-9 — the
+    spring forces see positions through posq + posqCorrection (~48 bits)."""
+    from plugin_driver import PluginSim
+    kw = dict(quantize_masses=True, pair_force="none", cold_drudes=True, drude_sigma=1.4e-4, force_sigma=2.0)
+    s = synth.swm4_box(600, **kw) if constrained else synth.water_box(1500, 3, **kw)
+    sim = PluginSim(s, force_model=1, precision="mixed", with_constraints=constrained, has_cm_motion_remover=constrained)
+    o = O.Oracle(s, O.TG, constraints=s.constraints if constrained else None, has_cm_motion_remover=constrained)
+    pa, va = s.positions.copy(), s.velocities.copy()
+    pb, vb = pa.copy(), va.copy()
+    ext = np.rint(s.forces * 4294967296.0) / 4294967296.0
+    fa = O.harmonic_forces(s, pa, ext)
+    fb = fa.copy()
+    sim.step(pa, va, fa, 100, ext)
+    o.step(pb, vb, fb, 100, 1, ext, s.k_spring)
+    assert rel_err(va, vb) < 1e-6          # int64 force quantisation (2^-32) + float-float positions feeding back for 100 steps
+    assert rel_err(pa, pb) < 1e-7
+    assert abs(sim.kinetic_energy() - o.ke_sum) / o.ke_sum < 1e-8
+    if constrained:
+        assert sim.constraint_calls() == 200
+    sim.close()
+
+
+@pytest.mark.gpu
 def test_plugin_single_pair_hard_wall(cuda):
     """The reference tests' 2-particle system (testSinglePair): the hard wall bound holds at every sample."""
     from plugin_driver import PluginSim
