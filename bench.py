@@ -268,6 +268,7 @@ def run_ours(args):
         a_ms, a_cnt = prof["half1"]
         b_ms, b_cnt = prof["half2"]
         ach = ALG_BYTES_HALF1 * n / (a_ms / max(a_cnt, 1) * 1e-3) / 1e9 if a_cnt else None
+        traffic, traffic_src = ncu_traffic(args.workload, n)
         out = {
             "metric": "TGNH step particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -285,7 +286,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "tgnh_stream_kernel<KIND_A> (scale+kick+drift+hard wall)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_particle": ALG_BYTES_HALF1,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_particle": ALG_BYTES_HALF1,
                          "avg_launch_ms": a_ms / max(a_cnt, 1),
                          "half2_avg_launch_ms": b_ms / max(b_cnt, 1),
                          "half2_achieved": (ALG_BYTES_HALF2 * n / (b_ms / max(b_cnt, 1) * 1e-3) / 1e9) if b_cnt else None},
@@ -306,6 +307,22 @@ def run_ours(args):
     if comm is not None:
         comm.close()
         dist.destroy_process_group()
+
+
+def ncu_traffic(workload, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE first-half launch, from the committed `ncu --set full` capture
+    of this workload (profiles/ncu_full_rNN.json, written by scripts/summarise_profiles.py).  Never measured in this
+    process: a run under a profiler is not a bench run.  None when no capture matches the workload's size."""
+    import glob
+    root = os.path.dirname(os.path.abspath(__file__))
+    for path in sorted(glob.glob(os.path.join(root, "profiles", "ncu_full_r*.json")), reverse=True):
+        try:
+            cap = json.load(open(path))
+            if workload == "c4" and cap.get("half1") and cap.get("particles", 10_000_000) == n:
+                return cap["half1"]["dram_bytes"], os.path.relpath(path, root) + " (half1, bytes per launch)"
+        except (OSError, ValueError, KeyError):
+            continue
+    return None, None
 
 
 def main():
