@@ -276,6 +276,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "particles_per_gpu": n, "total_particles": total_particles,
                        "parallelism": f"particle-range shards x{world}" if world > 1 else "single GPU",
+                       "exchange": {0: "none", 1: "ncclAllReduce of double[T] per step", 2: "peer-mapped inboxes over NVLink (no collective launch)"}[h.exchange_kind],
                        "l2": "inputs larger than L2 (>=440 MB working set per GPU vs 126 MB L2)",
                        "accumulation": "fp32 state (OpenMM single-precision layouts), fp64 KE reductions and NH chain",
                        "step_achieved_gbs": ALG_BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9,

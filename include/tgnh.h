@@ -168,11 +168,20 @@ int64_t tgnh_launch_count(const tgnh_handle* h);
 int tgnh_set_profiling(tgnh_handle* h, int enabled);
 int tgnh_get_profile(tgnh_handle* h, double* ms /*[3]*/, int64_t* counts /*[3]*/);
 
-/* ---- sharding over the GPUs of one node (NCCL over NVLink) --------------------------------- */
+/* ---- sharding over the GPUs of one node ----------------------------------------------------------
+ * Each rank owns a contiguous, molecule-aligned particle range; the thermostats see the whole system.  The only data
+ * exchanged per step is the double[T] vector of kinetic-energy partial sums.  When the ranks' GPUs can map each other's
+ * memory (CUDA IPC over NVLink / NVSwitch, one node) it travels through peer-mapped inboxes written by the reducing
+ * kernel's last CTA and read by the chain kernel — no collective launch; otherwise through ncclAllReduce.  The NCCL
+ * communicator also carries the one-time set-up collectives of tgnh_create.  All calls on a sharded handle that launch
+ * a kinetic-energy reduction are collective: every rank must make the same sequence of calls. */
 #define TGNH_UNIQUE_ID_BYTES 128
 int tgnh_comm_get_unique_id(void* id_out /*[128]*/);
 int tgnh_comm_create(const void* unique_id, int world_size, int rank, int device, tgnh_comm** out);
 void tgnh_comm_destroy(tgnh_comm* c);
+enum { TGNH_EXCHANGE_NONE = 0, TGNH_EXCHANGE_NCCL = 1, TGNH_EXCHANGE_PEER = 2 };
+/* how this handle exchanges the kinetic-energy partial sums (TGNH_EXCHANGE_*); environment TGNH_P2P=0 forces NCCL */
+int tgnh_exchange_kind(const tgnh_handle* h);
 
 #ifdef __cplusplus
 }

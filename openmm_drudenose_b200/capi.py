@@ -23,7 +23,7 @@ SYMBOLS = [
     "tgnh_thermostat", "tgnh_half2", "tgnh_flush",
     "tgnh_step", "tgnh_step_host", "tgnh_set_posq_correction", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
     "tgnh_kinetic_energy", "tgnh_compute_kinetic_energies", "tgnh_get_chain_state", "tgnh_set_chain_state",
-    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
+    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
     "tgnh_comm_create", "tgnh_comm_destroy",
 ]
 
@@ -84,6 +84,7 @@ def lib():
         L.tgnh_get_thermostat_params.argtypes = [vp, dp, dp, dp]
         L.tgnh_launch_count.argtypes = [vp]
         L.tgnh_launch_count.restype = C.c_int64
+        L.tgnh_exchange_kind.argtypes = [vp]
         L.tgnh_set_profiling.argtypes = [vp, C.c_int]
         L.tgnh_get_profile.argtypes = [vp, dp, C.POINTER(C.c_int64)]
         L.tgnh_comm_get_unique_id.argtypes = [vp]
@@ -250,3 +251,8 @@ class Handle:
     @property
     def launch_count(self):
         return lib().tgnh_launch_count(self.h)
+
+    @property
+    def exchange_kind(self):
+        """0 = not sharded, 1 = NCCL all-reduce, 2 = peer-mapped inboxes over NVLink"""
+        return lib().tgnh_exchange_kind(self.h)

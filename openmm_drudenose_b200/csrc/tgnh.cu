@@ -57,6 +57,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -70,8 +71,9 @@ static int nccl_load() {
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(lib, "ncclAllGather");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.GetErrorString)
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.GetErrorString)
         return fail(TGNH_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
     g_nccl.lib = lib;
     return TGNH_OK;
@@ -151,6 +153,10 @@ struct tgnh_handle {
     bool scalePending = false;    // chain.pending != 1 has not been applied to velm yet
     int64_t launches = 0;
     tgnh_comm* comm = nullptr;
+    // sharded: kinetic-energy exchange through peer-mapped inboxes (NVLink); world <= 1 when NCCL carries it instead
+    PeerInbox* dInbox = nullptr;
+    PeerView peers{};
+    unsigned int reduceSeq = 0;
     // optional per-launch device timing (bench.py's roofline leg)
     bool profiling = false;
     std::vector<cudaEvent_t> evPool;
@@ -162,6 +168,66 @@ struct tgnh_handle {
 };
 
 typedef void (*StreamKernel)(const StreamArgs);
+
+// Map every rank's inbox into this process (CUDA IPC over NVLink / NVSwitch).  Collective over the communicator; all
+// ranks end up with the same answer: either everybody uses the inboxes or (IPC unavailable, different nodes, more than
+// MAX_PEERS ranks, TGNH_P2P=0) everybody keeps the NCCL all-reduce.
+static int setup_peers(tgnh_handle* h) {
+    const int W = h->comm->worldSize, R = h->comm->rank;
+    h->peers = PeerView{};
+    const char* env = getenv("TGNH_P2P");
+    bool ok = W <= MAX_PEERS && !(env && atoi(env) == 0);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok) ok = cudaMalloc((void**)&h->dInbox, sizeof(PeerInbox)) == cudaSuccess && cudaMemset(h->dInbox, 0, sizeof(PeerInbox)) == cudaSuccess;
+    if (ok) ok = cudaIpcGetMemHandle(&mine, h->dInbox) == cudaSuccess;
+    (void)cudaGetLastError();
+    // all-gather the handles (and whether each rank got this far)
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    std::vector<unsigned char> all((size_t)W * rec, 0);
+    memcpy(&all[R * rec], &mine, sizeof mine);
+    all[R * rec + sizeof mine] = ok ? 1 : 0;
+    unsigned char* dall = nullptr;
+    if (cudaMalloc((void**)&dall, all.size()) != cudaSuccess) return fail(TGNH_ERR_CUDA, "cudaMalloc failed");
+    cudaMemcpy(dall, all.data(), all.size(), cudaMemcpyHostToDevice);
+    ncclResult_t r = g_nccl.AllGather(dall + R * rec, dall, rec, ncclChar, h->comm->comm, 0);
+    cudaError_t e = cudaStreamSynchronize(0);
+    cudaMemcpy(all.data(), dall, all.size(), cudaMemcpyDeviceToHost);
+    if (r != ncclSuccess || e != cudaSuccess) { cudaFree(dall); return fail(TGNH_ERR_NCCL, "all-gather of the inbox handles failed"); }
+    for (int q = 0; q < W; q++) ok = ok && all[q * rec + sizeof mine] == 1;
+    if (ok) {
+        for (int q = 0; q < W && ok; q++) {
+            if (q == R) { h->peers.inbox[q] = h->dInbox; continue; }
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, &all[q * rec], sizeof hd);
+            void* ptr = nullptr;
+            ok = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            h->peers.inbox[q] = ok ? (PeerInbox*)ptr : nullptr;
+        }
+        (void)cudaGetLastError();
+    }
+    // agreement: one rank failing to map a peer sends everybody back to NCCL
+    double flag = ok ? 1.0 : 0.0;
+    cudaMemcpy(dall, &flag, 8, cudaMemcpyHostToDevice);
+    r = g_nccl.AllReduce(dall, dall, 1, ncclDouble, ncclMin, h->comm->comm, 0);
+    e = cudaStreamSynchronize(0);
+    cudaMemcpy(&flag, dall, 8, cudaMemcpyDeviceToHost);
+    cudaFree(dall);
+    if (r != ncclSuccess || e != cudaSuccess) return fail(TGNH_ERR_NCCL, "all-reduce of the inbox status failed");
+    if (flag < 1.0) {
+        for (int q = 0; q < MAX_PEERS; q++) {
+            if (h->peers.inbox[q] && h->peers.inbox[q] != h->dInbox) cudaIpcCloseMemHandle(h->peers.inbox[q]);
+            h->peers.inbox[q] = nullptr;
+        }
+        cudaFree(h->dInbox);
+        h->dInbox = nullptr;
+        h->peers = PeerView{};
+        return TGNH_OK;
+    }
+    h->peers.world = W;
+    h->peers.rank = R;
+    return TGNH_OK;
+}
 
 template <int KIND, int FFMT, int PREC>
 static StreamKernel pick2(bool useCOM, bool hardwall) {
@@ -359,6 +425,8 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         for (int g = 0; g <= G; g++) redMass[g] = pack[T + g];
         drudeDof = pack[T + G + 1]; comDof = pack[T + G + 2];
     }
+    if (h->comm && h->comm->worldSize > 1)
+        if (int rc = setup_peers(h)) return bail(rc);
     if (p->use_com_temp_group) {
         dofv[G] = comDof;                                             // :197-199
         if (p->has_cm_motion_remover) dofv[G] -= 3;                   // :204-212
@@ -485,6 +553,9 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
 
 extern "C" void tgnh_destroy(tgnh_handle* h) {
     if (!h) return;
+    for (int r = 0; r < MAX_PEERS; r++)
+        if (h->peers.inbox[r] && h->peers.inbox[r] != h->dInbox) cudaIpcCloseMemHandle(h->peers.inbox[r]);
+    cudaFree(h->dInbox);
     cudaFree(h->dDesc); cudaFree(h->dTileStart); cudaFree(h->dResStart); cudaFree(h->dTileFirstRes); cudaFree(h->dChain); cudaFree(h->dPartials); cudaFree(h->dTicket);
     cudaFree(h->hsVelm); cudaFree(h->hsPosq); cudaFree(h->hsForce);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
@@ -519,8 +590,12 @@ static cudaError_t launch_pdl(void (*kernel)(Args...), int grid, int block, int 
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-static int launch_chain(tgnh_handle* h, cudaStream_t s, int mode) {
-    CUDA_TRY(launch_pdl(tgnh_chain_kernel, 1, 32, 0, s, h->chain, mode));
+// `gather`: the launch follows a reducing launch of a sharded run and first forms the global sums from all ranks' partials
+static int launch_chain(tgnh_handle* h, cudaStream_t s, int mode, bool gather = false) {
+    PeerView pv = h->peers;
+    pv.seq = h->reduceSeq;
+    if (!gather) pv.world = 0;
+    CUDA_TRY(launch_pdl(tgnh_chain_kernel, 1, 32, 0, s, h->chain, (const PeerView)pv, mode));
     h->launches++;
     return TGNH_OK;
 }
@@ -551,6 +626,9 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     if (tuneReverse == 0) a.reverse = 0;
     if (tuneReverse == 2) a.reverse = (prof == KIND_B) ? 0 : 1;
     a.partials = h->dPartials; a.ticket = h->dTicket; a.chain = h->chain;
+    a.peers = h->peers;
+    const bool p2p = h->peers.world > 1 && prof != KIND_A;
+    if (p2p) a.peers.seq = ++h->reduceSeq; else a.peers.world = 0;
     const int grid = kind == KIND_A1 ? h->gridA1 : kind == KIND_A2 ? h->gridA2 : prof == KIND_A ? h->gridA : prof == KIND_B ? h->gridB : h->gridKE;
     const int smem = kind == KIND_A1 ? h->smemA1 : kind == KIND_A2 ? h->smemA2 : prof == KIND_A ? h->smemA : prof == KIND_B ? h->smemB : h->smemKE;
     StreamKernel k = pick(kind, h->ffmt, h->prec, h->useCOM, h->hardwall);
@@ -572,8 +650,10 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     if (e1) CUDA_TRY(cudaEventRecord(e1, s));
     h->launches++;
     if (prof == KIND_A) return TGNH_OK;
-    if (sharded(h))   // the only collective on the path: double[G+2] kinetic-energy vector over NVLink
-        NCCL_TRY(g_nccl.AllReduce(h->chain.ke2Local, h->chain.ke2, h->T, ncclDouble, ncclSum, h->comm->comm, s));
+    // the only exchange on the path: double[G+2] kinetic-energy partials.  Peer inboxes: published by the launch above,
+    // gathered by the chain launch below (which therefore runs even without a chain update); otherwise an NCCL all-reduce
+    if (p2p) return launch_chain(h, s, chainMode, true);
+    if (sharded(h)) NCCL_TRY(g_nccl.AllReduce(h->chain.ke2Local, h->chain.ke2, h->T, ncclDouble, ncclSum, h->comm->comm, s));
     if (chainMode != CHAIN_NONE) return launch_chain(h, s, chainMode);
     return TGNH_OK;
 }
@@ -735,12 +815,19 @@ extern "C" int tgnh_step_host(tgnh_handle* h, void* velm_host, void* posq_host, 
 extern "C" int tgnh_num_thermostats(const tgnh_handle* h) { return h ? h->T : 0; }
 extern "C" int tgnh_num_nh_chains(const tgnh_handle* h) { return h ? h->M : 0; }
 extern "C" int64_t tgnh_launch_count(const tgnh_handle* h) { return h ? h->launches : 0; }
+extern "C" int tgnh_exchange_kind(const tgnh_handle* h) {
+    if (!h || !h->comm || h->comm->worldSize <= 1) return TGNH_EXCHANGE_NONE;
+    return h->peers.world > 1 ? TGNH_EXCHANGE_PEER : TGNH_EXCHANGE_NCCL;
+}
 
 static int d2h(tgnh_handle* h, void* stream, double* dst, const double* src, size_t n) {
     if (!h || !dst) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    unsigned int peerError = 0;
+    if (h->dInbox) CUDA_TRY(cudaMemcpyAsync(&peerError, &h->dInbox->error, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (peerError) return fail(TGNH_ERR_NCCL, "a peer rank did not deliver its kinetic energies within 10 s");
     return TGNH_OK;
 }
 

@@ -128,6 +128,72 @@ struct ChainView {
     double* keSum;      // [1]
 };
 
+// ---- sharded runs: the kinetic-energy exchange over NVLink peer memory -------------------------------------------
+// Every rank owns an inbox in its HBM that all peers map (CUDA IPC).  The last CTA of a reducing launch stores the
+// rank's partial sums into slot [seq & 1][rank] of EVERY inbox, fences, then publishes `seq` in the matching flag; the
+// chain launch that follows waits for all flags of its own inbox and adds the partials in rank order, so every rank
+// forms bit-identical sums and no collective launch sits between the two kernels.  Two slots suffice: a peer can only
+// be one reduction ahead, because its next one needs this rank's contribution to the current one.
+constexpr int MAX_PEERS = 16;
+struct PeerInbox {
+    double slot[2][MAX_PEERS][MAX_T];
+    unsigned int flag[2][MAX_PEERS];
+    unsigned int error;           // set when a wait timed out (a peer died): reported by the next host-side query
+};
+struct PeerView {
+    int world, rank;              // world <= 1: not sharded (or the NCCL path is in use)
+    unsigned int seq;             // number of this reduction, 1, 2, ...
+    PeerInbox* inbox[MAX_PEERS];  // inbox[r]: rank r's inbox as mapped into this process (inbox[rank] is local)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// one thread per peer: publish this rank's partial sums `part[0..T)` (global memory, already visible to this thread)
+__device__ __forceinline__ void peer_publish(const PeerView& pv, const double* part, int T, int r) {
+    PeerInbox* in = pv.inbox[r];
+    const int b = pv.seq & 1;
+    for (int g = 0; g < T; g++) in->slot[b][pv.rank][g] = part[g];
+    __threadfence_system();
+    st_release_sys(&in->flag[b][pv.rank], pv.seq);
+}
+
+// one warp: wait for every rank's partial sums of reduction `seq`, add them in rank order into out[0..T)
+__device__ __forceinline__ void peer_gather(const PeerView& pv, double* out, int T, int lane) {
+    PeerInbox* in = pv.inbox[pv.rank];
+    const int b = pv.seq & 1;
+    if (lane < pv.world) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(&in->flag[b][lane]) != pv.seq) {
+            if (global_timer_ns() - t0 > 10000000000ull) { in->error = 1u; break; }     // 10 s: a peer is gone
+            __nanosleep(100);
+        }
+    }
+    __syncwarp();
+    if (lane < T) {
+        double x = 0.0;
+        for (int r = 0; r < pv.world; r++) x += ld_relaxed_sys(&in->slot[b][r][lane]);
+        out[lane] = x;
+    }
+    __syncwarp();
+}
+
 enum ChainMode {
     CHAIN_NONE = 0,        // no chain update
     CHAIN_FIRST = 1,       // first half-step of a step: consumes pending^2 * ke2, scaleA = pending * s

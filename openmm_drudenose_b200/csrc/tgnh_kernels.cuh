@@ -76,6 +76,7 @@ struct StreamArgs {
     double* partials;         // [gridDim.x][T]
     unsigned int* ticket;     // last-CTA-done counter (self-resetting)
     ChainView chain;
+    PeerView peers;           // sharded runs with peer-mapped inboxes: where the last CTA publishes this rank's sums
 };
 
 template <int KIND, int FFMT, int PREC>
@@ -613,15 +614,21 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
         if (lane == 0) out[g] = x;
     }
+    if (a.peers.world > 1) {
+        // sharded: hand this rank's sums to every rank (this one included) over NVLink
+        __syncthreads();
+        if (tid < a.peers.world) peer_publish(a.peers, out, T, tid);
+    }
     if (tid == 0) *a.ticket = 0u;
     if (KIND == KIND_KE && a.applyScale && tid < T) a.chain.pending[tid] = 1.0;   // the deferred scaling is now applied
 }
 
 // The Nose-Hoover chain update(s) between two streaming launches: one warp, lane g = thermostat g.
-__global__ void __launch_bounds__(32, 1) tgnh_chain_kernel(ChainView c, int mode) {
+__global__ void __launch_bounds__(32, 1) tgnh_chain_kernel(ChainView c, const __grid_constant__ PeerView peers, int mode) {
     pdl_launch_dependents();      // the next streaming launch may start its prologue; it waits for our results
     pdl_wait();
-    chain_phase(c, mode, threadIdx.x);
+    if (peers.world > 1) peer_gather(peers, c.ke2, c.T, threadIdx.x);    // sharded: global sums from all ranks' partials
+    if (mode != CHAIN_NONE) chain_phase(c, mode, threadIdx.x);
 }
 
 }  // namespace tgnh

@@ -1,5 +1,5 @@
-"""torchrun worker for tests/test_sharded.py: the particle-range sharded TGNH step (NCCL all-reduce of the double[G+2]
-kinetic-energy vector) against the same system on one GPU."""
+"""torchrun worker for tests/test_sharded.py: the particle-range sharded TGNH step (exchange of the double[G+2]
+kinetic-energy partial sums through peer-mapped inboxes, or NCCL with TGNH_P2P=0) against the same system on one GPU."""
 import os
 import sys
 
@@ -27,7 +27,17 @@ per = MOL // world
 shard = synth.water_box(per, G, first_molecule=rank * per, box_molecules=MOL, quantize_masses=True)
 st = DeviceState(shard, dev)
 h = capi.Handle(shard, device=local, comm=comm)
-h.step(*st.ptrs, nsteps=STEPS)
+kind = h.exchange_kind
+assert kind == (1 if os.environ.get("TGNH_P2P") == "0" else int(os.environ.get("EXPECT_EXCHANGE", kind))), kind
+h.step(*st.ptrs, nsteps=STEPS - 5)
+# the OpenMM-facing call sequence, a kinetic-energy query and a deferred-scale flush in between (all collective)
+for i in range(5):
+    h.half1(*st.ptrs)
+    h.half2(st.velm.data_ptr(), st.force.data_ptr(), capi.HALF2_DEFER_SCALE if i == 2 else capi.HALF2_DEFAULT)
+    if i == 2:
+        h.flush(st.velm.data_ptr())
+    if i == 3:
+        ke_now = h.compute_kinetic_energies(st.velm.data_ptr())
 torch.cuda.synchronize()
 ke, vs, ed = h.kinetic_energies(), h.vscale(), h.chain_state()[1]
 dof = h.thermostat_params()[0]
@@ -42,14 +52,21 @@ if rank == 0:
     whole = synth.water_box(MOL, G, quantize_masses=True)
     st1 = DeviceState(whole, dev)
     h1 = capi.Handle(whole, device=local)
-    h1.step(*st1.ptrs, nsteps=STEPS)
+    h1.step(*st1.ptrs, nsteps=STEPS - 5)
+    for i in range(5):
+        h1.half1(*st1.ptrs)
+        h1.half2(st1.velm.data_ptr(), st1.force.data_ptr(), capi.HALF2_DEFER_SCALE if i == 2 else capi.HALF2_DEFAULT)
+        if i == 2:
+            h1.flush(st1.velm.data_ptr())
+        if i == 3:
+            np.testing.assert_allclose(ke_now, h1.compute_kinetic_energies(st1.velm.data_ptr()), rtol=1e-12)
     np.testing.assert_allclose(dof, h1.thermostat_params()[0], rtol=1e-12)         # DOF tables summed over ranks at create (order of the COM-share sum differs)
     np.testing.assert_allclose(ke, h1.kinetic_energies(), rtol=1e-12)              # only the summation order differs
     np.testing.assert_allclose(vs, h1.vscale(), rtol=1e-12)
     np.testing.assert_allclose(ed, h1.chain_state()[1], rtol=1e-9, atol=1e-12)
     n = shard.num_particles
     np.testing.assert_allclose(vel, st1.vel()[:n], rtol=0, atol=1e-6)
-    print("SHARD_OK", world)
+    print("SHARD_OK", world, "exchange", kind)
 h.close()
 comm.close()
 dist.destroy_process_group()
