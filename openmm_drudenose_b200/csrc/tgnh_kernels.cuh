@@ -490,7 +490,22 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
             vn = scaled_velocity(v, eT, r, eCOM, V, coef * fj, rel);
         }
 
-        if (L::HAS_KE) {
+        if (KIND == KIND_BU) {
+            // computeNormalizedKineticEnergies (drudeTGNH.cu:152-188) for residue-uniform groups, without the pair transform:
+            // M_p |v_cm|^2 + mu |rel|^2 = m_i |v_i|^2 + m_j |v_j|^2 for a Drude pair, so EVERY particle adds its own
+            // m |v|^2 to its group and only the Drude particle moves the pair's internal term mu |rel|^2 from the group
+            // to the Drude thermostat; 1/mu = 1/m_i + 1/m_j = w_i + w_j needs no masses at all
+            const double md = massive ? mass_d(w, m) : 0.0;
+            double ke = md * (double)dot3(r);
+            if (role == ROLE_DRUDE) {
+                const double wsum = (double)w + (double)wj;
+                const double mu = (massive && wj != real(0)) ? rcp_d(wsum, rcp_fast((float)wsum)) : 0.0;
+                const double keD = mu * (double)dot3(rel);
+                ke -= keD;
+                accDrude += keD;
+            }
+            if (active && massive) ske[tg * TILE + tid] += ke;
+        } else if (L::HAS_KE) {
             // computeNormalizedKineticEnergies (drudeTGNH.cu:152-188), branch-free: an ordinary particle is its own
             // "pair centre of mass" (rel = 0); the Drude particle of a pair carries the pair's two terms
             const R3 cm = axpy(fj, rel, r);           // pair COM relative to the residue
