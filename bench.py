@@ -138,6 +138,23 @@ def cpu_run(system, steps, warmup, threads):
     return dt, "port", threads
 
 
+def cpu_port_all_cores(system, steps):
+    """the OpenMP-over-molecules variant of the oracle port (temperature groups + COM group, fp64) on all
+    host cores, beside the serial reference platform.  Returns a dict for the JSON line."""
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    O.lib().tgnh_oracle_set_threads(threads)
+    o = O.Oracle(system, O.TG, constraints=system.constraints)
+    p, v, f = system.positions.copy(), system.velocities.copy(), system.forces.copy()
+    o.step(p, v, f, 2)
+    t0 = time.perf_counter()
+    o.step(p, v, f, steps)
+    dt = time.perf_counter() - t0
+    O.lib().tgnh_oracle_set_threads(1)
+    return {"value": system.num_particles * steps / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{system.num_particles} particles x {steps} steps ({dt:.2f} s), oracle-tg port, OpenMP over molecules"}
+
+
 def cpu_sample_system(workload):
     """Bounded sample of the workload for the CPU legs: 1M particles of the same generator (C4/C5), else the config itself."""
     if workload in ("c4", "c4-wall", "c5"):
@@ -164,6 +181,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "cpu_port_all_cores": cpu_port_all_cores(system, max(args.steps, 10)),
     }
     print(json.dumps(out))
 
@@ -302,7 +320,8 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": sysb.num_particles * bsteps / dt, "unit": "particle-steps/s", "cores": cores, "kind": kind,
                                    "sample": f"{sysb.num_particles} particles of the same generator x {bsteps} steps ({dt:.1f} s), "
                                              + ("the reference platform's own sources (oracle/_ref), serial fp64" if kind == "reference"
-                                                else "oracle-tg port, serial fp64")}
+                                                else "oracle-tg port, serial fp64"),
+                                   "port_all_cores": cpu_port_all_cores(sysb, 20)}
         print(json.dumps(out))
     h.close()
     if comm is not None:
