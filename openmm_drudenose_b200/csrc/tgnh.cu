@@ -138,6 +138,9 @@ struct tgnh_handle {
     int* dTileStart = nullptr;
     int* dResStart = nullptr;     // first particle of every residue in particle order, then N (padded to a multiple of 4)
     int* dTileFirstRes = nullptr; // index into dResStart of each tile's first residue
+    int numBig = 0;               // residues of more than MAX_RES particles
+    int *dBigFirst = nullptr, *dBigLast = nullptr;
+    double4* dBigCom = nullptr;   // {V, M} of the big residues (tgnh_bigcom_kernel)
     int kindB = KIND_B;           // KIND_BU when every residue lies in one temperature group
     double* dChain = nullptr;     // one allocation holding every ChainView array
     double* dPartials = nullptr;
@@ -351,9 +354,6 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
     bool uniform = true;
     for (int r = 0; r < R; r++) {
         if (resFirst[r] < 0) return fail(TGNH_ERR_INVALID_ARGUMENT, "residue %d has no particles", r);
-        if (resLast[r] - resFirst[r] + 1 > MAX_RES)
-            return fail(TGNH_ERR_UNSUPPORTED, "residue %d has %d particles; the in-tile COM path handles at most %d", r,
-                        resLast[r] - resFirst[r] + 1, MAX_RES);
         for (int i = resFirst[r] + 1; i <= resLast[r]; i++)
             if (p->particle_temp_group[i] != p->particle_temp_group[resFirst[r]]) uniform = false;
     }
@@ -462,8 +462,16 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
     for (int i = 0; i < N; i++) {
         const int r = p->particle_res_id[i];
         if (partner[i] < -128 || partner[i] > 127) return bail(fail(TGNH_ERR_UNSUPPORTED, "Drude pair partner of particle %d is %d particles away (limit 127)", i, partner[i]));
-        desc[i] = desc_pack(p->particle_temp_group[i], role[i], i - resFirst[r], resLast[r] - i, partner[i]);
+        const bool big = resLast[r] - resFirst[r] + 1 > MAX_RES;      // COM velocity from the pre-pass table, not from the tile
+        desc[i] = big ? desc_pack(p->particle_temp_group[i], role[i], 0, 0, partner[i], true)
+                      : desc_pack(p->particle_temp_group[i], role[i], i - resFirst[r], resLast[r] - i, partner[i]);
     }
+    // split points inside big residues must not separate a Drude pair: unsafe[s] != 0 <=> some pair (a < b) has a < s <= b
+    std::vector<int> unsafe(N + 2, 0);
+    for (int i = 0; i < N; i++)
+        if (partner[i] > 0) { unsafe[i + 1]++; unsafe[i + partner[i] + 1]--; }
+    for (int i = 1; i <= N; i++) unsafe[i] += unsafe[i - 1];
+    std::vector<int> bigFirst, bigLast;
     std::vector<int> tileStart;
     tileStart.push_back(0);
     {
@@ -473,6 +481,25 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         while (i < N) {
             r = p->particle_res_id[i];
             const int len = resLast[r] - resFirst[r] + 1;
+            if (len > MAX_RES) {
+                // big residue: its own tiles, cut where no Drude pair is separated (nothing else ties its particles to a tile)
+                bigFirst.push_back(i); bigLast.push_back(resLast[r]);
+                if (cur > 0) { tileStart.push_back(i); cur = 0; }
+                const int end = resLast[r] + 1;
+                int segStart = i;
+                while (end - segStart > TILE) {
+                    int cut = segStart + TILE;
+                    while (cut > segStart && unsafe[cut]) cut--;
+                    if (cut == segStart)
+                        return bail(fail(TGNH_ERR_UNSUPPORTED, "residue %d: no place to cut %d..%d without separating a Drude pair", r, segStart, segStart + TILE));
+                    tileStart.push_back(cut);
+                    segStart = cut;
+                }
+                if (end < N) tileStart.push_back(end);
+                cur = 0;
+                i = end;
+                continue;
+            }
             if (cur + len > TILE) { tileStart.push_back(i); cur = 0; }
             cur += len;
             i += len;
@@ -487,7 +514,9 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         for (int i = 0; i < N;) {
             if (t < tileStart.size() && tileStart[t] == i) { tileFirstRes.push_back((int)resStart.size()); t++; }
             resStart.push_back(i);
-            i = resLast[p->particle_res_id[i]] + 1;
+            int next = resLast[p->particle_res_id[i]] + 1;
+            if (t < tileStart.size() && tileStart[t] < next) next = tileStart[t];     // a big residue continues in the next tile
+            i = next;
         }
         tileFirstRes.push_back((int)resStart.size());
         resStart.push_back(N);
@@ -505,6 +534,15 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
     cudaMemcpy(h->dTileStart, tileStart.data(), tileStart.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(h->dResStart, resStart.data(), resStart.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(h->dTileFirstRes, tileFirstRes.data(), tileFirstRes.size() * 4, cudaMemcpyHostToDevice);
+    h->numBig = (int)bigFirst.size();
+    if (h->numBig) {
+        if (!dmalloc((void**)&h->dBigFirst, bigFirst.size() * 4) || !dmalloc((void**)&h->dBigLast, bigLast.size() * 4) ||
+            !dmalloc((void**)&h->dBigCom, bigFirst.size() * sizeof(double4)))
+            return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the big-residue tables failed"));
+        cudaMemcpy(h->dBigFirst, bigFirst.data(), bigFirst.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(h->dBigLast, bigLast.data(), bigLast.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemset(h->dBigCom, 0, bigFirst.size() * sizeof(double4));
+    }
     cudaMemset(h->dTicket, 0, 4);
 
     // chain block: etaMass, invEtaMass, eta, etaDot, etaDotDot, nkbt, ke2, ke2Local, ke2Used, pending, scaleA, vscale, keSum
@@ -556,7 +594,7 @@ extern "C" void tgnh_destroy(tgnh_handle* h) {
     for (int r = 0; r < MAX_PEERS; r++)
         if (h->peers.inbox[r] && h->peers.inbox[r] != h->dInbox) cudaIpcCloseMemHandle(h->peers.inbox[r]);
     cudaFree(h->dInbox);
-    cudaFree(h->dDesc); cudaFree(h->dTileStart); cudaFree(h->dResStart); cudaFree(h->dTileFirstRes); cudaFree(h->dChain); cudaFree(h->dPartials); cudaFree(h->dTicket);
+    cudaFree(h->dDesc); cudaFree(h->dTileStart); cudaFree(h->dResStart); cudaFree(h->dTileFirstRes); cudaFree(h->dBigFirst); cudaFree(h->dBigLast); cudaFree(h->dBigCom); cudaFree(h->dChain); cudaFree(h->dPartials); cudaFree(h->dTicket);
     cudaFree(h->hsVelm); cudaFree(h->hsPosq); cudaFree(h->hsForce);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     if (h->hsStream) cudaStreamDestroy(h->hsStream);
@@ -610,6 +648,7 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
         return fail(TGNH_ERR_INVALID_ARGUMENT, "mixed precision: register the posqCorrection array with tgnh_set_posq_correction first");
     a.desc = h->dDesc; a.tileStart = h->dTileStart; a.numTiles = h->numTiles; a.paddedN = h->paddedN;
     a.resStart = h->dResStart; a.tileFirstRes = h->dTileFirstRes;
+    a.bigFirst = h->dBigFirst; a.bigCom = h->dBigCom; a.numBig = h->numBig;
     const bool firstHalf = kind == KIND_A || kind == KIND_A1 || kind == KIND_A2;
     const int prof = firstHalf ? KIND_A : kind;      // profiling slot (first half / second half / reduce)
     if (kind == KIND_B) kind = h->kindB;
@@ -645,6 +684,16 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
         h->evKind[h->evUsed / 2] = prof;
         h->evUsed += 2;
         CUDA_TRY(cudaEventRecord(e0, s));
+    }
+    if (h->numBig && h->useCOM && kind != KIND_A2) {
+        // residues that do not fit a tile: their COM velocity (as this launch will see / store the velocities) first
+        BigComArgs b;
+        b.velm = velm; b.force = force; b.bigFirst = h->dBigFirst; b.bigLast = h->dBigLast; b.bigCom = h->dBigCom; b.paddedN = h->paddedN;
+        b.fscale = (prof == KIND_B) ? a.fscale : 0.0;
+        void (*bk)(const BigComArgs) = h->prec ? (h->ffmt ? tgnh_bigcom_kernel<1, 1> : tgnh_bigcom_kernel<0, 1>)
+                                               : (h->ffmt ? tgnh_bigcom_kernel<1, 0> : tgnh_bigcom_kernel<0, 0>);
+        CUDA_TRY(launch_pdl(bk, h->numBig, 256, 0, s, (const BigComArgs)b));
+        h->launches++;
     }
     CUDA_TRY(launch_pdl(k, grid, TILE, smem, s, (const StreamArgs)a));
     if (e1) CUDA_TRY(cudaEventRecord(e1, s));

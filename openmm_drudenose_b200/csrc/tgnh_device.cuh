@@ -14,17 +14,20 @@ constexpr int MAX_M = 16;          // Nose-Hoover chain length
 constexpr int MAX_RES = 128;       // particles per residue handled in-tile
 
 // ---- descriptor word: one uint32 per particle, built once in tgnh_create ----------------------
-//  [7:0]   temperature group
+//  [6:0]   temperature group (< MAX_T)
+//  [7]     the particle belongs to a "big" residue (more than MAX_RES particles, e.g. a protein): its residue's COM
+//          velocity comes from the pre-pass kernel's table instead of the tile; offsets [23:10] are 0
 //  [9:8]   role: 0 ordinary, 1 Drude particle (pairParticles.x), 2 parent (pairParticles.y)
 //  [16:10] offset back to the first particle of the residue
 //  [23:17] offset forward to the last particle of the residue
 //  [31:24] signed offset to the pair partner
 constexpr uint32_t ROLE_NORMAL = 0, ROLE_DRUDE = 1, ROLE_PARENT = 2;
-__host__ __device__ inline uint32_t desc_pack(int tg, uint32_t role, int offFirst, int offLast, int partner) {
-    return (uint32_t)(tg & 0xff) | (role << 8) | ((uint32_t)offFirst << 10) | ((uint32_t)offLast << 17) |
+__host__ __device__ inline uint32_t desc_pack(int tg, uint32_t role, int offFirst, int offLast, int partner, bool big = false) {
+    return (uint32_t)(tg & 0x7f) | (big ? 0x80u : 0u) | (role << 8) | ((uint32_t)offFirst << 10) | ((uint32_t)offLast << 17) |
            ((uint32_t)(partner & 0xff) << 24);
 }
-__device__ __forceinline__ int desc_tg(uint32_t d) { return d & 0xff; }
+__device__ __forceinline__ int desc_tg(uint32_t d) { return d & 0x7f; }
+__device__ __forceinline__ bool desc_big(uint32_t d) { return (d & 0x80u) != 0; }
 __device__ __forceinline__ uint32_t desc_role(uint32_t d) { return (d >> 8) & 3; }
 __device__ __forceinline__ int desc_off_first(uint32_t d) { return (d >> 10) & 0x7f; }
 __device__ __forceinline__ int desc_off_last(uint32_t d) { return (d >> 17) & 0x7f; }

@@ -63,6 +63,9 @@ struct StreamArgs {
     const int* tileStart;     // [numTiles + 1]
     const int* resStart;      // [R + 1] first particle of every residue in particle order, then N   (KIND_BU)
     const int* tileFirstRes;  // [numTiles + 1] index into resStart of each tile's first residue      (KIND_BU)
+    const int* bigFirst;      // [numBig] first particle of every big residue (> MAX_RES particles), ascending
+    const double4* bigCom;    // [numBig] {V_x, V_y, V_z, M} of the big residues, written by tgnh_bigcom_kernel before this launch
+    int numBig;
     int numTiles;
     int paddedN;
     double dt;                // step size
@@ -253,6 +256,68 @@ template <int PREC> __device__ __forceinline__ PosTile<PREC> make_pos(const floa
 template <> __device__ __forceinline__ PosTile<0> make_pos<0>(const float4* sx, const float4*) { PosTile<0> p; p.sx = sx; return p; }
 template <> __device__ __forceinline__ PosTile<1> make_pos<1>(const float4* sx, const float4* sc) { PosTile<1> p; p.sx = sx; p.sc = sc; return p; }
 
+// index of the big residue that holds `particle`: the last entry of the ascending table that is <= particle
+__device__ __forceinline__ int big_index(const int* bigFirst, int numBig, int particle) {
+    int lo = 0, hi = numBig - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(bigFirst + mid) <= particle) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// Pre-pass for residues that do not fit a tile (calcCOMVelocities, drudeTGNH.cu:82-113, for those residues only): one
+// CTA per big residue sums momentum and mass in double, in a fixed order, and leaves {V, M} in bigCom.  fscale != 0:
+// velocities as the second-half kernel is about to store them (v + fscale w F).
+struct BigComArgs {
+    const void* velm;
+    const void* force;
+    const int* bigFirst;
+    const int* bigLast;
+    double4* bigCom;
+    int paddedN;
+    double fscale;
+};
+template <int FFMT, int PREC>
+__global__ void __launch_bounds__(256) tgnh_bigcom_kernel(const __grid_constant__ BigComArgs a) {
+    using real = typename Prec<PREC>::real;
+    using real4 = typename Prec<PREC>::real4;
+    __shared__ double red[4][256];
+    pdl_wait();
+    const int first = a.bigFirst[blockIdx.x], last = a.bigLast[blockIdx.x];
+    const real4* velm = static_cast<const real4*>(a.velm);
+    double px = 0.0, py = 0.0, pz = 0.0, M = 0.0;
+    for (int i = first + threadIdx.x; i <= last; i += 256) {
+        const real4 q = velm[i];
+        if (q.w == real(0)) continue;
+        const double md = mass_d(q.w, rcp_fast(q.w));
+        double vx = q.x, vy = q.y, vz = q.z;
+        if (a.fscale != 0.0) {
+            const double fw = a.fscale * (double)q.w;
+            if (FFMT == 1) {
+                const long long* f = static_cast<const long long*>(a.force);
+                vx += fw * (double)f[i]; vy += fw * (double)f[a.paddedN + i]; vz += fw * (double)f[2 * (size_t)a.paddedN + i];
+            } else {
+                const float* f = static_cast<const float*>(a.force);
+                vx += fw * (double)f[i]; vy += fw * (double)f[a.paddedN + i]; vz += fw * (double)f[2 * (size_t)a.paddedN + i];
+            }
+        }
+        px += md * vx; py += md * vy; pz += md * vz; M += md;
+    }
+    red[0][threadIdx.x] = px; red[1][threadIdx.x] = py; red[2][threadIdx.x] = pz; red[3][threadIdx.x] = M;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int c = 0; c < 4; c++) red[c][threadIdx.x] += red[c][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double Mt = red[3][0], inv = Mt > 0.0 ? 1.0 / Mt : 0.0;
+        a.bigCom[blockIdx.x] = make_double4(red[0][0] * inv, red[1][0] * inv, red[2][0] * inv, Mt);
+    }
+    pdl_launch_dependents();
+}
+
 // L2 hand-over: velm is written by one streaming launch and read (then overwritten) by the next.  B200's L2
 // holds 126 MB, so when consecutive launches walk the tiles in opposite directions the tail of what the
 // previous launch wrote is still resident: those reads never reach HBM and the dirty lines are overwritten in
@@ -414,7 +479,15 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
         // after the kick
         R3 V = v3(real(0), real(0), real(0));
         double keC = 0.0;                             // M |V|^2 of this particle's residue (kinds that reduce energies)
-        if (USE_COM && active && KIND != KIND_BU && KIND != KIND_A2) {
+        bool firstOfRes = desc_off_first(d) == 0;       // the residue's first particle carries M |V|^2
+        if (USE_COM && active && KIND != KIND_A2 && desc_big(d)) {
+            // big residue (a protein, a polymer): V and M from the pre-pass table (tgnh_bigcom_kernel)
+            const int b = big_index(a.bigFirst, a.numBig, start + tid);
+            const double4 c = a.bigCom[b];
+            V = v3((real)c.x, (real)c.y, (real)c.z);
+            firstOfRes = a.bigFirst[b] == start + tid;
+            keC = c.w * (c.x * c.x + c.y * c.y + c.z * c.z);
+        } else if (USE_COM && active && KIND != KIND_BU && KIND != KIND_A2) {
             const int j0 = tid - desc_off_first(d), j1 = tid + desc_off_last(d);
             if (!L::HAS_KE && !PREC) {
                 // first half, fp32 layout: V only feeds the small corrections (sT-1)(v - V) and (sCOM-1) V, fp32 sums are ample
@@ -459,10 +532,15 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
             // one thread per residue of the tile; the duty rotates over the warps from tile to tile so that no warp is
             // always the slow one (a stage is recycled only when all 16 warps have left it)
             const int ridx = (tid - it * 128) & (TILE - 1);
+            if (USE_COM && active && desc_big(d) && firstOfRes) {   // big residue: M |V|^2 from the pre-pass table
+                accCOM += keC;
+                ske[tg * TILE + tid] -= keC;
+            }
             if (USE_COM && ridx < hdr.w) {
                 // P = sum_j m_j v_j (kicked velocities), M = sum_j m_j over the residue's massive members
                 const int* sr = reinterpret_cast<const int*>(st + St::OFF_R) + (hdr.z & 3);
-                const int j0 = sr[ridx] - start, j1 = sr[ridx + 1] - start;
+                const int j0 = sr[ridx] - start;
+                const int j1 = desc_big(sd[fo + j0]) ? j0 : sr[ridx + 1] - start;      // segments of big residues: nothing to do here
                 V3<double> P = v3(0.0, 0.0, 0.0);
                 double M = 0.0;
                 for (int j = j0; j < j1; j++) {
@@ -474,7 +552,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
                     P = axpy(mqd, to_double(vq), P);
                     M += mqd;
                 }
-                const double keRes = dot3(P) * rcp_d(M, rcp_fast((float)M));   // M |V|^2 = |P|^2 / M
+                const double keRes = j1 > j0 ? dot3(P) * rcp_d(M, rcp_fast((float)M)) : 0.0;   // M |V|^2 = |P|^2 / M
                 accCOM += keRes;
                 ske[desc_tg(sd[fo + j0]) * TILE + tid] -= keRes;
             }
@@ -516,7 +594,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
             const double s2T = doScale ? ssq[tg] : 1.0, s2D = doScale ? ssq[G + 1] : 1.0, s2C = doScale ? ssq[G] : 1.0;
             const double keT = massT * s2T * (double)dot3(cm);
             const double keD = isDrude ? md * mjd * rcp_d(Mp, (float)invTot) * s2D * (double)dot3(rel) : 0.0;   // reduced mass
-            if (!(USE_COM && KIND != KIND_BU && active && desc_off_first(d) == 0)) keC = 0.0;        // the residue's first particle carries M |V|^2
+            if (!(USE_COM && KIND != KIND_BU && active && firstOfRes)) keC = 0.0;        // the residue's first particle carries M |V|^2
             keC *= s2C;
             if (active && massT != 0.0) ske[tg * TILE + tid] += keT;
             accDrude += keD;

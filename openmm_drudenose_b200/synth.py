@@ -119,6 +119,32 @@ SOD = Template("sod", np.array([22.59, 0.4]), np.array([[1, 0]], np.int32), np.z
 CLA = Template("cla", np.array([35.05, 0.4]), np.array([[1, 0]], np.int32), np.zeros((2, 3)))
 
 
+def polymer_template(heavy_atoms=300, seed_tag=4242):
+    """A chain molecule far larger than a tile residue slot (CHARMM-Drude style: every heavy atom is followed by its
+    Drude particle and two hydrogens): 4 * heavy_atoms particles in ONE residue, as OpenMM's getMolecules() reports a
+    protein or a polymer (openmmapi/src/DrudeTGNHIntegrator.cpp:121-141)."""
+    masses, pairs = [], []
+    for k in range(heavy_atoms):
+        masses += [12.011 - 0.4 if k % 3 else 14.007 - 0.4, 0.4, 1.008, 1.008]
+        pairs.append([4 * k + 1, 4 * k])
+    rng = np.random.Generator(np.random.Philox(key=[SEED, seed_tag]))
+    off = np.cumsum(rng.uniform(-0.08, 0.08, (4 * heavy_atoms, 3)), axis=0)
+    for d, p in pairs:
+        off[d] = off[p]
+    return Template(f"polymer{heavy_atoms}", np.array(masses), np.array(pairs, np.int32), off - off[0])
+
+
+def polymer_in_water(waters=1500, polymers=(300, 700), G=2, **kw):
+    """Waters with a few big molecules in between (first, middle, last positions in particle order)."""
+    templates = [WATER4] + [polymer_template(n, 4242 + n) for n in polymers]
+    types = [1] + [0] * (waters // 2)
+    for k in range(1, len(polymers)):
+        types += [k + 1] + [0] * (waters // (2 * max(1, len(polymers) - 1)))
+    types += [len(polymers)]                       # a big molecule last as well
+    types = np.array(types, np.int32)
+    return build(templates, types, np.arange(len(types)) % G, G, **kw)
+
+
 def _ionic_templates():
     """[BMIM]+ (25 atoms, 10 heavy atoms carrying Drudes -> 35 particles) and [BF4]- (5 atoms, all
     polarizable -> 10 particles); masses are element masses minus 0.4 for Drude carriers."""

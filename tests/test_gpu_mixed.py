@@ -24,6 +24,7 @@ SYSTEMS = {
     "water_G1_nocom": lambda: synth.water_box(2000, 1, use_com_temp_group=False),
     "nacl_C1": lambda: synth.nacl_box(),
     "ionic_C3": lambda: synth.ionic_liquid(200),
+    "polymer_big_residues": lambda: synth.polymer_in_water(600, (300, 500), 2),
     "ragged_M1": lambda: synth.build([synth.WATER4, synth.SOD, synth.SWM4], np.arange(1501) % 3, np.arange(1501) % 2, 2, num_nh_chains=1,
                                      use_drude_nh_chains=False),
 }

@@ -182,6 +182,38 @@ def test_temperature_groups_not_residue_uniform(cuda):
     h.close()
 
 
+@pytest.mark.parametrize("variant", ["uniform", "split_groups", "no_com", "i64"])
+def test_big_residues(cuda, variant):
+    """Molecules of 1200 and 2800 particles (a polymer, a protein: ONE residue each for the COM thermostat,
+    openmmapi/src/DrudeTGNHIntegrator.cpp:121-141) among waters.  They span several tiles; their COM velocity comes from
+    the pre-pass kernel's table (calcCOMVelocities, drudeTGNH.cu:82-113), everything else is the usual path."""
+    s = synth.polymer_in_water(1500, (300, 700), 2, quantize_masses=True, use_com_temp_group=variant != "no_com")
+    if variant == "split_groups":                        # not residue-uniform: general second-half kernel, non-folded step
+        tg = s.temp_group.copy()
+        tg[2::4] = 1 - tg[2::4]
+        s.temp_group = tg
+    fmt = capi.FORCE_I64_SOA if variant == "i64" else capi.FORCE_F32_SOA
+    if fmt:
+        s.forces = np.rint(s.forces * 4294967296.0) / 4294967296.0
+    st = DeviceState(s, cuda, force_format=fmt)
+    h = capi.Handle(s, force_format=fmt)
+    o = O.Oracle(s, O.TG)
+    for got, ref in zip(h.thermostat_params(), o.thermostat_params()):
+        np.testing.assert_allclose(got, ref, rtol=1e-14)      # the COM share sums 12800 terms; last-ulp differences
+    p, v, f = s.positions.copy(), s.velocities.copy(), s.forces.copy()
+    np.testing.assert_allclose(h.compute_kinetic_energies(st.velm.data_ptr()), o.compute_ke2(v), rtol=1e-6)
+    h.step(*st.ptrs, nsteps=3)
+    o.step(p, v, f, 3)
+    assert rel_err(st.vel(), v) < 3 * TOL_STEP and rel_err(st.pos(), p) < TOL_STEP
+    assert ke_err(h.kinetic_energies(), o.ke2, o.thermostat_params()[1]) < 1e-6
+    np.testing.assert_allclose(h.vscale(), o.vscale, rtol=1e-6)
+    # the OpenMM-facing calls and the constraint split take the same path
+    h.half1(*st.ptrs); h.half2(st.velm.data_ptr(), st.force.data_ptr())
+    o.step(p, v, f, 1)
+    assert rel_err(st.vel(), v) < 4 * TOL_STEP
+    h.close()
+
+
 def test_invalidate_after_external_velocity_change(cuda):
     """stateChanged (openmmapi/src/DrudeTGNHIntegrator.cpp:166-170): after velocities are rewritten the cached KE is dropped."""
     import torch
