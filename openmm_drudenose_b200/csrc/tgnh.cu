@@ -232,31 +232,37 @@ static int setup_peers(tgnh_handle* h) {
     return TGNH_OK;
 }
 
-template <int KIND, int FFMT, int PREC>
-static StreamKernel pick2(bool useCOM, bool hardwall) {
+template <int KIND, int FFMT, int PREC, bool BIG>
+static StreamKernel pick3(bool useCOM, bool hardwall) {
     if (KIND == KIND_A) {   // only the kernels that move positions contain the hard wall
-        if (useCOM) return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, true, true, PREC> : tgnh_stream_kernel<KIND_A, FFMT, true, false, PREC>;
-        return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, false, true, PREC> : tgnh_stream_kernel<KIND_A, FFMT, false, false, PREC>;
+        if (useCOM) return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, true, true, PREC, BIG> : tgnh_stream_kernel<KIND_A, FFMT, true, false, PREC, BIG>;
+        return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, false, true, PREC, false> : tgnh_stream_kernel<KIND_A, FFMT, false, false, PREC, false>;
     }
-    if (KIND == KIND_A2) return hardwall ? tgnh_stream_kernel<KIND_A2, 0, false, true, PREC> : tgnh_stream_kernel<KIND_A2, 0, false, false, PREC>;
-    if (KIND == KIND_KE) return useCOM ? tgnh_stream_kernel<KIND_KE, 0, true, false, PREC> : tgnh_stream_kernel<KIND_KE, 0, false, false, PREC>;
-    return useCOM ? tgnh_stream_kernel<KIND, FFMT, true, false, PREC> : tgnh_stream_kernel<KIND, FFMT, false, false, PREC>;
+    if (KIND == KIND_A2) return hardwall ? tgnh_stream_kernel<KIND_A2, 0, false, true, PREC, false> : tgnh_stream_kernel<KIND_A2, 0, false, false, PREC, false>;
+    if (KIND == KIND_KE) return useCOM ? tgnh_stream_kernel<KIND_KE, 0, true, false, PREC, BIG> : tgnh_stream_kernel<KIND_KE, 0, false, false, PREC, false>;
+    return useCOM ? tgnh_stream_kernel<KIND, FFMT, true, false, PREC, BIG> : tgnh_stream_kernel<KIND, FFMT, false, false, PREC, false>;
+}
+
+// residues larger than a tile only matter to kernels that use the residues' COM velocity (USE_COM)
+template <int KIND, int FFMT, int PREC>
+static StreamKernel pick2(bool useCOM, bool hardwall, bool big) {
+    return big ? pick3<KIND, FFMT, PREC, true>(useCOM, hardwall) : pick3<KIND, FFMT, PREC, false>(useCOM, hardwall);
 }
 
 template <int KIND>
-static StreamKernel pick1(int ffmt, int prec, bool useCOM, bool hardwall) {
-    if (prec) return ffmt ? pick2<KIND, 1, 1>(useCOM, hardwall) : pick2<KIND, 0, 1>(useCOM, hardwall);
-    return ffmt ? pick2<KIND, 1, 0>(useCOM, hardwall) : pick2<KIND, 0, 0>(useCOM, hardwall);
+static StreamKernel pick1(int ffmt, int prec, bool useCOM, bool hardwall, bool big) {
+    if (prec) return ffmt ? pick2<KIND, 1, 1>(useCOM, hardwall, big) : pick2<KIND, 0, 1>(useCOM, hardwall, big);
+    return ffmt ? pick2<KIND, 1, 0>(useCOM, hardwall, big) : pick2<KIND, 0, 0>(useCOM, hardwall, big);
 }
 
-static StreamKernel pick(int kind, int ffmt, int prec, bool useCOM, bool hardwall) {
+static StreamKernel pick(int kind, int ffmt, int prec, bool useCOM, bool hardwall, bool big) {
     switch (kind) {
-        case KIND_A: return pick1<KIND_A>(ffmt, prec, useCOM, hardwall);
-        case KIND_B: return pick1<KIND_B>(ffmt, prec, useCOM, hardwall);
-        case KIND_BU: return pick1<KIND_BU>(ffmt, prec, useCOM, hardwall);
-        case KIND_A1: return pick1<KIND_A1>(ffmt, prec, useCOM, hardwall);
-        case KIND_A2: return pick1<KIND_A2>(ffmt, prec, useCOM, hardwall);
-        default: return pick1<KIND_KE>(ffmt, prec, useCOM, hardwall);
+        case KIND_A: return pick1<KIND_A>(ffmt, prec, useCOM, hardwall, big);
+        case KIND_B: return pick1<KIND_B>(ffmt, prec, useCOM, hardwall, big);
+        case KIND_BU: return pick1<KIND_BU>(ffmt, prec, useCOM, hardwall, big);
+        case KIND_A1: return pick1<KIND_A1>(ffmt, prec, useCOM, hardwall, big);
+        case KIND_A2: return pick1<KIND_A2>(ffmt, prec, useCOM, hardwall, big);
+        default: return pick1<KIND_KE>(ffmt, prec, useCOM, hardwall, big);
     }
 }
 
@@ -285,7 +291,7 @@ static int smem_bytes(int kind, int ffmt, int prec, bool useCOM, int T) {
 }
 
 static int configure_kernel(tgnh_handle* h, int kind, int* grid, int* smem) {
-    StreamKernel k = pick(kind, h->ffmt, h->prec, h->useCOM, h->hardwall);
+    StreamKernel k = pick(kind, h->ffmt, h->prec, h->useCOM, h->hardwall, h->numBig > 0);
     *smem = smem_bytes(kind, h->ffmt, h->prec, h->useCOM, h->T);
     if (*smem > 227 * 1024)
         return fail(TGNH_ERR_UNSUPPORTED, "%d temperature groups need %d bytes of shared memory per CTA (limit 232448)", h->G, *smem);
@@ -670,7 +676,7 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     if (p2p) a.peers.seq = ++h->reduceSeq; else a.peers.world = 0;
     const int grid = kind == KIND_A1 ? h->gridA1 : kind == KIND_A2 ? h->gridA2 : prof == KIND_A ? h->gridA : prof == KIND_B ? h->gridB : h->gridKE;
     const int smem = kind == KIND_A1 ? h->smemA1 : kind == KIND_A2 ? h->smemA2 : prof == KIND_A ? h->smemA : prof == KIND_B ? h->smemB : h->smemKE;
-    StreamKernel k = pick(kind, h->ffmt, h->prec, h->useCOM, h->hardwall);
+    StreamKernel k = pick(kind, h->ffmt, h->prec, h->useCOM, h->hardwall, h->numBig > 0);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
         if (h->evUsed + 2 > h->evPool.size()) {

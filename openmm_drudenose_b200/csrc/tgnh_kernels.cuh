@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) tgnh_bigcom_kernel(const __grid_constant_
 // previous launch wrote is still resident: those reads never reach HBM and the dirty lines are overwritten in
 // L2 before they are evicted.  velm stores therefore use the default L2 policy while everything that is touched
 // once per step (posq, forces, descriptors) is loaded evict-first / stored streaming.
-template <int KIND, int FFMT, bool USE_COM, bool HARDWALL, int PREC>
+template <int KIND, int FFMT, bool USE_COM, bool HARDWALL, int PREC, bool BIG>
 __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const __grid_constant__ StreamArgs a) {
     using L = SmemLayout<KIND, FFMT, USE_COM, PREC>;
     using St = typename L::Stage;
@@ -480,7 +480,8 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
         R3 V = v3(real(0), real(0), real(0));
         double keC = 0.0;                             // M |V|^2 of this particle's residue (kinds that reduce energies)
         bool firstOfRes = desc_off_first(d) == 0;       // the residue's first particle carries M |V|^2
-        if (USE_COM && active && KIND != KIND_A2 && desc_big(d)) {
+        const bool big = BIG && desc_big(d);            // BIG: the system has residues larger than a tile (separate instantiation)
+        if (USE_COM && active && KIND != KIND_A2 && big) {
             // big residue (a protein, a polymer): V and M from the pre-pass table (tgnh_bigcom_kernel)
             const int b = big_index(a.bigFirst, a.numBig, start + tid);
             const double4 c = a.bigCom[b];
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
             // one thread per residue of the tile; the duty rotates over the warps from tile to tile so that no warp is
             // always the slow one (a stage is recycled only when all 16 warps have left it)
             const int ridx = (tid - it * 128) & (TILE - 1);
-            if (USE_COM && active && desc_big(d) && firstOfRes) {   // big residue: M |V|^2 from the pre-pass table
+            if (USE_COM && active && big && firstOfRes) {   // big residue: M |V|^2 from the pre-pass table
                 accCOM += keC;
                 ske[tg * TILE + tid] -= keC;
             }
@@ -540,7 +541,8 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
                 // P = sum_j m_j v_j (kicked velocities), M = sum_j m_j over the residue's massive members
                 const int* sr = reinterpret_cast<const int*>(st + St::OFF_R) + (hdr.z & 3);
                 const int j0 = sr[ridx] - start;
-                const int j1 = desc_big(sd[fo + j0]) ? j0 : sr[ridx + 1] - start;      // segments of big residues: nothing to do here
+                const uint32_t d0 = sd[fo + j0];
+                const int j1 = (BIG && desc_big(d0)) ? j0 : sr[ridx + 1] - start;      // segments of big residues: nothing to do here
                 V3<double> P = v3(0.0, 0.0, 0.0);
                 double M = 0.0;
                 for (int j = j0; j < j1; j++) {
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
                 }
                 const double keRes = j1 > j0 ? dot3(P) * rcp_d(M, rcp_fast((float)M)) : 0.0;   // M |V|^2 = |P|^2 / M
                 accCOM += keRes;
-                ske[desc_tg(sd[fo + j0]) * TILE + tid] -= keRes;
+                ske[desc_tg(d0) * TILE + tid] -= keRes;
             }
         } else if (KIND == KIND_B) {
             // integrateDrudeTGNHVelocities (drudeTGNH.cu:314-364), updatePosDelta = false
