@@ -414,3 +414,52 @@ def test_constraint_split_uses_the_constrained_displacement(cuda):
     assert torch.equal(st.posq[:n][~massive], x0[:n][~massive])
     assert torch.equal(st.posq[:n, 3], x0[:n, 3]) and torch.equal(st.velm[:n, 3], v1[:n, 3])
     h.close()
+
+
+@pytest.mark.parametrize("prec", [capi.PRECISION_SINGLE, capi.PRECISION_MIXED])
+@pytest.mark.parametrize("name", ["ragged", "polymer"])
+def test_kernels_stay_inside_their_buffers(cuda, name, prec):
+    """Every caller-owned array sits between guard zones filled with a bit pattern; after all kinds of launches (fused
+    step, OpenMM-facing halves, constraint split, flush, kinetic-energy query) the guards are untouched, the padding
+    particles beyond N are untouched, and forces / charges are unmodified.  (The TMA tiles read up to 3 elements beyond a
+    tile's end inside 4-aligned windows: reads only, and only inside paddedN.)"""
+    import torch
+    s = (synth.build([synth.WATER4, synth.SOD, synth.SWM4], np.arange(1501) % 3, np.arange(1501) % 2, 2) if name == "ragged"
+         else synth.polymer_in_water(300, (300, 450), 2))
+    n = s.num_particles
+    padded = ((n + 31) // 32) * 32
+    GUARD = 4096                                             # bytes on each side
+
+    def guarded(nbytes):
+        buf = torch.full((GUARD + nbytes + GUARD,), 0xA5, dtype=torch.uint8, device=cuda)
+        return buf, buf[GUARD:GUARD + nbytes]
+
+    vb = 32 if prec else 16
+    st = DeviceState(s, cuda, force_format=capi.FORCE_I64_SOA, padded=padded, precision=prec)
+    bufs = {}
+    for key, src in (("velm", st.velm), ("posq", st.posq), ("force", st.force), ("delta", torch.zeros((padded, 4), dtype=st.velm.dtype, device=cuda)),
+                     ("corr", st.corr if prec else torch.zeros((padded, 4), dtype=torch.float32, device=cuda))):
+        whole, view = guarded(src.numel() * src.element_size())
+        view.copy_(src.contiguous().view(torch.uint8).reshape(-1))
+        bufs[key] = (whole, view)
+    ptr = {k: v[1].data_ptr() for k, v in bufs.items()}
+    assert all(p % 16 == 0 for p in ptr.values())
+    force_before = bufs["force"][1].clone()
+    h = capi.Handle(s, force_format=capi.FORCE_I64_SOA, precision=prec, padded=padded)
+    if prec:
+        h.set_posq_correction(ptr["corr"])
+    h.step(ptr["velm"], ptr["posq"], ptr["force"], nsteps=3)
+    h.half1(ptr["velm"], ptr["posq"], ptr["force"]); h.half2(ptr["velm"], ptr["force"], capi.HALF2_DEFER_SCALE); h.flush(ptr["velm"])
+    h.half1_kick(ptr["velm"], ptr["force"], ptr["delta"]); h.half1_drift(ptr["velm"], ptr["posq"], ptr["delta"])
+    h.half2(ptr["velm"], ptr["force"], capi.HALF2_KICK_ONLY); h.thermostat(ptr["velm"])
+    h.compute_kinetic_energies(ptr["velm"])
+    torch.cuda.synchronize()
+    for key, (whole, view) in bufs.items():
+        assert bool((whole[:GUARD] == 0xA5).all()) and bool((whole[-GUARD:] == 0xA5).all()), f"guard zone of {key} was written"
+    assert torch.equal(bufs["force"][1], force_before), "forces were modified"
+    velm_after = bufs["velm"][1].view(st.velm.dtype).reshape(padded, 4)
+    posq_after = bufs["posq"][1].view(torch.float32).reshape(padded, 4)
+    assert bool((velm_after[n:] == 0).all()) and bool((posq_after[n:] == 0).all()), "padding particles were written"
+    assert np.array_equal(posq_after[:n, 3].cpu().numpy(), st.charges)
+    assert bool(torch.isfinite(velm_after).all()) and bool(torch.isfinite(posq_after).all())
+    h.close()
