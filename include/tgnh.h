@@ -49,11 +49,12 @@ enum {
 
 enum { TGNH_FORCE_F32_SOA = 0, TGNH_FORCE_I64_SOA = 1 };
 
-/* OpenMM CUDA precision modes (cu.getUseMixedPrecision()):
+/* OpenMM CUDA precision modes (cu.getUseMixedPrecision() / cu.getUseDoublePrecision()):
  *   SINGLE  velm float4,  posq float4,                         posDelta float4;  fp32 arithmetic, fp64 energy sums + chain
  *   MIXED   velm double4, posq float4 + posqCorrection float4, posDelta double4; fp64 arithmetic ("mixed" = double in
- *           drudeTGNH.cu); register cu.getPosqCorrection() once with tgnh_set_posq_correction */
-enum { TGNH_PRECISION_SINGLE = 0, TGNH_PRECISION_MIXED = 1 };
+ *           drudeTGNH.cu); register cu.getPosqCorrection() once with tgnh_set_posq_correction
+ *   DOUBLE  velm double4, posq double4,                        posDelta double4; fp64 arithmetic */
+enum { TGNH_PRECISION_SINGLE = 0, TGNH_PRECISION_MIXED = 1, TGNH_PRECISION_DOUBLE = 2 };
 
 /* flags for tgnh_half2 */
 enum {

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libtgnh.so")
 
 OK, ERR_INVALID_ARGUMENT, ERR_TEMP_GROUP, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE = range(7)
 FORCE_F32_SOA, FORCE_I64_SOA = 0, 1
-PRECISION_SINGLE, PRECISION_MIXED = 0, 1
+PRECISION_SINGLE, PRECISION_MIXED, PRECISION_DOUBLE = 0, 1, 2
 HALF2_DEFAULT, HALF2_DEFER_SCALE, HALF2_KICK_ONLY = 0, 1, 2
 UNIQUE_ID_BYTES = 128
 BOLTZ = 1.380649e-23 * 6.02214076e23 / 1000.0

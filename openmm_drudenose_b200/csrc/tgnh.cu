@@ -249,8 +249,12 @@ static StreamKernel pick2(bool useCOM, bool hardwall, bool big) {
     return big ? pick3<KIND, FFMT, PREC, true>(useCOM, hardwall) : pick3<KIND, FFMT, PREC, false>(useCOM, hardwall);
 }
 
+// PREC 2 (double4 posq) exists only for the kernels that touch positions; elsewhere double and mixed are the same kernel
 template <int KIND>
 static StreamKernel pick1(int ffmt, int prec, bool useCOM, bool hardwall, bool big) {
+    if (prec == 2 && (KIND == KIND_A || KIND == KIND_A2))
+        return ffmt ? pick2<KIND, 1, (KIND == KIND_A || KIND == KIND_A2) ? 2 : 1>(useCOM, hardwall, big)
+                    : pick2<KIND, 0, (KIND == KIND_A || KIND == KIND_A2) ? 2 : 1>(useCOM, hardwall, big);
     if (prec) return ffmt ? pick2<KIND, 1, 1>(useCOM, hardwall, big) : pick2<KIND, 0, 1>(useCOM, hardwall, big);
     return ffmt ? pick2<KIND, 1, 0>(useCOM, hardwall, big) : pick2<KIND, 0, 0>(useCOM, hardwall, big);
 }
@@ -275,6 +279,8 @@ static int smem2(bool useCOM, int T) {
 
 template <int KIND>
 static int smem1(int ffmt, int prec, bool useCOM, int T) {
+    if (prec == 2 && (KIND == KIND_A || KIND == KIND_A2))
+        return ffmt ? smem2<KIND, 1, (KIND == KIND_A || KIND == KIND_A2) ? 2 : 1>(useCOM, T) : smem2<KIND, 0, (KIND == KIND_A || KIND == KIND_A2) ? 2 : 1>(useCOM, T);
     if (prec) return ffmt ? smem2<KIND, 1, 1>(useCOM, T) : smem2<KIND, 0, 1>(useCOM, T);
     return ffmt ? smem2<KIND, 1, 0>(useCOM, T) : smem2<KIND, 0, 0>(useCOM, T);
 }
@@ -327,7 +333,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         return fail(TGNH_ERR_INVALID_ARGUMENT, "padded_num_particles must be a multiple of 4 and >= num_particles");
     if (p->force_format != TGNH_FORCE_F32_SOA && p->force_format != TGNH_FORCE_I64_SOA)
         return fail(TGNH_ERR_INVALID_ARGUMENT, "unknown force_format %d", p->force_format);
-    if (p->precision != TGNH_PRECISION_SINGLE && p->precision != TGNH_PRECISION_MIXED)
+    if (p->precision != TGNH_PRECISION_SINGLE && p->precision != TGNH_PRECISION_MIXED && p->precision != TGNH_PRECISION_DOUBLE)
         return fail(TGNH_ERR_INVALID_ARGUMENT, "unknown precision %d", p->precision);
     if (p->max_drude_distance < 0) return fail(TGNH_ERR_INVALID_ARGUMENT, "setMaxDrudeDistance: Distance cannot be negative");
     if (!(p->step_size > 0)) return fail(TGNH_ERR_INVALID_ARGUMENT, "step_size must be positive");
@@ -649,8 +655,8 @@ static int launch_chain(tgnh_handle* h, cudaStream_t s, int mode, bool gather = 
 static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, void* posq, const void* force, int applyScale, int chainMode,
                          void* posDelta = nullptr) {
     StreamArgs a;
-    a.velm = velm; a.posq = (float4*)posq; a.posqCorrection = (float4*)h->posqCorrection; a.force = force; a.posDelta = posDelta;
-    if (h->prec && posq != nullptr && h->posqCorrection == nullptr)
+    a.velm = velm; a.posq = posq; a.posqCorrection = (float4*)h->posqCorrection; a.force = force; a.posDelta = posDelta;
+    if (h->prec == TGNH_PRECISION_MIXED && posq != nullptr && h->posqCorrection == nullptr)
         return fail(TGNH_ERR_INVALID_ARGUMENT, "mixed precision: register the posqCorrection array with tgnh_set_posq_correction first");
     a.desc = h->dDesc; a.tileStart = h->dTileStart; a.numTiles = h->numTiles; a.paddedN = h->paddedN;
     a.resStart = h->dResStart; a.tileFirstRes = h->dTileFirstRes;
@@ -828,7 +834,7 @@ extern "C" int tgnh_step(tgnh_handle* h, void* stream, void* velm, void* posq, c
 
 extern "C" int tgnh_set_posq_correction(tgnh_handle* h, void* posq_correction) {
     if (!h) return fail(TGNH_ERR_INVALID_ARGUMENT, "null handle");
-    if (!h->prec) return fail(TGNH_ERR_INVALID_ARGUMENT, "posqCorrection exists in mixed precision only");
+    if (h->prec != TGNH_PRECISION_MIXED) return fail(TGNH_ERR_INVALID_ARGUMENT, "posqCorrection exists in mixed precision only");
     if (!posq_correction || ((uintptr_t)posq_correction & 15)) return fail(TGNH_ERR_INVALID_ARGUMENT, "posq_correction must be a 16-byte aligned device pointer");
     h->posqCorrection = posq_correction;
     return TGNH_OK;

@@ -39,7 +39,8 @@
 //
 // Precision (template parameter PREC): 0 = OpenMM's single-precision layout (float4 velm, float4 posq), fp32 arithmetic
 // with fp64 energy sums; 1 = OpenMM's mixed-precision layout (double4 velm, float4 posq + float4 posqCorrection, double4
-// posDelta; `mixed` = double in drudeTGNH.cu), all arithmetic in double.
+// posDelta; `mixed` = double in drudeTGNH.cu), all arithmetic in double; 2 = OpenMM's double-precision layout (as 1, but
+// posq is double4 and there is no posqCorrection) — instantiated only for the kernels that touch positions.
 #pragma once
 #include "tgnh_device.cuh"
 
@@ -52,10 +53,11 @@ constexpr int TLIST_CAP = 128;     // tile bounds cached in shared memory per CT
 template <int PREC> struct Prec;
 template <> struct Prec<0> { typedef float real; typedef float4 real4; };
 template <> struct Prec<1> { typedef double real; typedef double4 real4; };
+template <> struct Prec<2> { typedef double real; typedef double4 real4; };   // differs from 1 only where positions are touched
 
 struct StreamArgs {
     void* velm;               // real4[paddedN]
-    float4* posq;             // float4[paddedN]
+    void* posq;               // float4[paddedN] (single, mixed) or double4[paddedN] (double)
     float4* posqCorrection;   // float4[paddedN], mixed precision only (cu.getPosqCorrection())
     void* posDelta;           // real4[paddedN] (dt*v, 0): integration.getPosDelta() (KIND_A1 writes, KIND_A2 reads)
     const void* force;        // SoA [3][paddedN], float or long long
@@ -92,8 +94,9 @@ struct StageLayout {
     static constexpr int VB = PREC ? 32 : 16;                    // bytes of one velm / posDelta element
     static constexpr int OFF_V = 0;
     static constexpr int OFF_X = OFF_V + TILE * VB;
-    static constexpr int OFF_XC = OFF_X + (HAS_X ? TILE * 16 : 0);             // posqCorrection tile (mixed)
-    static constexpr int OFF_F = OFF_XC + ((HAS_X && PREC) ? TILE * 16 : 0);
+    static constexpr int XB = PREC == 2 ? 32 : 16;               // bytes of one posq element
+    static constexpr int OFF_XC = OFF_X + (HAS_X ? TILE * XB : 0);             // posqCorrection tile (mixed)
+    static constexpr int OFF_F = OFF_XC + ((HAS_X && PREC == 1) ? TILE * 16 : 0);
     static constexpr int OFF_D = OFF_F + (HAS_F ? 3 * PADW * FBYTES : 0);
     static constexpr int OFF_R = OFF_D + PADW * 4;              // residue starts of the tile (KIND_BU)
     static constexpr int OFF_P = OFF_R + (HAS_R ? PADW * 4 : 0);
@@ -132,6 +135,10 @@ __device__ __forceinline__ float4 pack4(V3<float> a, float w) { return make_floa
 __device__ __forceinline__ double4 pack4(V3<double> a, double w) { return make_double4(a.x, a.y, a.z, w); }
 template <typename T> __device__ __forceinline__ V3<double> to_double(V3<T> a) { return v3((double)a.x, (double)a.y, (double)a.z); }
 
+__device__ __forceinline__ void st_stream(double4* p, double4 v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(reinterpret_cast<double2*>(p) + 1), "d"(v.z), "d"(v.w) : "memory");
+}
 __device__ __forceinline__ void st_global(double4* p, double4 v) {
     asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
     asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(reinterpret_cast<double2*>(p) + 1), "d"(v.z), "d"(v.w) : "memory");
@@ -233,11 +240,23 @@ template <typename T> __device__ __forceinline__ V3<T> kicked(V3<T> v, T fw, V3<
 // positions: single = posq; mixed = posq + posqCorrection in double (drudeTGNH.cu:441-448, 476-486)
 template <int PREC> struct PosTile;
 template <> struct PosTile<0> {
+    typedef float Q;                                   // type of the charge carried in posq.w
     const float4* sx;
     __device__ __forceinline__ V3<float> load(int i, float& q) const { const float4 p = sx[i]; q = p.w; return v3(p.x, p.y, p.z); }
-    __device__ __forceinline__ static void store(const StreamArgs& a, int gi, V3<float> x, float q) { st_stream(a.posq + gi, make_float4(x.x, x.y, x.z, q)); }
+    __device__ __forceinline__ static void store(const StreamArgs& a, int gi, V3<float> x, float q) {
+        st_stream(static_cast<float4*>(a.posq) + gi, make_float4(x.x, x.y, x.z, q));
+    }
+};
+template <> struct PosTile<2> {
+    typedef double Q;
+    const double4* sx;
+    __device__ __forceinline__ V3<double> load(int i, double& q) const { const double4 p = sx[i]; q = p.w; return v3(p.x, p.y, p.z); }
+    __device__ __forceinline__ static void store(const StreamArgs& a, int gi, V3<double> x, double q) {
+        st_stream(static_cast<double4*>(a.posq) + gi, make_double4(x.x, x.y, x.z, q));
+    }
 };
 template <> struct PosTile<1> {
+    typedef float Q;
     const float4* sx;
     const float4* sc;
     __device__ __forceinline__ V3<double> load(int i, float& q) const {
@@ -247,14 +266,17 @@ template <> struct PosTile<1> {
     }
     __device__ __forceinline__ static void store(const StreamArgs& a, int gi, V3<double> x, float q) {
         const float hx = (float)x.x, hy = (float)x.y, hz = (float)x.z;                       // :457-458
-        st_stream(a.posq + gi, make_float4(hx, hy, hz, q));
+        st_stream(static_cast<float4*>(a.posq) + gi, make_float4(hx, hy, hz, q));
         st_stream(a.posqCorrection + gi, make_float4((float)(x.x - hx), (float)(x.y - hy), (float)(x.z - hz), 0.0f));
     }
 };
 
-template <int PREC> __device__ __forceinline__ PosTile<PREC> make_pos(const float4* sx, const float4* sc);
-template <> __device__ __forceinline__ PosTile<0> make_pos<0>(const float4* sx, const float4*) { PosTile<0> p; p.sx = sx; return p; }
-template <> __device__ __forceinline__ PosTile<1> make_pos<1>(const float4* sx, const float4* sc) { PosTile<1> p; p.sx = sx; p.sc = sc; return p; }
+template <int PREC> __device__ __forceinline__ PosTile<PREC> make_pos(const void* sx, const void* sc);
+template <> __device__ __forceinline__ PosTile<0> make_pos<0>(const void* sx, const void*) { PosTile<0> p; p.sx = static_cast<const float4*>(sx); return p; }
+template <> __device__ __forceinline__ PosTile<1> make_pos<1>(const void* sx, const void* sc) {
+    PosTile<1> p; p.sx = static_cast<const float4*>(sx); p.sc = static_cast<const float4*>(sc); return p;
+}
+template <> __device__ __forceinline__ PosTile<2> make_pos<2>(const void* sx, const void*) { PosTile<2> p; p.sx = static_cast<const double4*>(sx); return p; }
 
 // index of the big residue that holds `particle`: the last entry of the ascending table that is <= particle
 __device__ __forceinline__ int big_index(const int* bigFirst, int numBig, int particle) {
@@ -370,7 +392,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
         const int4 b = it < TLIST_CAP ? tlist[it] : tile_bounds(it);
         const int start = b.x, end = b.y;
         const int n = end - start, a0 = start & ~3, na = ((end + 3) & ~3) - a0;
-        if (St::HAS_X) bulk_prefetch_l2(a.posq + start, n * 16);
+        if (St::HAS_X) bulk_prefetch_l2(static_cast<const unsigned char*>(a.posq) + (size_t)start * St::XB, n * St::XB);
         if (St::HAS_F) {
             const unsigned char* f = static_cast<const unsigned char*>(a.force);
             for (int c = 0; c < 3; c++) bulk_prefetch_l2(f + ((size_t)c * a.paddedN + a0) * St::FBYTES, na * St::FBYTES);
@@ -392,13 +414,13 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
             uint32_t bytes = n * St::VB + na * 4;
             const int ra0 = r0 & ~3, rna = ((r1 + 1 + 3) & ~3) - ra0;     // residues r0..r1 inclusive (r1 = end marker)
             if (St::HAS_R) bytes += rna * 4;
-            if (St::HAS_X) bytes += n * (PREC ? 32 : 16);
+            if (St::HAS_X) bytes += n * (PREC == 1 ? 32 : St::XB);
             if (St::HAS_P) bytes += n * St::VB;
             if (St::HAS_F) bytes += 3 * na * St::FBYTES;
             mbar_arrive_expect_tx(bar, bytes);
             if (St::HAS_X) {
-                bulk_g2s(st + St::OFF_X, a.posq + start, n * 16, bar, polOnce);
-                if (PREC) bulk_g2s(st + St::OFF_XC, a.posqCorrection + start, n * 16, bar, polOnce);
+                bulk_g2s(st + St::OFF_X, static_cast<const unsigned char*>(a.posq) + (size_t)start * St::XB, n * St::XB, bar, polOnce);
+                if (PREC == 1) bulk_g2s(st + St::OFF_XC, a.posqCorrection + start, n * 16, bar, polOnce);
             }
             if (St::HAS_F) {
                 const unsigned char* f = static_cast<const unsigned char*>(a.force);
@@ -440,7 +462,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
         const uint32_t phase = (it / NS) & 1;
         unsigned char* st = smem + stg * St::BYTES;
         const real4* sv = reinterpret_cast<const real4*>(st + St::OFF_V);
-        const PosTile<PREC> pos = make_pos<PREC>(reinterpret_cast<const float4*>(st + St::OFF_X), reinterpret_cast<const float4*>(st + St::OFF_XC));
+        const PosTile<PREC> pos = make_pos<PREC>(st + St::OFF_X, st + St::OFF_XC);
         const unsigned char* sF = st + St::OFF_F;
         const uint32_t* sd = reinterpret_cast<const uint32_t*>(st + St::OFF_D);
 
@@ -616,12 +638,12 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
             // integrateDrudeTGNHPositions (drudeTGNH.cu:438-465): x += delta, v = delta / dt; then the hard wall (:474-573)
             const real4* sp = reinterpret_cast<const real4*>(st + St::OFF_P);
             const real invDt = real(1) / dt;
-            float q;
+            typename PosTile<PREC>::Q q;
             const R3 dl = xyz(sp[tid]), x = pos.load(tid, q);
             R3 xn = x + dl;
             vn = invDt * dl;
             if (HARDWALL && role != ROLE_NORMAL) {
-                float qj;
+                typename PosTile<PREC>::Q qj;
                 const R3 dj = xyz(sp[pj]), xj = pos.load(pj, qj);
                 R3 vjn = invDt * dj;
                 const R3 delta = (x - xj) + (dl - dj);
@@ -639,7 +661,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
         } else if (KIND == KIND_A && active) {
             // half kick + drift (+ hard wall) (drudeTGNH.cu:314-364, 438-465, 474-573)
             vn = kicked(vn, fw, F);
-            float q;
+            typename PosTile<PREC>::Q q;
             const R3 x = pos.load(tid, q);
             R3 xn = axpy(dt, vn, x);
             if (HARDWALL && role != ROLE_NORMAL) {
@@ -647,7 +669,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
                 // seen from the partner, rel changes sign and the mass fraction is this particle's
                 const R3 rj = vj - V;
                 R3 vjn = kicked(scaled_velocity(vj, eT, rj, eCOM, V, coef * fi, -rel), fwj, Fj);
-                float qj;
+                typename PosTile<PREC>::Q qj;
                 const R3 xj = pos.load(pj, qj);
                 // displacement from the exact difference of the old positions plus the relative drift: avoids the
                 // cancellation of two rounded box-sized coordinates in the wall test

@@ -19,10 +19,8 @@ public:
     explicit CudaContextAccess(CudaContext& cu) : cu(cu) {}
     TgnhDeviceView view() {
         cu.setAsCurrent();
-        if (cu.getUseDoublePrecision())
-            throw OpenMMException("DrudeTGNH (libtgnh): the single and mixed CUDA layouts are implemented; create the Context with Precision=single or mixed");
         TgnhDeviceView v;
-        v.precision = cu.getUseMixedPrecision() ? TGNH_PRECISION_MIXED : TGNH_PRECISION_SINGLE;
+        v.precision = cu.getUseDoublePrecision() ? TGNH_PRECISION_DOUBLE : cu.getUseMixedPrecision() ? TGNH_PRECISION_MIXED : TGNH_PRECISION_SINGLE;
         v.posqCorrection = cu.getUseMixedPrecision() ? (void*)cu.getPosqCorrection().getDevicePointer() : NULL;
         v.velm = (void*)cu.getVelm().getDevicePointer();
         v.posq = (void*)cu.getPosq().getDevicePointer();

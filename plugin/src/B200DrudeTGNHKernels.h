@@ -16,14 +16,14 @@ namespace OpenMM {
 /** Device arrays of the platform the kernel runs on, in OpenMM's CUDA layouts. */
 struct TgnhDeviceView {
     void* velm;          // float4 (single) / double4 (mixed) [paddedNumAtoms]   cu.getVelm()
-    void* posq;          // float4[paddedNumAtoms]   cu.getPosq()
+    void* posq;          // float4 (single, mixed) / double4 (double) [paddedNumAtoms]   cu.getPosq()
     const void* force;   // SoA [3][paddedNumAtoms]  cu.getForce()
     void* posDelta;      // float4 / double4 [paddedNumAtoms]   integration.getPosDelta() (constrained systems only, may be NULL otherwise)
     int paddedNumAtoms;  // cu.getPaddedNumAtoms()
     int forceFormat;     // TGNH_FORCE_I64_SOA for OpenMM's fixed-point buffer
     void* stream;        // cudaStream_t the platform launches on
     int device;          // CUDA device ordinal
-    int precision;       // TGNH_PRECISION_SINGLE / TGNH_PRECISION_MIXED   cu.getUseMixedPrecision()
+    int precision;       // TGNH_PRECISION_SINGLE / _MIXED / _DOUBLE   cu.getUseMixedPrecision(), cu.getUseDoublePrecision()
     void* posqCorrection;  // float4[paddedNumAtoms], mixed only   cu.getPosqCorrection()
 };
 

@@ -14,8 +14,9 @@ MIXED = capi.PRECISION_MIXED
 
 
 def _handle(s, st, **kw):
-    h = capi.Handle(s, force_format=st.force_format, precision=MIXED, padded=st.padded, **kw)
-    h.set_posq_correction(st.corr.data_ptr())
+    h = capi.Handle(s, force_format=st.force_format, precision=st.precision, padded=st.padded, **kw)
+    if st.precision == MIXED:
+        h.set_posq_correction(st.corr.data_ptr())
     return h
 
 
@@ -32,26 +33,38 @@ SYSTEMS = {
 
 @pytest.mark.parametrize("name", sorted(SYSTEMS))
 @pytest.mark.parametrize("fmt", [capi.FORCE_F32_SOA, capi.FORCE_I64_SOA])
-def test_mixed_steps_match_oracle_to_rounding(cuda, name, fmt):
+@pytest.mark.parametrize("prec", [capi.PRECISION_MIXED, capi.PRECISION_DOUBLE])
+def test_mixed_steps_match_oracle_to_rounding(cuda, name, fmt, prec):
+    """prec = DOUBLE: OpenMM's double-precision layout (double4 posq, no posqCorrection); same kernels except where positions
+    are loaded and stored."""
     s = SYSTEMS[name]()
     # forces exactly representable in the device format, positions as posq + posqCorrection can hold them
     s.forces = (np.rint(s.forces * 4294967296.0) / 4294967296.0) if fmt else s.forces.astype(np.float32).astype(np.float64)
     s.positions = s.positions + 1e-9 * np.sin(np.arange(s.positions.size).reshape(s.positions.shape))      # needs the correction array
     hi = s.positions.astype(np.float32).astype(np.float64)
     s.positions = hi + (s.positions - hi).astype(np.float32).astype(np.float64)
-    st = DeviceState(s, cuda, force_format=fmt, precision=1)
+    st = DeviceState(s, cuda, force_format=fmt, precision=prec)
     h = _handle(s, st)
     o = O.Oracle(s, O.TG, constraints=s.constraints)
     p, v, f = s.positions.copy(), s.velocities.copy(), s.forces.copy()
     h.step(*st.ptrs, nsteps=5)
     o.step(p, v, f, 5)
     assert rel_err(st.vel(), v) < 1e-11
-    assert rel_err(st.pos(), p) < 2e-8                      # positions are stored as float + float residual (~48 bits)
+    assert rel_err(st.pos(), p) < (2e-8 if prec == MIXED else 1e-13)   # mixed: float + float residual (~48 bits)
     nkbt = o.thermostat_params()[1]
     assert ke_err(h.kinetic_energies(), o.ke2, nkbt) < 1e-11
     np.testing.assert_allclose(h.vscale(), o.vscale, rtol=1e-12)
     assert chain_err(h.chain_state()[1], o.chain_state()[1]) < 1e-9
     assert np.array_equal(st.posq[: s.num_particles, 3].cpu().numpy(), st.charges)
+    if prec == capi.PRECISION_DOUBLE:                     # the constraint split in the double layout
+        import torch
+        delta = torch.zeros_like(st.velm)
+        h.half1_kick(st.velm.data_ptr(), st.force.data_ptr(), delta.data_ptr())
+        h.half1_drift(st.velm.data_ptr(), st.posq.data_ptr(), delta.data_ptr())
+        h.half2(st.velm.data_ptr(), st.force.data_ptr(), capi.HALF2_KICK_ONLY)
+        h.thermostat(st.velm.data_ptr())
+        o.step(p, v, f, 1)
+        assert rel_err(st.vel(), v) < 1e-10 and rel_err(st.pos(), p) < 1e-12
     h.close()
 
 

@@ -416,7 +416,7 @@ def test_constraint_split_uses_the_constrained_displacement(cuda):
     h.close()
 
 
-@pytest.mark.parametrize("prec", [capi.PRECISION_SINGLE, capi.PRECISION_MIXED])
+@pytest.mark.parametrize("prec", [capi.PRECISION_SINGLE, capi.PRECISION_MIXED, capi.PRECISION_DOUBLE])
 @pytest.mark.parametrize("name", ["ragged", "polymer"])
 def test_kernels_stay_inside_their_buffers(cuda, name, prec):
     """Every caller-owned array sits between guard zones filled with a bit pattern; after all kinds of launches (fused
@@ -438,7 +438,7 @@ def test_kernels_stay_inside_their_buffers(cuda, name, prec):
     st = DeviceState(s, cuda, force_format=capi.FORCE_I64_SOA, padded=padded, precision=prec)
     bufs = {}
     for key, src in (("velm", st.velm), ("posq", st.posq), ("force", st.force), ("delta", torch.zeros((padded, 4), dtype=st.velm.dtype, device=cuda)),
-                     ("corr", st.corr if prec else torch.zeros((padded, 4), dtype=torch.float32, device=cuda))):
+                     ("corr", st.corr if prec == capi.PRECISION_MIXED else torch.zeros((padded, 4), dtype=torch.float32, device=cuda))):
         whole, view = guarded(src.numel() * src.element_size())
         view.copy_(src.contiguous().view(torch.uint8).reshape(-1))
         bufs[key] = (whole, view)
@@ -446,7 +446,7 @@ def test_kernels_stay_inside_their_buffers(cuda, name, prec):
     assert all(p % 16 == 0 for p in ptr.values())
     force_before = bufs["force"][1].clone()
     h = capi.Handle(s, force_format=capi.FORCE_I64_SOA, precision=prec, padded=padded)
-    if prec:
+    if prec == capi.PRECISION_MIXED:
         h.set_posq_correction(ptr["corr"])
     h.step(ptr["velm"], ptr["posq"], ptr["force"], nsteps=3)
     h.half1(ptr["velm"], ptr["posq"], ptr["force"]); h.half2(ptr["velm"], ptr["force"], capi.HALF2_DEFER_SCALE); h.flush(ptr["velm"])
@@ -458,7 +458,7 @@ def test_kernels_stay_inside_their_buffers(cuda, name, prec):
         assert bool((whole[:GUARD] == 0xA5).all()) and bool((whole[-GUARD:] == 0xA5).all()), f"guard zone of {key} was written"
     assert torch.equal(bufs["force"][1], force_before), "forces were modified"
     velm_after = bufs["velm"][1].view(st.velm.dtype).reshape(padded, 4)
-    posq_after = bufs["posq"][1].view(torch.float32).reshape(padded, 4)
+    posq_after = bufs["posq"][1].view(st.posq.dtype).reshape(padded, 4)
     assert bool((velm_after[n:] == 0).all()) and bool((posq_after[n:] == 0).all()), "padding particles were written"
     assert np.array_equal(posq_after[:n, 3].cpu().numpy(), st.charges)
     assert bool(torch.isfinite(velm_after).all()) and bool(torch.isfinite(posq_after).all())

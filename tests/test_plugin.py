@@ -85,15 +85,16 @@ def test_plugin_constrained_system_takes_the_split_sequence(cuda):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["mixed", "double"])
 @pytest.mark.parametrize("constrained", [False, True])
-def test_plugin_stack_mixed_precision(cuda, constrained):
+def test_plugin_stack_mixed_precision(cuda, constrained, precision):
     """Context created with Precision=mixed (what example/nacl_tg.py:60 asks for): double4 velm, posqCorrection, int64
     forces recomputed from the positions each step (Drude springs).  100 steps agree with the oracle to 1e-9 — the
     spring forces see positions through posq + posqCorrection (~48 bits)."""
     from plugin_driver import PluginSim
     kw = dict(quantize_masses=True, pair_force="none", cold_drudes=True, drude_sigma=1.4e-4, force_sigma=2.0)
     s = synth.swm4_box(600, **kw) if constrained else synth.water_box(1500, 3, **kw)
-    sim = PluginSim(s, force_model=1, precision="mixed", with_constraints=constrained, has_cm_motion_remover=constrained)
+    sim = PluginSim(s, force_model=1, precision=precision, with_constraints=constrained, has_cm_motion_remover=constrained)
     o = O.Oracle(s, O.TG, constraints=s.constraints if constrained else None, has_cm_motion_remover=constrained)
     pa, va = s.positions.copy(), s.velocities.copy()
     pb, vb = pa.copy(), va.copy()

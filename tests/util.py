@@ -6,7 +6,8 @@ from oracle import oracle as O
 
 class DeviceState:
     """velm / posq / force of a DrudeSystem as CUDA tensors in the boundary layouts.
-    precision 0: OpenMM single (float4 velm, float4 posq); 1: OpenMM mixed (double4 velm, float4 posq + float4 posqCorrection)."""
+    precision 0: OpenMM single (float4 velm, float4 posq); 1: OpenMM mixed (double4 velm, float4 posq + float4 posqCorrection);
+    2: OpenMM double (double4 velm, double4 posq)."""
 
     def __init__(self, system, device, force_format=0, padded=None, precision=0):
         import torch
@@ -19,13 +20,13 @@ class DeviceState:
         velm = np.zeros((self.padded, 4), vt)
         velm[:n, :3] = system.velocities
         velm[:n, 3] = system.inv_masses.astype(np.float32) if not precision else system.inv_masses
-        posq = np.zeros((self.padded, 4), np.float32)
+        posq = np.zeros((self.padded, 4), np.float64 if precision == 2 else np.float32)
         posq[:n, :3] = system.positions
         posq[:n, 3] = np.arange(n) % 7 - 3.0
         self.velm = torch.from_numpy(velm).to(device)
         self.posq = torch.from_numpy(posq).to(device)
         self.corr = None
-        if precision:
+        if precision == 1:
             corr = np.zeros((self.padded, 4), np.float32)
             corr[:n, :3] = system.positions - posq[:n, :3].astype(np.float64)
             self.corr = torch.from_numpy(corr).to(device)
