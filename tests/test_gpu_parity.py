@@ -463,3 +463,25 @@ def test_kernels_stay_inside_their_buffers(cuda, name, prec):
     assert np.array_equal(posq_after[:n, 3].cpu().numpy(), st.charges)
     assert bool(torch.isfinite(velm_after).all()) and bool(torch.isfinite(posq_after).all())
     h.close()
+
+
+def test_system_without_drude_pairs(cuda):
+    """700 monatomic molecules, no Drude pair at all (a legal System: the DrudeForce is present but empty).  Every atom is
+    its own residue, so the relative groups have no degrees of freedom and the COM thermostat carries everything.  The
+    reference's Drude thermostat divides by its zero mass there (scale factor NaN, applied to nothing); this library
+    reports 1 (deviations)."""
+    ar = synth.Template("ar", np.array([39.948]), np.zeros((0, 2), np.int32), np.zeros((1, 3)))
+    s = synth.build([ar], np.zeros(700, np.int32), np.arange(700) % 2, 2, quantize_masses=True)
+    assert s.num_pairs == 0
+    st = DeviceState(s, cuda)
+    h = capi.Handle(s)
+    o = O.Oracle(s, O.TG)
+    p, v, f = s.positions.copy(), s.velocities.copy(), s.forces.copy()
+    h.step(*st.ptrs, nsteps=4)
+    o.step(p, v, f, 4)
+    assert rel_err(st.vel(), v) < 4 * TOL_STEP and rel_err(st.pos(), p) < TOL_STEP
+    np.testing.assert_allclose(h.vscale()[:3], o.vscale[:3], rtol=TOL_THERMO)
+    assert h.vscale()[3] == 1.0 and np.isnan(o.vscale[3])
+    np.testing.assert_allclose(h.kinetic_energies()[2], o.ke2[2], rtol=TOL_THERMO)
+    assert np.all(np.abs(h.kinetic_energies()[[0, 1, 3]]) <= 1e-7 * o.ke2[2])      # m|v|^2 - |P|^2/M with fp32 products: cancellation noise
+    h.close()
