@@ -147,14 +147,15 @@ struct tgnh_handle {
     unsigned int* dTicket = nullptr;
     ChainView chain{};
     size_t chainDoubles = 0;
-    int gridA = 0, gridB = 0, gridKE = 0, gridA1 = 0, gridA2 = 0;
-    int smemA = 0, smemB = 0, smemKE = 0, smemA1 = 0, smemA2 = 0;
+    int gridA = 0, gridB = 0, gridKE = 0, gridA1 = 0, gridA2 = 0, gridS = 0;
+    int smemA = 0, smemB = 0, smemKE = 0, smemA1 = 0, smemA2 = 0, smemS = 0;
     // host copies of the thermostat parameters
     std::vector<double> dof, nkbt, etaMass;
     // state machine
     bool keValid = false;         // chain.ke2 describes the velocities as stored
     bool scalePending = false;    // chain.pending != 1 has not been applied to velm yet
     int64_t launches = 0;
+    int nextReverse = 0;          // direction of the next streaming launch (alternates, see launch_stream)
     tgnh_comm* comm = nullptr;
     // sharded: kinetic-energy exchange through peer-mapped inboxes (NVLink); world <= 1 when NCCL carries it instead
     PeerInbox* dInbox = nullptr;
@@ -240,6 +241,7 @@ static StreamKernel pick3(bool useCOM, bool hardwall) {
     }
     if (KIND == KIND_A2) return hardwall ? tgnh_stream_kernel<KIND_A2, 0, false, true, PREC, false> : tgnh_stream_kernel<KIND_A2, 0, false, false, PREC, false>;
     if (KIND == KIND_KE) return useCOM ? tgnh_stream_kernel<KIND_KE, 0, true, false, PREC, BIG> : tgnh_stream_kernel<KIND_KE, 0, false, false, PREC, false>;
+    if (KIND == KIND_S) return useCOM ? tgnh_stream_kernel<KIND_S, 0, true, false, PREC, BIG> : tgnh_stream_kernel<KIND_S, 0, false, false, PREC, false>;
     return useCOM ? tgnh_stream_kernel<KIND, FFMT, true, false, PREC, BIG> : tgnh_stream_kernel<KIND, FFMT, false, false, PREC, false>;
 }
 
@@ -266,6 +268,7 @@ static StreamKernel pick(int kind, int ffmt, int prec, bool useCOM, bool hardwal
         case KIND_BU: return pick1<KIND_BU>(ffmt, prec, useCOM, hardwall, big);
         case KIND_A1: return pick1<KIND_A1>(ffmt, prec, useCOM, hardwall, big);
         case KIND_A2: return pick1<KIND_A2>(ffmt, prec, useCOM, hardwall, big);
+        case KIND_S: return pick1<KIND_S>(ffmt, prec, useCOM, hardwall, big);
         default: return pick1<KIND_KE>(ffmt, prec, useCOM, hardwall, big);
     }
 }
@@ -274,6 +277,7 @@ template <int KIND, int FFMT, int PREC>
 static int smem2(bool useCOM, int T) {
     if (KIND == KIND_A2) return SmemLayout<KIND_A2, 0, false, PREC>::bytes(T);
     if (KIND == KIND_KE) return useCOM ? SmemLayout<KIND_KE, 0, true, PREC>::bytes(T) : SmemLayout<KIND_KE, 0, false, PREC>::bytes(T);
+    if (KIND == KIND_S) return useCOM ? SmemLayout<KIND_S, 0, true, PREC>::bytes(T) : SmemLayout<KIND_S, 0, false, PREC>::bytes(T);
     return useCOM ? SmemLayout<KIND, FFMT, true, PREC>::bytes(T) : SmemLayout<KIND, FFMT, false, PREC>::bytes(T);
 }
 
@@ -292,6 +296,7 @@ static int smem_bytes(int kind, int ffmt, int prec, bool useCOM, int T) {
         case KIND_BU: return smem1<KIND_BU>(ffmt, prec, useCOM, T);
         case KIND_A1: return smem1<KIND_A1>(ffmt, prec, useCOM, T);
         case KIND_A2: return smem1<KIND_A2>(ffmt, prec, useCOM, T);
+        case KIND_S: return smem1<KIND_S>(ffmt, prec, useCOM, T);
         default: return smem1<KIND_KE>(ffmt, prec, useCOM, T);
     }
 }
@@ -589,7 +594,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
     int rc;
     if ((rc = configure_kernel(h, KIND_A, &h->gridA, &h->smemA)) || (rc = configure_kernel(h, h->kindB, &h->gridB, &h->smemB)) ||
         (rc = configure_kernel(h, KIND_KE, &h->gridKE, &h->smemKE)) || (rc = configure_kernel(h, KIND_A1, &h->gridA1, &h->smemA1)) ||
-        (rc = configure_kernel(h, KIND_A2, &h->gridA2, &h->smemA2)))
+        (rc = configure_kernel(h, KIND_A2, &h->gridA2, &h->smemA2)) || (rc = configure_kernel(h, KIND_S, &h->gridS, &h->smemS)))
         return bail(rc);
     int maxGrid = h->gridA > h->gridB ? h->gridA : h->gridB;
     if (h->gridKE > maxGrid) maxGrid = h->gridKE;
@@ -662,7 +667,8 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     a.resStart = h->dResStart; a.tileFirstRes = h->dTileFirstRes;
     a.bigFirst = h->dBigFirst; a.bigCom = h->dBigCom; a.numBig = h->numBig;
     const bool firstHalf = kind == KIND_A || kind == KIND_A1 || kind == KIND_A2;
-    const int prof = firstHalf ? KIND_A : kind;      // profiling slot (first half / second half / reduce)
+    const int prof = firstHalf ? KIND_A : kind == KIND_S ? KIND_KE : kind;      // profiling slot (first half / second half / reduce+scale)
+    const bool reduces = !firstHalf && kind != KIND_S;
     if (kind == KIND_B) kind = h->kindB;
     a.dt = h->dt;
     a.fscale = h->ffmt == TGNH_FORCE_I64_SOA ? 0.5 * h->dt / 4294967296.0 : 0.5 * h->dt;             // CudaDrudeTGNHKernels.cpp:295
@@ -670,18 +676,20 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     a.hardwallScale = std::sqrt(h->kTD);                                                              // :299
     a.applyScale = applyScale;
     a.useLocalKE = sharded(h) ? 1 : 0;
-    a.reverse = (prof == KIND_B) ? 1 : 0;   // first-half and reduce/flush launches walk forward, second-half backward
+    // L2 hand-over: every streaming launch walks the tiles in the direction opposite to the previous one, so it starts
+    // on what that launch wrote last (first half forward, second half backward, a scaling pass forward again, ...)
+    a.reverse = h->nextReverse;
+    h->nextReverse ^= 1;
     static const int tunePrefetch = getenv("TGNH_TUNE_PREFETCH") ? atoi(getenv("TGNH_TUNE_PREFETCH")) : 0;                  // experiments only
     a.prologuePrefetch = (prof == KIND_A) ? tunePrefetch : 0;
     static const int tuneReverse = getenv("TGNH_TUNE_REVERSE") ? atoi(getenv("TGNH_TUNE_REVERSE")) : -1;   // experiments only
     if (tuneReverse == 0) a.reverse = 0;
-    if (tuneReverse == 2) a.reverse = (prof == KIND_B) ? 0 : 1;
     a.partials = h->dPartials; a.ticket = h->dTicket; a.chain = h->chain;
     a.peers = h->peers;
-    const bool p2p = h->peers.world > 1 && prof != KIND_A;
+    const bool p2p = h->peers.world > 1 && reduces;
     if (p2p) a.peers.seq = ++h->reduceSeq; else a.peers.world = 0;
-    const int grid = kind == KIND_A1 ? h->gridA1 : kind == KIND_A2 ? h->gridA2 : prof == KIND_A ? h->gridA : prof == KIND_B ? h->gridB : h->gridKE;
-    const int smem = kind == KIND_A1 ? h->smemA1 : kind == KIND_A2 ? h->smemA2 : prof == KIND_A ? h->smemA : prof == KIND_B ? h->smemB : h->smemKE;
+    const int grid = kind == KIND_S ? h->gridS : kind == KIND_A1 ? h->gridA1 : kind == KIND_A2 ? h->gridA2 : prof == KIND_A ? h->gridA : prof == KIND_B ? h->gridB : h->gridKE;
+    const int smem = kind == KIND_S ? h->smemS : kind == KIND_A1 ? h->smemA1 : kind == KIND_A2 ? h->smemA2 : prof == KIND_A ? h->smemA : prof == KIND_B ? h->smemB : h->smemKE;
     StreamKernel k = pick(kind, h->ffmt, h->prec, h->useCOM, h->hardwall, h->numBig > 0);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
@@ -710,7 +718,7 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     CUDA_TRY(launch_pdl(k, grid, TILE, smem, s, (const StreamArgs)a));
     if (e1) CUDA_TRY(cudaEventRecord(e1, s));
     h->launches++;
-    if (prof == KIND_A) return TGNH_OK;
+    if (!reduces) return TGNH_OK;
     // the only exchange on the path: double[G+2] kinetic-energy partials.  Peer inboxes: published by the launch above,
     // gathered by the chain launch below (which therefore runs even without a chain update); otherwise an NCCL all-reduce
     if (p2p) return launch_chain(h, s, chainMode, true);
@@ -730,17 +738,20 @@ static int ensure_ke(tgnh_handle* h, cudaStream_t s, void* velm, int chainMode) 
 // apply chain.pending to velm (integrateDrudeTGNHChain) and refresh ke2 from the scaled velocities
 static int flush_scale(tgnh_handle* h, cudaStream_t s, void* velm) {
     if (!h->scalePending) return TGNH_OK;
+    if (h->uniformGroups) {
+        // residue-uniform groups: one scaling pass; the kernel also turns ke2 into s_g^2 ke2 and resets pending to 1
+        int rc = launch_stream(h, s, KIND_S, velm, nullptr, nullptr, 1, CHAIN_NONE);
+        if (rc) return rc;
+        h->scalePending = false;
+        h->keValid = true;
+        return TGNH_OK;
+    }
+    // residues that span temperature groups: COM velocities do not simply scale; apply, then recompute from scratch
     int rc = launch_stream(h, s, KIND_KE, velm, nullptr, nullptr, 1, CHAIN_NONE);
     if (rc) return rc;
-    // the kernel's last CTA resets pending to 1 (scaleA keeps the factors that were just applied)
-    h->scalePending = false;
-    h->keValid = true;
-    if (!h->uniformGroups) {
-        // residues that span temperature groups: COM velocities do not simply scale, recompute from scratch
-        h->keValid = false;
-        rc = ensure_ke(h, s, velm, CHAIN_NONE);
-    }
-    return rc;
+    h->scalePending = false;      // the kernel's last CTA resets pending to 1 (scaleA keeps the factors that were just applied)
+    h->keValid = false;
+    return ensure_ke(h, s, velm, CHAIN_NONE);
 }
 
 extern "C" int tgnh_half1(tgnh_handle* h, void* stream, void* velm, void* posq, const void* force) {

@@ -16,6 +16,10 @@
 //                            (drudeTGNH.cu:435-574)
 //   KIND_KE (reduce/flush) = the kinetic-energy reduction alone, optionally applying a pending scaling
 //                            (drudeTGNH.cu:82-242, 249-301)
+//   KIND_S  (scale)        = integrateDrudeTGNHChain alone (drudeTGNH.cu:249-301): applies the second thermostat half-step's
+//                            factors to velm right away, for callers whose other kernels (CMMotionRemover, barostat,
+//                            reporters) read velocities between steps; residue-uniform groups only, where the scaled
+//                            kinetic energies are s_g^2 KE_g and need no second reduction
 //
 // Data movement: every CTA is persistent and walks residue-aligned tiles of <= 512 consecutive
 // particles.  One elected thread streams each tile's velm / posq / force / descriptor slices into a
@@ -46,7 +50,7 @@
 
 namespace tgnh {
 
-enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2, KIND_BU = 3, KIND_A1 = 4, KIND_A2 = 5 };
+enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2, KIND_BU = 3, KIND_A1 = 4, KIND_A2 = 5, KIND_S = 6 };
 constexpr int NWARPS = TILE / 32;
 constexpr int TLIST_CAP = 128;     // tile bounds cached in shared memory per CTA (later tiles are looked up in global memory)
 
@@ -87,7 +91,7 @@ struct StreamArgs {
 template <int KIND, int FFMT, int PREC>
 struct StageLayout {
     static constexpr bool HAS_X = (KIND == KIND_A || KIND == KIND_A2);
-    static constexpr bool HAS_F = (KIND != KIND_KE && KIND != KIND_A2);
+    static constexpr bool HAS_F = (KIND != KIND_KE && KIND != KIND_A2 && KIND != KIND_S);
     static constexpr bool HAS_P = (KIND == KIND_A2);             // posDelta tile
     static constexpr bool HAS_R = (KIND == KIND_BU);
     static constexpr int FBYTES = FFMT == 1 ? 8 : 4;
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
     }
     __syncthreads();
 
-    const bool doScale = (KIND == KIND_A || KIND == KIND_A1) || (KIND == KIND_KE && a.applyScale);
+    const bool doScale = (KIND == KIND_A || KIND == KIND_A1 || KIND == KIND_S) || (KIND == KIND_KE && a.applyScale);
     const real eCOM = doScale ? (real)seps[G] : real(0);
     const real eDrude = doScale ? (real)seps[G + 1] : real(0);
     const real dt = (real)a.dt, fscale = (real)a.fscale, rmax = (real)a.rmax;
@@ -625,7 +629,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
             accCOM += keC;
         }
 
-        if (KIND == KIND_KE) {
+        if (KIND == KIND_KE || KIND == KIND_S) {
             if (doScale && active && massive) st_global(gvelm + start + tid, pack4(vn, w));
         } else if (KIND == KIND_A1) {
             // scaling + half kick; posDelta = dt * v for OpenMM's constraint kernels (drudeTGNH.cu:322-324, 360-363)
@@ -696,6 +700,12 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
         }
     }
     pdl_launch_dependents();
+    if (KIND == KIND_S && blockIdx.x == 0 && tid < T) {
+        // the factors are applied: the kinetic energies of the stored velocities are s_g^2 KE_g (residue-uniform groups)
+        const double sg = a.chain.scaleA[tid];
+        a.chain.ke2[tid] *= sg * sg;
+        a.chain.pending[tid] = 1.0;
+    }
     if (!L::HAS_KE) return;
 
     // ---- deterministic reduction: thread columns -> warp -> CTA -> (last CTA) grid ----
