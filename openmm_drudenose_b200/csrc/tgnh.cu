@@ -147,8 +147,9 @@ struct tgnh_handle {
     unsigned int* dTicket = nullptr;
     ChainView chain{};
     size_t chainDoubles = 0;
-    int gridA = 0, gridB = 0, gridKE = 0, gridA1 = 0, gridA2 = 0, gridS = 0;
-    int smemA = 0, smemB = 0, smemKE = 0, smemA1 = 0, smemA2 = 0, smemS = 0;
+    int gridA = 0, gridB = 0, gridKE = 0, gridA1 = 0, gridA2 = 0, gridS = 0, gridK = 0;
+    int smemA = 0, smemB = 0, smemKE = 0, smemA1 = 0, smemA2 = 0, smemS = 0, smemK = 0;
+    int kindKE = KIND_KE;         // KIND_KU when every residue lies in one temperature group
     // host copies of the thermostat parameters
     std::vector<double> dof, nkbt, etaMass;
     // state machine
@@ -242,6 +243,8 @@ static StreamKernel pick3(bool useCOM, bool hardwall) {
     if (KIND == KIND_A2) return hardwall ? tgnh_stream_kernel<KIND_A2, 0, false, true, PREC, false> : tgnh_stream_kernel<KIND_A2, 0, false, false, PREC, false>;
     if (KIND == KIND_KE) return useCOM ? tgnh_stream_kernel<KIND_KE, 0, true, false, PREC, BIG> : tgnh_stream_kernel<KIND_KE, 0, false, false, PREC, false>;
     if (KIND == KIND_S) return useCOM ? tgnh_stream_kernel<KIND_S, 0, true, false, PREC, BIG> : tgnh_stream_kernel<KIND_S, 0, false, false, PREC, false>;
+    if (KIND == KIND_KU) return useCOM ? tgnh_stream_kernel<KIND_KU, 0, true, false, PREC, BIG> : tgnh_stream_kernel<KIND_KU, 0, false, false, PREC, false>;
+    if (KIND == KIND_K) return tgnh_stream_kernel<KIND_K, FFMT, false, false, PREC, false>;
     return useCOM ? tgnh_stream_kernel<KIND, FFMT, true, false, PREC, BIG> : tgnh_stream_kernel<KIND, FFMT, false, false, PREC, false>;
 }
 
@@ -269,6 +272,8 @@ static StreamKernel pick(int kind, int ffmt, int prec, bool useCOM, bool hardwal
         case KIND_A1: return pick1<KIND_A1>(ffmt, prec, useCOM, hardwall, big);
         case KIND_A2: return pick1<KIND_A2>(ffmt, prec, useCOM, hardwall, big);
         case KIND_S: return pick1<KIND_S>(ffmt, prec, useCOM, hardwall, big);
+        case KIND_K: return pick1<KIND_K>(ffmt, prec, useCOM, hardwall, big);
+        case KIND_KU: return pick1<KIND_KU>(ffmt, prec, useCOM, hardwall, big);
         default: return pick1<KIND_KE>(ffmt, prec, useCOM, hardwall, big);
     }
 }
@@ -278,6 +283,8 @@ static int smem2(bool useCOM, int T) {
     if (KIND == KIND_A2) return SmemLayout<KIND_A2, 0, false, PREC>::bytes(T);
     if (KIND == KIND_KE) return useCOM ? SmemLayout<KIND_KE, 0, true, PREC>::bytes(T) : SmemLayout<KIND_KE, 0, false, PREC>::bytes(T);
     if (KIND == KIND_S) return useCOM ? SmemLayout<KIND_S, 0, true, PREC>::bytes(T) : SmemLayout<KIND_S, 0, false, PREC>::bytes(T);
+    if (KIND == KIND_KU) return useCOM ? SmemLayout<KIND_KU, 0, true, PREC>::bytes(T) : SmemLayout<KIND_KU, 0, false, PREC>::bytes(T);
+    if (KIND == KIND_K) return SmemLayout<KIND_K, FFMT, false, PREC>::bytes(T);
     return useCOM ? SmemLayout<KIND, FFMT, true, PREC>::bytes(T) : SmemLayout<KIND, FFMT, false, PREC>::bytes(T);
 }
 
@@ -297,6 +304,8 @@ static int smem_bytes(int kind, int ffmt, int prec, bool useCOM, int T) {
         case KIND_A1: return smem1<KIND_A1>(ffmt, prec, useCOM, T);
         case KIND_A2: return smem1<KIND_A2>(ffmt, prec, useCOM, T);
         case KIND_S: return smem1<KIND_S>(ffmt, prec, useCOM, T);
+        case KIND_K: return smem1<KIND_K>(ffmt, prec, useCOM, T);
+        case KIND_KU: return smem1<KIND_KU>(ffmt, prec, useCOM, T);
         default: return smem1<KIND_KE>(ffmt, prec, useCOM, T);
     }
 }
@@ -540,6 +549,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         while (resStart.size() & 3) resStart.push_back(N);
     }
     h->kindB = uniform ? KIND_BU : KIND_B;
+    h->kindKE = uniform ? KIND_KU : KIND_KE;
 
     // ---- device allocations ----
     auto dmalloc = [&](void** ptr, size_t bytes) { return cudaMalloc(ptr, bytes ? bytes : 16) == cudaSuccess; };
@@ -593,7 +603,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
 
     int rc;
     if ((rc = configure_kernel(h, KIND_A, &h->gridA, &h->smemA)) || (rc = configure_kernel(h, h->kindB, &h->gridB, &h->smemB)) ||
-        (rc = configure_kernel(h, KIND_KE, &h->gridKE, &h->smemKE)) || (rc = configure_kernel(h, KIND_A1, &h->gridA1, &h->smemA1)) ||
+        (rc = configure_kernel(h, h->kindKE, &h->gridKE, &h->smemKE)) || (rc = configure_kernel(h, KIND_K, &h->gridK, &h->smemK)) || (rc = configure_kernel(h, KIND_A1, &h->gridA1, &h->smemA1)) ||
         (rc = configure_kernel(h, KIND_A2, &h->gridA2, &h->smemA2)) || (rc = configure_kernel(h, KIND_S, &h->gridS, &h->smemS)))
         return bail(rc);
     int maxGrid = h->gridA > h->gridB ? h->gridA : h->gridB;
@@ -667,8 +677,9 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     a.resStart = h->dResStart; a.tileFirstRes = h->dTileFirstRes;
     a.bigFirst = h->dBigFirst; a.bigCom = h->dBigCom; a.numBig = h->numBig;
     const bool firstHalf = kind == KIND_A || kind == KIND_A1 || kind == KIND_A2;
-    const int prof = firstHalf ? KIND_A : kind == KIND_S ? KIND_KE : kind;      // profiling slot (first half / second half / reduce+scale)
-    const bool reduces = !firstHalf && kind != KIND_S;
+    const int prof = firstHalf ? KIND_A : (kind == KIND_S || kind == KIND_KE) ? KIND_KE : KIND_B;      // profiling slot (first half / second half / reduce+scale)
+    const bool reduces = !firstHalf && kind != KIND_S && kind != KIND_K;
+    if (kind == KIND_KE && applyScale == 0) kind = h->kindKE;
     if (kind == KIND_B) kind = h->kindB;
     a.dt = h->dt;
     a.fscale = h->ffmt == TGNH_FORCE_I64_SOA ? 0.5 * h->dt / 4294967296.0 : 0.5 * h->dt;             // CudaDrudeTGNHKernels.cpp:295
@@ -688,8 +699,8 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     a.peers = h->peers;
     const bool p2p = h->peers.world > 1 && reduces;
     if (p2p) a.peers.seq = ++h->reduceSeq; else a.peers.world = 0;
-    const int grid = kind == KIND_S ? h->gridS : kind == KIND_A1 ? h->gridA1 : kind == KIND_A2 ? h->gridA2 : prof == KIND_A ? h->gridA : prof == KIND_B ? h->gridB : h->gridKE;
-    const int smem = kind == KIND_S ? h->smemS : kind == KIND_A1 ? h->smemA1 : kind == KIND_A2 ? h->smemA2 : prof == KIND_A ? h->smemA : prof == KIND_B ? h->smemB : h->smemKE;
+    const int grid = kind == KIND_K ? h->gridK : kind == KIND_S ? h->gridS : kind == KIND_A1 ? h->gridA1 : kind == KIND_A2 ? h->gridA2 : prof == KIND_A ? h->gridA : prof == KIND_B ? h->gridB : h->gridKE;
+    const int smem = kind == KIND_K ? h->smemK : kind == KIND_S ? h->smemS : kind == KIND_A1 ? h->smemA1 : kind == KIND_A2 ? h->smemA2 : prof == KIND_A ? h->smemA : prof == KIND_B ? h->smemB : h->smemKE;
     StreamKernel k = pick(kind, h->ffmt, h->prec, h->useCOM, h->hardwall, h->numBig > 0);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
@@ -705,7 +716,7 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
         h->evUsed += 2;
         CUDA_TRY(cudaEventRecord(e0, s));
     }
-    if (h->numBig && h->useCOM && kind != KIND_A2) {
+    if (h->numBig && h->useCOM && kind != KIND_A2 && kind != KIND_K) {
         // residues that do not fit a tile: their COM velocity (as this launch will see / store the velocities) first
         BigComArgs b;
         b.velm = velm; b.force = force; b.bigFirst = h->dBigFirst; b.bigLast = h->dBigLast; b.bigCom = h->dBigCom; b.paddedN = h->paddedN;
@@ -800,7 +811,7 @@ extern "C" int tgnh_half2(tgnh_handle* h, void* stream, void* velm, const void* 
     if (flags & TGNH_HALF2_KICK_ONLY) {
         // constrained systems: OpenMM's velocity constraints (:391) come between the kick and the thermostat half-step;
         // the kinetic energies this launch reduces are discarded and tgnh_thermostat recomputes them
-        if (int rc = launch_stream(h, s, KIND_B, velm, nullptr, force, 0, CHAIN_NONE)) return rc;
+        if (int rc = launch_stream(h, s, KIND_K, velm, nullptr, force, 0, CHAIN_NONE)) return rc;
         h->keValid = false;
         return TGNH_OK;
     }

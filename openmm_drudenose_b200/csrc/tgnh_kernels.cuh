@@ -16,6 +16,9 @@
 //                            (drudeTGNH.cu:435-574)
 //   KIND_KE (reduce/flush) = the kinetic-energy reduction alone, optionally applying a pending scaling
 //                            (drudeTGNH.cu:82-242, 249-301)
+//   KIND_K  (kick)         = integrateDrudeTGNHVelocities alone (drudeTGNH.cu:307-365): the second half kick of constrained
+//                            systems, whose energies are reduced only after OpenMM's velocity constraints
+//   KIND_KU                = KIND_KE for residue-uniform groups, in the lab-frame form of KIND_BU (no kick, no store)
 //   KIND_S  (scale)        = integrateDrudeTGNHChain alone (drudeTGNH.cu:249-301): applies the second thermostat half-step's
 //                            factors to velm right away, for callers whose other kernels (CMMotionRemover, barostat,
 //                            reporters) read velocities between steps; residue-uniform groups only, where the scaled
@@ -50,7 +53,7 @@
 
 namespace tgnh {
 
-enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2, KIND_BU = 3, KIND_A1 = 4, KIND_A2 = 5, KIND_S = 6 };
+enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2, KIND_BU = 3, KIND_A1 = 4, KIND_A2 = 5, KIND_S = 6, KIND_K = 7, KIND_KU = 8 };
 constexpr int NWARPS = TILE / 32;
 constexpr int TLIST_CAP = 128;     // tile bounds cached in shared memory per CTA (later tiles are looked up in global memory)
 
@@ -91,9 +94,9 @@ struct StreamArgs {
 template <int KIND, int FFMT, int PREC>
 struct StageLayout {
     static constexpr bool HAS_X = (KIND == KIND_A || KIND == KIND_A2);
-    static constexpr bool HAS_F = (KIND != KIND_KE && KIND != KIND_A2 && KIND != KIND_S);
+    static constexpr bool HAS_F = (KIND != KIND_KE && KIND != KIND_A2 && KIND != KIND_S && KIND != KIND_KU);
     static constexpr bool HAS_P = (KIND == KIND_A2);             // posDelta tile
-    static constexpr bool HAS_R = (KIND == KIND_BU);
+    static constexpr bool HAS_R = (KIND == KIND_BU || KIND == KIND_KU);
     static constexpr int FBYTES = FFMT == 1 ? 8 : 4;
     static constexpr int VB = PREC ? 32 : 16;                    // bytes of one velm / posDelta element
     static constexpr int OFF_V = 0;
@@ -111,7 +114,7 @@ struct StageLayout {
 template <int KIND, int FFMT, bool USE_COM, int PREC>
 struct SmemLayout {
     using Stage = StageLayout<KIND, FFMT, PREC>;
-    static constexpr bool HAS_KE = (KIND == KIND_B || KIND == KIND_BU || KIND == KIND_KE);
+    static constexpr bool HAS_KE = (KIND == KIND_B || KIND == KIND_BU || KIND == KIND_KE || KIND == KIND_KU);
     static constexpr int NSTAGE = (KIND == KIND_A || KIND == KIND_A2) ? 3 : 4;
     static constexpr int OFF_BAR = NSTAGE * Stage::BYTES;         // full[NS], empty[NS] mbarriers
     static constexpr int OFF_TLIST = OFF_BAR + 128;               // int4[TLIST_CAP] bounds of this CTA's first tiles
@@ -448,7 +451,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
     if (tid == 0)
         for (int it = 0; it < NS && it < myTiles; it++) issue(it, 2);
     if (tid < T) {
-        const double sg = (KIND == KIND_B || KIND == KIND_BU || KIND == KIND_A2) ? 1.0 : a.chain.scaleA[tid];
+        const double sg = (KIND == KIND_B || KIND == KIND_BU || KIND == KIND_A2 || KIND == KIND_K || KIND == KIND_KU) ? 1.0 : a.chain.scaleA[tid];
         ssq[tid] = sg * sg;
         seps[tid] = sg - 1.0;
     }
@@ -507,14 +510,15 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
         double keC = 0.0;                             // M |V|^2 of this particle's residue (kinds that reduce energies)
         bool firstOfRes = desc_off_first(d) == 0;       // the residue's first particle carries M |V|^2
         const bool big = BIG && desc_big(d);            // BIG: the system has residues larger than a tile (separate instantiation)
-        if (USE_COM && active && KIND != KIND_A2 && big) {
+        constexpr bool LAB = (KIND == KIND_BU || KIND == KIND_KU);      // lab-frame energies, M |V|^2 per residue subtracted
+        if (USE_COM && active && KIND != KIND_A2 && KIND != KIND_K && big) {
             // big residue (a protein, a polymer): V and M from the pre-pass table (tgnh_bigcom_kernel)
             const int b = big_index(a.bigFirst, a.numBig, start + tid);
             const double4 c = a.bigCom[b];
             V = v3((real)c.x, (real)c.y, (real)c.z);
             firstOfRes = a.bigFirst[b] == start + tid;
             keC = c.w * (c.x * c.x + c.y * c.y + c.z * c.z);
-        } else if (USE_COM && active && KIND != KIND_BU && KIND != KIND_A2) {
+        } else if (USE_COM && active && !LAB && KIND != KIND_A2 && KIND != KIND_K) {
             const int j0 = tid - desc_off_first(d), j1 = tid + desc_off_last(d);
             if (!L::HAS_KE && !PREC) {
                 // first half, fp32 layout: V only feeds the small corrections (sT-1)(v - V) and (sCOM-1) V, fp32 sums are ample
@@ -549,10 +553,15 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
 
         R3 vn;                                        // this particle's new velocity
         R3 r;                                         // ... relative to the residue (after scaling / kick)
-        if (KIND == KIND_BU) {
-            // kick (drudeTGNH.cu:314-364); kinetic energies in the lab frame, the residues' M |V|^2 is removed below
-            vn = kicked(v, fw, F);
+        if (KIND == KIND_K) {
+            vn = kicked(v, fw, F);                     // drudeTGNH.cu:314-364
             if (active && massive) st_global(gvelm + start + tid, pack4(vn, w));
+            r = vn;
+        } else if (LAB) {
+            // kick (drudeTGNH.cu:314-364; KIND_KU: F = 0, nothing stored); kinetic energies in the lab frame, the residues'
+            // M |V|^2 is removed below
+            vn = kicked(v, fw, F);
+            if (KIND == KIND_BU && active && massive) st_global(gvelm + start + tid, pack4(vn, w));
             const R3 vjn = kicked(vj, fwj, Fj);
             rel = vjn - vn;
             r = vn;
@@ -576,7 +585,8 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
                     const bool mass = q.w != real(0);
                     const real mq = mass ? rcp_fast(q.w) : real(0);
                     const double mqd = mass ? mass_d(q.w, mq) : 0.0;
-                    const R3 vq = kicked(xyz(q), fscale * q.w, load_force3<FFMT, real>(sF, fo + j));   // what member j stores
+                    R3 vq = xyz(q);
+                    if (St::HAS_F) vq = kicked(vq, fscale * q.w, load_force3<FFMT, real>(sF, fo + j));   // what member j stores
                     P = axpy(mqd, to_double(vq), P);
                     M += mqd;
                 }
@@ -596,7 +606,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
             vn = scaled_velocity(v, eT, r, eCOM, V, coef * fj, rel);
         }
 
-        if (KIND == KIND_BU) {
+        if (LAB) {
             // computeNormalizedKineticEnergies (drudeTGNH.cu:152-188) for residue-uniform groups, without the pair transform:
             // M_p |v_cm|^2 + mu |rel|^2 = m_i |v_i|^2 + m_j |v_j|^2 for a Drude pair, so EVERY particle adds its own
             // m |v|^2 to its group and only the Drude particle moves the pair's internal term mu |rel|^2 from the group
@@ -622,7 +632,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
             const double s2T = doScale ? ssq[tg] : 1.0, s2D = doScale ? ssq[G + 1] : 1.0, s2C = doScale ? ssq[G] : 1.0;
             const double keT = massT * s2T * (double)dot3(cm);
             const double keD = isDrude ? md * mjd * rcp_d(Mp, (float)invTot) * s2D * (double)dot3(rel) : 0.0;   // reduced mass
-            if (!(USE_COM && KIND != KIND_BU && active && firstOfRes)) keC = 0.0;        // the residue's first particle carries M |V|^2
+            if (!(USE_COM && !LAB && active && firstOfRes)) keC = 0.0;        // the residue's first particle carries M |V|^2
             keC *= s2C;
             if (active && massT != 0.0) ske[tg * TILE + tid] += keT;
             accDrude += keD;
