@@ -84,6 +84,7 @@ void B200IntegrateDrudeTGNHStepKernel::execute(ContextImpl& context, const Drude
     const TgnhDeviceView dv = device.view();
     const double tol = integrator.getConstraintTolerance();
     if (dv.precision == TGNH_PRECISION_MIXED) check(tgnh_set_posq_correction(handle, dv.posqCorrection));
+    if (recomputeKE && !deferScale) check(tgnh_invalidate(handle));     // reference semantics: energies from velm, every step (:336)
     if (!constrained) {
         // thermostat half-step, half kick, drift, hard wall in one launch (:336-376)
         check(tgnh_half1(handle, dv.stream, dv.velm, dv.posq, dv.force));

@@ -42,7 +42,7 @@ public:
 class B200IntegrateDrudeTGNHStepKernel : public IntegrateDrudeTGNHStepKernel {
 public:
     B200IntegrateDrudeTGNHStepKernel(std::string name, const Platform& platform, TgnhDeviceAccess& device)
-        : IntegrateDrudeTGNHStepKernel(name, platform), device(device), handle(NULL), deferScale(false), constrained(false) {}
+        : IntegrateDrudeTGNHStepKernel(name, platform), device(device), handle(NULL), deferScale(false), recomputeKE(false), constrained(false) {}
     ~B200IntegrateDrudeTGNHStepKernel();
     void initialize(const System& system, const DrudeTGNHIntegrator& integrator, const DrudeForce& force);
     void execute(ContextImpl& context, const DrudeTGNHIntegrator& integrator);
@@ -55,11 +55,17 @@ public:
     /** Leave the second half-step's scaling pending between the steps of one step(n) call.  Only safe when nothing else
      *  (barostat, CMMotionRemover, reporters) touches velocities between steps; off by default. */
     void setDeferScaling(bool on) { deferScale = on; }
+    /** Recompute the kinetic energies from velm at the start of every step, as the reference does, instead of carrying
+     *  them over from the end of the previous step.  Needed only when something rewrites velocities between steps without
+     *  going through Context::setVelocities (an AndersenThermostat; CMMotionRemover's correction is at rounding level once
+     *  the total momentum has been removed).  Costs one extra pass over velm per step; off by default. */
+    void setRecomputeKineticEnergies(bool on) { recomputeKE = on; }
 private:
     void check(int rc) const;
     TgnhDeviceAccess& device;
     tgnh_handle* handle;
     bool deferScale;
+    bool recomputeKE;
     bool constrained;    // the System has constraints: the split call sequence leaves room for OpenMM's constraint kernels
 };
 
