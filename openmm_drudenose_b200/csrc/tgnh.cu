@@ -236,16 +236,18 @@ static int setup_peers(tgnh_handle* h) {
 
 template <int KIND, int FFMT, int PREC, bool BIG>
 static StreamKernel pick3(bool useCOM, bool hardwall) {
-    if (KIND == KIND_A) {   // only the kernels that move positions contain the hard wall
+    if constexpr (KIND == KIND_A) {   // only the kernels that move positions contain the hard wall
         if (useCOM) return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, true, true, PREC, BIG> : tgnh_stream_kernel<KIND_A, FFMT, true, false, PREC, BIG>;
         return hardwall ? tgnh_stream_kernel<KIND_A, FFMT, false, true, PREC, false> : tgnh_stream_kernel<KIND_A, FFMT, false, false, PREC, false>;
+    } else if constexpr (KIND == KIND_A2) {
+        return hardwall ? tgnh_stream_kernel<KIND_A2, 0, false, true, PREC, false> : tgnh_stream_kernel<KIND_A2, 0, false, false, PREC, false>;
+    } else if constexpr (KIND == KIND_KE || KIND == KIND_S || KIND == KIND_KU) {      // no forces: one force format
+        return useCOM ? tgnh_stream_kernel<KIND, 0, true, false, PREC, BIG> : tgnh_stream_kernel<KIND, 0, false, false, PREC, false>;
+    } else if constexpr (KIND == KIND_K) {
+        return tgnh_stream_kernel<KIND_K, FFMT, false, false, PREC, false>;
+    } else {
+        return useCOM ? tgnh_stream_kernel<KIND, FFMT, true, false, PREC, BIG> : tgnh_stream_kernel<KIND, FFMT, false, false, PREC, false>;
     }
-    if (KIND == KIND_A2) return hardwall ? tgnh_stream_kernel<KIND_A2, 0, false, true, PREC, false> : tgnh_stream_kernel<KIND_A2, 0, false, false, PREC, false>;
-    if (KIND == KIND_KE) return useCOM ? tgnh_stream_kernel<KIND_KE, 0, true, false, PREC, BIG> : tgnh_stream_kernel<KIND_KE, 0, false, false, PREC, false>;
-    if (KIND == KIND_S) return useCOM ? tgnh_stream_kernel<KIND_S, 0, true, false, PREC, BIG> : tgnh_stream_kernel<KIND_S, 0, false, false, PREC, false>;
-    if (KIND == KIND_KU) return useCOM ? tgnh_stream_kernel<KIND_KU, 0, true, false, PREC, BIG> : tgnh_stream_kernel<KIND_KU, 0, false, false, PREC, false>;
-    if (KIND == KIND_K) return tgnh_stream_kernel<KIND_K, FFMT, false, false, PREC, false>;
-    return useCOM ? tgnh_stream_kernel<KIND, FFMT, true, false, PREC, BIG> : tgnh_stream_kernel<KIND, FFMT, false, false, PREC, false>;
 }
 
 // residues larger than a tile only matter to kernels that use the residues' COM velocity (USE_COM)
