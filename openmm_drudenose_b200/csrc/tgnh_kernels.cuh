@@ -463,6 +463,8 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
     const real dt = (real)a.dt, fscale = (real)a.fscale, rmax = (real)a.rmax;
     const real rmax2 = rmax * rmax;
     double accCOM = 0.0, accDrude = 0.0;               // this thread's share of the COM-group and Drude-group sums
+    double accT = 0.0;                                 // ... and of the group curTg its recent particles belong to (lab-frame kinds)
+    int curTg = -1;
 
     for (int it = 0; it < myTiles; it++) {
         const int stg = it % NS;
@@ -620,7 +622,16 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
                 ke -= keD;
                 accDrude += keD;
             }
-            if (active && massive) ske[tg * TILE + tid] += ke;
+            // this thread's particles usually stay in one group from tile to tile (molecule-periodic group patterns): the
+            // running sum lives in a register and moves to its shared-memory column only when the group changes
+            if (active && massive) {
+                if (tg != curTg) {
+                    if (curTg >= 0) ske[curTg * TILE + tid] += accT;
+                    accT = 0.0;
+                    curTg = tg;
+                }
+                accT += ke;
+            }
         } else if (L::HAS_KE) {
             // computeNormalizedKineticEnergies (drudeTGNH.cu:152-188), branch-free: an ordinary particle is its own
             // "pair centre of mass" (rel = 0); the Drude particle of a pair carries the pair's two terms
@@ -719,6 +730,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
     if (!L::HAS_KE) return;
 
     // ---- deterministic reduction: thread columns -> warp -> CTA -> (last CTA) grid ----
+    if (curTg >= 0) ske[curTg * TILE + tid] += accT;
     ske[G * TILE + tid] += accCOM;
     ske[(G + 1) * TILE + tid] += accDrude;
     for (int g = 0; g < T; g++) {
