@@ -55,7 +55,7 @@ namespace tgnh {
 
 enum { KIND_A = 0, KIND_B = 1, KIND_KE = 2, KIND_BU = 3, KIND_A1 = 4, KIND_A2 = 5, KIND_S = 6, KIND_K = 7, KIND_KU = 8 };
 constexpr int NWARPS = TILE / 32;
-constexpr int TLIST_CAP = 128;     // tile bounds cached in shared memory per CTA (later tiles are looked up in global memory)
+constexpr int TLIST_CAP = 256;     // tile bounds cached in shared memory per CTA (later tiles are looked up in global memory)
 
 template <int PREC> struct Prec;
 template <> struct Prec<0> { typedef float real; typedef float4 real4; };
