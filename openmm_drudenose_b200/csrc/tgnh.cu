@@ -150,6 +150,7 @@ struct tgnh_handle {
     int gridA = 0, gridB = 0, gridKE = 0, gridA1 = 0, gridA2 = 0, gridS = 0, gridK = 0;
     int smemA = 0, smemB = 0, smemKE = 0, smemA1 = 0, smemA2 = 0, smemS = 0, smemK = 0;
     int kindKE = KIND_KE;         // KIND_KU when every residue lies in one temperature group
+    bool fuseChain = false;       // small system: reducing launches run the chain update in their last CTA
     // host copies of the thermostat parameters
     std::vector<double> dof, nkbt, etaMass;
     // state machine
@@ -277,6 +278,21 @@ static StreamKernel pick(int kind, int ffmt, int prec, bool useCOM, bool hardwal
         case KIND_K: return pick1<KIND_K>(ffmt, prec, useCOM, hardwall, big);
         case KIND_KU: return pick1<KIND_KU>(ffmt, prec, useCOM, hardwall, big);
         default: return pick1<KIND_KE>(ffmt, prec, useCOM, hardwall, big);
+    }
+}
+
+// small systems: the reducing launch runs the chain update in its last CTA (tgnh_stream_chain_kernel)
+template <int KIND, int FFMT>
+static StreamKernel pick_fused2(int prec, bool useCOM) {
+    if (prec) return useCOM ? tgnh_stream_chain_kernel<KIND, FFMT, true, 1> : tgnh_stream_chain_kernel<KIND, FFMT, false, 1>;
+    return useCOM ? tgnh_stream_chain_kernel<KIND, FFMT, true, 0> : tgnh_stream_chain_kernel<KIND, FFMT, false, 0>;
+}
+static StreamKernel pick_fused(int kind, int ffmt, int prec, bool useCOM) {
+    switch (kind) {
+        case KIND_B: return ffmt ? pick_fused2<KIND_B, 1>(prec, useCOM) : pick_fused2<KIND_B, 0>(prec, useCOM);
+        case KIND_BU: return ffmt ? pick_fused2<KIND_BU, 1>(prec, useCOM) : pick_fused2<KIND_BU, 0>(prec, useCOM);
+        case KIND_KU: return pick_fused2<KIND_KU, 0>(prec, useCOM);
+        default: return pick_fused2<KIND_KE, 0>(prec, useCOM);
     }
 }
 
@@ -608,6 +624,20 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         (rc = configure_kernel(h, h->kindKE, &h->gridKE, &h->smemKE)) || (rc = configure_kernel(h, KIND_K, &h->gridK, &h->smemK)) || (rc = configure_kernel(h, KIND_A1, &h->gridA1, &h->smemA1)) ||
         (rc = configure_kernel(h, KIND_A2, &h->gridA2, &h->smemA2)) || (rc = configure_kernel(h, KIND_S, &h->gridS, &h->smemS)))
         return bail(rc);
+    {
+        // small systems (one tile per SM at most, nothing sharded, no big residues): chain update inside the reducing launch
+        const char* e = getenv("TGNH_FUSE_CHAIN");
+        h->fuseChain = h->numTiles <= h->numSMs && h->numBig == 0 && !(h->comm && h->comm->worldSize > 1) && !(e && atoi(e) == 0);
+        if (h->fuseChain)
+            for (int kind : {h->kindB, h->kindKE}) {
+                StreamKernel k = pick_fused(kind, h->ffmt, h->prec, h->useCOM);
+                const int smem = smem_bytes(kind, h->ffmt, h->prec, h->useCOM, h->T);
+                if (cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    h->fuseChain = false;
+                }
+            }
+    }
     int maxGrid = h->gridA > h->gridB ? h->gridA : h->gridB;
     if (h->gridKE > maxGrid) maxGrid = h->gridKE;
     if (h->gridA1 > maxGrid) maxGrid = h->gridA1;
@@ -728,10 +758,13 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
         CUDA_TRY(launch_pdl(bk, h->numBig, 256, 0, s, (const BigComArgs)b));
         h->launches++;
     }
-    CUDA_TRY(launch_pdl(k, grid, TILE, smem, s, (const StreamArgs)a));
+    const bool fused = h->fuseChain && reduces && chainMode != CHAIN_NONE && (kind == h->kindB || (kind == h->kindKE && !applyScale));
+    a.fusedChainMode = fused ? chainMode : CHAIN_NONE;
+    if (fused) CUDA_TRY(launch_pdl(pick_fused(kind, h->ffmt, h->prec, h->useCOM), h->numTiles, TILE, smem, s, (const StreamArgs)a));
+    else CUDA_TRY(launch_pdl(k, grid, TILE, smem, s, (const StreamArgs)a));
     if (e1) CUDA_TRY(cudaEventRecord(e1, s));
     h->launches++;
-    if (!reduces) return TGNH_OK;
+    if (!reduces || fused) return TGNH_OK;
     // the only exchange on the path: double[G+2] kinetic-energy partials.  Peer inboxes: published by the launch above,
     // gathered by the chain launch below (which therefore runs even without a chain update); otherwise an NCCL all-reduce
     if (p2p) return launch_chain(h, s, chainMode, true);

@@ -85,6 +85,7 @@ struct StreamArgs {
     int useLocalKE;           // sharded: reduce into chain.ke2Local (all-reduced into ke2 afterwards)
     int reverse;              // walk the tiles from the last to the first (see "L2 hand-over" below)
     int prologuePrefetch;     // tiles per CTA whose read-only inputs are prefetched into L2 before griddepcontrol.wait
+    int fusedChainMode;       // tgnh_stream_chain_kernel: the chain update the last CTA runs (ChainMode)
     double* partials;         // [gridDim.x][T]
     unsigned int* ticket;     // last-CTA-done counter (self-resetting)
     ChainView chain;
@@ -352,8 +353,9 @@ __global__ void __launch_bounds__(256) tgnh_bigcom_kernel(const __grid_constant_
 // previous launch wrote is still resident: those reads never reach HBM and the dirty lines are overwritten in
 // L2 before they are evicted.  velm stores therefore use the default L2 policy while everything that is touched
 // once per step (posq, forces, descriptors) is loaded evict-first / stored streaming.
+// Body of every streaming kernel.  Returns true in the one CTA that finished the grid-wide energy reduction (all threads of it).
 template <int KIND, int FFMT, bool USE_COM, bool HARDWALL, int PREC, bool BIG>
-__global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const __grid_constant__ StreamArgs a) {
+__device__ __forceinline__ bool stream_body(const StreamArgs& a) {
     using L = SmemLayout<KIND, FFMT, USE_COM, PREC>;
     using St = typename L::Stage;
     using real = typename Prec<PREC>::real;
@@ -727,7 +729,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
         a.chain.ke2[tid] *= sg * sg;
         a.chain.pending[tid] = 1.0;
     }
-    if (!L::HAS_KE) return;
+    if (!L::HAS_KE) return false;
 
     // ---- deterministic reduction: thread columns -> warp -> CTA -> (last CTA) grid ----
     if (curTg >= 0) ske[curTg * TILE + tid] += accT;
@@ -752,7 +754,7 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
         smisc[0] = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (!smisc[0]) return;
+    if (!smisc[0]) return false;
     __threadfence();
     // last CTA: warp g sums column g of the partials over all CTAs in a fixed order
     double* out = a.useLocalKE ? a.chain.ke2Local : a.chain.ke2;
@@ -770,6 +772,22 @@ __global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const _
     }
     if (tid == 0) *a.ticket = 0u;
     if (KIND == KIND_KE && a.applyScale && tid < T) a.chain.pending[tid] = 1.0;   // the deferred scaling is now applied
+    return true;
+}
+
+template <int KIND, int FFMT, bool USE_COM, bool HARDWALL, int PREC, bool BIG>
+__global__ void __launch_bounds__(TILE, PREC ? 1 : 2) tgnh_stream_kernel(const __grid_constant__ StreamArgs a) {
+    stream_body<KIND, FFMT, USE_COM, HARDWALL, PREC, BIG>(a);
+}
+
+// Small systems (every CTA owns at most one tile; launch hand-over, not bandwidth, sets the step time): the CTA that
+// finishes the energy reduction runs the Nose-Hoover chain update itself instead of a separate chain launch.  One CTA per
+// SM: the chain needs more registers than the streaming body and occupancy is irrelevant at this size.
+template <int KIND, int FFMT, bool USE_COM, int PREC>
+__global__ void __launch_bounds__(TILE, 1) tgnh_stream_chain_kernel(const __grid_constant__ StreamArgs a) {
+    if (!stream_body<KIND, FFMT, USE_COM, false, PREC, false>(a)) return;
+    __syncthreads();                                   // the energy vector written by this CTA's warps
+    if (threadIdx.x < 32) chain_phase(a.chain, a.fusedChainMode, threadIdx.x);
 }
 
 // The Nose-Hoover chain update(s) between two streaming launches: one warp, lane g = thermostat g.
