@@ -161,6 +161,13 @@ int tgnh_set_chain_state(tgnh_handle* h, void* stream, const double* eta, const 
 int tgnh_get_vscale(tgnh_handle* h, void* stream, double* vscale /*[T]*/);
 /* dof[T] (dof - COM share), NkT[T], eta_mass[T*M]  (tempGroupDof/tempGroupNkbT/etaMass, :215-235) */
 int tgnh_get_thermostat_params(const tgnh_handle* h, double* dof, double* nkbt, double* eta_mass);
+/* The host-side plan tgnh_create would build for these parameters, without touching a device: every check of the tables
+ * (contiguous residues, Drude pairs inside one residue and one temperature group, constraint partners in one group: the
+ * reference's two exceptions, CudaDrudeTGNHKernels.cpp:146,193) and the tiling.  tile_start (may be NULL) receives
+ * num_tiles + 1 particle indices: tile t covers [tile_start[t], tile_start[t+1]), at most 512 particles, never separating
+ * a Drude pair nor a residue of up to 128 particles. */
+int tgnh_plan_tiles(const tgnh_params* p, int32_t* tile_start, int32_t capacity, int32_t* num_tiles, int32_t* num_big_residues,
+                    int32_t* residue_uniform);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t tgnh_launch_count(const tgnh_handle* h);
 /* Per-launch device timing: while enabled every streaming launch is bracketed by CUDA events on its stream.

@@ -23,7 +23,7 @@ SYMBOLS = [
     "tgnh_thermostat", "tgnh_half2", "tgnh_flush",
     "tgnh_step", "tgnh_step_host", "tgnh_set_posq_correction", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
     "tgnh_kinetic_energy", "tgnh_compute_kinetic_energies", "tgnh_get_chain_state", "tgnh_set_chain_state",
-    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
+    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_plan_tiles", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
     "tgnh_comm_create", "tgnh_comm_destroy",
 ]
 
@@ -85,6 +85,8 @@ def lib():
         L.tgnh_launch_count.argtypes = [vp]
         L.tgnh_launch_count.restype = C.c_int64
         L.tgnh_exchange_kind.argtypes = [vp]
+        ip32 = C.POINTER(C.c_int32)
+        L.tgnh_plan_tiles.argtypes = [C.POINTER(Params), ip32, C.c_int32, ip32, ip32, ip32]
         L.tgnh_set_profiling.argtypes = [vp, C.c_int]
         L.tgnh_get_profile.argtypes = [vp, dp, C.POINTER(C.c_int64)]
         L.tgnh_comm_get_unique_id.argtypes = [vp]
@@ -129,36 +131,54 @@ class Comm:
             self.h = None
 
 
+def make_params(system, *, force_format=FORCE_F32_SOA, precision=PRECISION_SINGLE, padded=None, device=-1, comm=None,
+                has_cm_motion_remover=False, constraints=None, **overrides):
+    """tgnh_params for a synth.DrudeSystem.  Returns (params, arrays that must outlive it, padded particle count)."""
+    s = system
+    n = s.num_particles
+    padded = padded or ((n + 31) // 32) * 32
+    cons = s.constraints if constraints is None else constraints
+    cons = np.ascontiguousarray(cons, np.int32).reshape(-1, 2)
+    k = dict(
+        masses=np.ascontiguousarray(s.masses, np.float64), pd=np.ascontiguousarray(s.pair_drude, np.int32),
+        pp=np.ascontiguousarray(s.pair_parent, np.int32), tg=np.ascontiguousarray(s.temp_group, np.int32),
+        res=np.ascontiguousarray(s.res_id, np.int32), c0=np.ascontiguousarray(cons[:, 0]),
+        c1=np.ascontiguousarray(cons[:, 1]))
+    p = Params(
+        num_particles=n, padded_num_particles=padded, num_pairs=len(k["pd"]), num_residues=s.num_residues,
+        num_temp_groups=s.num_temp_groups, num_constraints=len(cons), num_nh_chains=s.num_nh_chains,
+        drude_steps_per_real_step=s.drude_steps, use_drude_nh_chains=int(s.use_drude_nh_chains),
+        use_com_temp_group=int(s.use_com_temp_group), has_cm_motion_remover=int(has_cm_motion_remover),
+        force_format=force_format, device=device, precision=precision, temperature=s.temperature, coupling_time=s.coupling_time,
+        drude_temperature=s.drude_temperature, drude_coupling_time=s.drude_coupling_time, step_size=s.step_size,
+        max_drude_distance=s.max_drude_distance, masses=_dp(k["masses"]), pair_drude=_ip(k["pd"]),
+        pair_parent=_ip(k["pp"]), particle_temp_group=_ip(k["tg"]), particle_res_id=_ip(k["res"]),
+        constraint_p=_ip(k["c0"]), constraint_p1=_ip(k["c1"]), comm=comm.h if comm is not None else None)
+    for key, val in overrides.items():
+        setattr(p, key, val)
+    return p, k, padded
+
+
+def plan_tiles(system, **kw):
+    """tgnh_plan_tiles: the host-side plan of tgnh_create without a device.  Returns (tile_start[num_tiles + 1],
+    number of big residues, residue_uniform); raises TgnhError for every table error tgnh_create would report."""
+    p, keep, _ = make_params(system, **kw)
+    nt, nb, uni = C.c_int32(), C.c_int32(), C.c_int32()
+    check(lib().tgnh_plan_tiles(C.byref(p), None, 0, C.byref(nt), C.byref(nb), C.byref(uni)))
+    ts = np.zeros(nt.value + 1, np.int32)
+    check(lib().tgnh_plan_tiles(C.byref(p), ts.ctypes.data_as(C.POINTER(C.c_int32)), len(ts), C.byref(nt), C.byref(nb), C.byref(uni)))
+    return ts, nb.value, bool(uni.value)
+
+
 class Handle:
     """Owns one tgnh_handle.  Buffers are passed as raw device pointers (ints), e.g. tensor.data_ptr()."""
 
     def __init__(self, system, *, force_format=FORCE_F32_SOA, precision=PRECISION_SINGLE, padded=None, device=-1, comm=None,
                  has_cm_motion_remover=False, constraints=None, **overrides):
-        s = system
-        n = s.num_particles
-        padded = padded or ((n + 31) // 32) * 32
-        cons = s.constraints if constraints is None else constraints
-        cons = np.ascontiguousarray(cons, np.int32).reshape(-1, 2)
-        self._keep = dict(
-            masses=np.ascontiguousarray(s.masses, np.float64), pd=np.ascontiguousarray(s.pair_drude, np.int32),
-            pp=np.ascontiguousarray(s.pair_parent, np.int32), tg=np.ascontiguousarray(s.temp_group, np.int32),
-            res=np.ascontiguousarray(s.res_id, np.int32), c0=np.ascontiguousarray(cons[:, 0]),
-            c1=np.ascontiguousarray(cons[:, 1]))
-        k = self._keep
-        p = Params(
-            num_particles=n, padded_num_particles=padded, num_pairs=len(k["pd"]), num_residues=s.num_residues,
-            num_temp_groups=s.num_temp_groups, num_constraints=len(cons), num_nh_chains=s.num_nh_chains,
-            drude_steps_per_real_step=s.drude_steps, use_drude_nh_chains=int(s.use_drude_nh_chains),
-            use_com_temp_group=int(s.use_com_temp_group), has_cm_motion_remover=int(has_cm_motion_remover),
-            force_format=force_format, device=device, precision=precision, temperature=s.temperature, coupling_time=s.coupling_time,
-            drude_temperature=s.drude_temperature, drude_coupling_time=s.drude_coupling_time, step_size=s.step_size,
-            max_drude_distance=s.max_drude_distance, masses=_dp(k["masses"]), pair_drude=_ip(k["pd"]),
-            pair_parent=_ip(k["pp"]), particle_temp_group=_ip(k["tg"]), particle_res_id=_ip(k["res"]),
-            constraint_p=_ip(k["c0"]), constraint_p1=_ip(k["c1"]), comm=comm.h if comm is not None else None)
-        for key, val in overrides.items():
-            setattr(p, key, val)
+        p, self._keep, padded = make_params(system, force_format=force_format, precision=precision, padded=padded, device=device, comm=comm,
+                                            has_cm_motion_remover=has_cm_motion_remover, constraints=constraints, **overrides)
         self.padded = padded
-        self.num_particles = n
+        self.num_particles = system.num_particles
         self.M = p.num_nh_chains
         h = C.c_void_p()
         check(lib().tgnh_create(C.byref(p), C.byref(h)))

@@ -347,9 +347,8 @@ static int configure_kernel(tgnh_handle* h, int kind, int* grid, int* smem) {
 // ------------------------------------------------------------------------------------------------
 // create: index tables, DOF bookkeeping, thermostat masses (CudaDrudeTGNHKernels.cpp:75-235)
 // ------------------------------------------------------------------------------------------------
-extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
-    if (!p || !out) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
-    *out = nullptr;
+// scalar arguments of tgnh_params (no table is read, no device is touched)
+static int validate_params(const tgnh_params* p) {
     const int N = p->num_particles, P = p->num_pairs, R = p->num_residues, G = p->num_temp_groups, M = p->num_nh_chains;
     const int T = G + 2;
     if (N < 1) return fail(TGNH_ERR_INVALID_ARGUMENT, "num_particles must be positive");
@@ -369,21 +368,34 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         return fail(TGNH_ERR_INVALID_ARGUMENT, "unknown precision %d", p->precision);
     if (p->max_drude_distance < 0) return fail(TGNH_ERR_INVALID_ARGUMENT, "setMaxDrudeDistance: Distance cannot be negative");
     if (!(p->step_size > 0)) return fail(TGNH_ERR_INVALID_ARGUMENT, "step_size must be positive");
+    return TGNH_OK;
+}
 
-    int deviceCount = 0;
-    if (cudaGetDeviceCount(&deviceCount) != cudaSuccess || deviceCount == 0)
-        return fail(TGNH_ERR_NO_DEVICE, "no CUDA device: libtgnh has no CPU fallback");
-    int device = p->device;
-    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
-    CUDA_TRY(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return fail(TGNH_ERR_NO_DEVICE, "device %d is sm_%d%d; libtgnh is built for sm_100a (B200) only", device, prop.major, prop.minor);
+// Everything tgnh_create derives on the host from the System's tables: residue ranges, DOF bookkeeping, pair partners,
+// per-particle descriptors, residue-aligned tiles (big residues cut where no Drude pair is separated), the per-tile residue
+// lists.  No device is touched, so it is also what tgnh_plan_tiles exposes to tests that run without a GPU.
+struct HostPlan {
+    std::vector<int> resFirst, resLast;
+    std::vector<double> resMass, dofv, redMass;
+    std::vector<int> partner;
+    std::vector<uint32_t> role, desc;
+    std::vector<int> tileStart, resStart, tileFirstRes, bigFirst, bigLast;
+    double drudeDof = 0, comDof = 0;
+    bool uniform = true;
+};
 
+static int build_plan(const tgnh_params* p, HostPlan& hp) {
+    const int N = p->num_particles, P = p->num_pairs, R = p->num_residues, G = p->num_temp_groups;
+    const int T = G + 2;
+    std::vector<int>&resFirst = hp.resFirst, &resLast = hp.resLast, &partner = hp.partner;
+    std::vector<double>&resMass = hp.resMass, &dofv = hp.dofv, &redMass = hp.redMass;
+    std::vector<uint32_t>&role = hp.role, &desc = hp.desc;
+    std::vector<int>&tileStart = hp.tileStart, &resStart = hp.resStart, &tileFirstRes = hp.tileFirstRes, &bigFirst = hp.bigFirst, &bigLast = hp.bigLast;
+    double& drudeDof = hp.drudeDof;
+    bool& uniform = hp.uniform;
     // ---- residues: contiguous ranges (drudeTGNH.cu:86-101 assumes it silently; we check) ----
-    std::vector<int> resFirst(R, -1), resLast(R, -1);
-    std::vector<double> resMass(R, 0.0);
+    resFirst.assign(R, -1); resLast.assign(R, -1);
+    resMass.assign(R, 0.0);
     for (int i = 0; i < N; i++) {
         const int r = p->particle_res_id[i];
         if (r < 0 || r >= R) return fail(TGNH_ERR_INVALID_ARGUMENT, "particle %d has residue id %d outside [0,%d)", i, r, R);
@@ -395,7 +407,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         const int tg = p->particle_temp_group[i];
         if (tg < 0 || tg >= G) return fail(TGNH_ERR_INVALID_ARGUMENT, "particle %d has temperature group %d outside [0,%d)", i, tg, G);
     }
-    bool uniform = true;
+    uniform = true;
     for (int r = 0; r < R; r++) {
         if (resFirst[r] < 0) return fail(TGNH_ERR_INVALID_ARGUMENT, "residue %d has no particles", r);
         for (int i = resFirst[r] + 1; i <= resLast[r]; i++)
@@ -403,7 +415,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
     }
 
     // ---- DOF bookkeeping (CudaDrudeTGNHKernels.cpp:114-150, 186-212) ----
-    std::vector<double> dofv(T, 0.0), redMass(G + 1, 0.0);
+    dofv.assign(T, 0.0); redMass.assign(G + 1, 0.0);
     for (int i = 0; i < N; i++) {
         const int tg = p->particle_temp_group[i];
         const double mass = p->masses[i];
@@ -412,9 +424,9 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
             if (p->use_com_temp_group) redMass[tg] += 3 * mass * (1.0 / resMass[p->particle_res_id[i]]);
         }
     }
-    std::vector<int> partner(N, 0);
-    std::vector<uint32_t> role(N, ROLE_NORMAL);
-    double drudeDof = 0;
+    partner.assign(N, 0);
+    role.assign(N, ROLE_NORMAL);
+    drudeDof = 0;
     for (int i = 0; i < P; i++) {
         const int d = p->pair_drude[i], q = p->pair_parent[i];
         if (d < 0 || d >= N || q < 0 || q >= N || d == q) return fail(TGNH_ERR_INVALID_ARGUMENT, "Drude pair %d has a bad particle index", i);
@@ -437,7 +449,105 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
             return fail(TGNH_ERR_TEMP_GROUP, "Temperature group of constrained particles must be the same");
         dofv[p->particle_temp_group[a]] -= 1;
     }
-    double comDof = p->use_com_temp_group ? 3.0 * R : 0.0;
+    hp.comDof = p->use_com_temp_group ? 3.0 * R : 0.0;
+
+
+    // ---- descriptors and residue-aligned tiles ----
+    const int descLen = (N + 3) & ~3;
+    desc.assign(descLen, 0u);
+    for (int i = 0; i < N; i++) {
+        const int r = p->particle_res_id[i];
+        if (partner[i] < -128 || partner[i] > 127) return (fail(TGNH_ERR_UNSUPPORTED, "Drude pair partner of particle %d is %d particles away (limit 127)", i, partner[i]));
+        const bool big = resLast[r] - resFirst[r] + 1 > MAX_RES;      // COM velocity from the pre-pass table, not from the tile
+        desc[i] = big ? desc_pack(p->particle_temp_group[i], role[i], 0, 0, partner[i], true)
+                      : desc_pack(p->particle_temp_group[i], role[i], i - resFirst[r], resLast[r] - i, partner[i]);
+    }
+    // split points inside big residues must not separate a Drude pair: unsafe[s] != 0 <=> some pair (a < b) has a < s <= b
+    std::vector<int> unsafe(N + 2, 0);
+    for (int i = 0; i < N; i++)
+        if (partner[i] > 0) { unsafe[i + 1]++; unsafe[i + partner[i] + 1]--; }
+    for (int i = 1; i <= N; i++) unsafe[i] += unsafe[i - 1];
+    bigFirst.clear(); bigLast.clear();
+    tileStart.assign(1, 0);
+    {
+        int cur = 0;                          // particles in the open tile
+        int r = p->particle_res_id[0];
+        int i = 0;
+        while (i < N) {
+            r = p->particle_res_id[i];
+            const int len = resLast[r] - resFirst[r] + 1;
+            if (len > MAX_RES) {
+                // big residue: its own tiles, cut where no Drude pair is separated (nothing else ties its particles to a tile)
+                bigFirst.push_back(i); bigLast.push_back(resLast[r]);
+                if (cur > 0) { tileStart.push_back(i); cur = 0; }
+                const int end = resLast[r] + 1;
+                int segStart = i;
+                while (end - segStart > TILE) {
+                    int cut = segStart + TILE;
+                    while (cut > segStart && unsafe[cut]) cut--;
+                    if (cut == segStart)
+                        return (fail(TGNH_ERR_UNSUPPORTED, "residue %d: no place to cut %d..%d without separating a Drude pair", r, segStart, segStart + TILE));
+                    tileStart.push_back(cut);
+                    segStart = cut;
+                }
+                if (end < N) tileStart.push_back(end);
+                cur = 0;
+                i = end;
+                continue;
+            }
+            if (cur + len > TILE) { tileStart.push_back(i); cur = 0; }
+            cur += len;
+            i += len;
+        }
+        tileStart.push_back(N);
+    }
+    // residues in particle order (tiles are residue-aligned, so each tile owns a contiguous slice of this list)
+    resStart.clear(); tileFirstRes.clear();
+    {
+        size_t t = 0;
+        for (int i = 0; i < N;) {
+            if (t < tileStart.size() && tileStart[t] == i) { tileFirstRes.push_back((int)resStart.size()); t++; }
+            resStart.push_back(i);
+            int next = resLast[p->particle_res_id[i]] + 1;
+            if (t < tileStart.size() && tileStart[t] < next) next = tileStart[t];     // a big residue continues in the next tile
+            i = next;
+        }
+        tileFirstRes.push_back((int)resStart.size());
+        resStart.push_back(N);
+        while (resStart.size() & 3) resStart.push_back(N);
+    }
+    (void)T;
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
+    if (!p || !out) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (int rc = validate_params(p)) return rc;
+    const int N = p->num_particles, P = p->num_pairs, R = p->num_residues, G = p->num_temp_groups, M = p->num_nh_chains;
+    const int T = G + 2;
+
+    // ---- everything derived on the host (also reachable without a device through tgnh_plan_tiles) ----
+    HostPlan hp;
+    if (int rc = build_plan(p, hp)) return rc;
+    std::vector<int>&resFirst = hp.resFirst, &resLast = hp.resLast, &tileStart = hp.tileStart, &resStart = hp.resStart, &tileFirstRes = hp.tileFirstRes,
+                    &bigFirst = hp.bigFirst, &bigLast = hp.bigLast;
+    std::vector<double>&dofv = hp.dofv, &redMass = hp.redMass;
+    std::vector<uint32_t>& desc = hp.desc;
+    double &drudeDof = hp.drudeDof, &comDof = hp.comDof;
+    const bool uniform = hp.uniform;
+    (void)resFirst; (void)resLast;
+
+    int deviceCount = 0;
+    if (cudaGetDeviceCount(&deviceCount) != cudaSuccess || deviceCount == 0)
+        return fail(TGNH_ERR_NO_DEVICE, "no CUDA device: libtgnh has no CPU fallback");
+    int device = p->device;
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(TGNH_ERR_NO_DEVICE, "device %d is sm_%d%d; libtgnh is built for sm_100a (B200) only", device, prop.major, prop.minor);
 
     tgnh_handle* h = new tgnh_handle();
     h->device = device; h->numSMs = prop.multiProcessorCount;
@@ -500,72 +610,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         if (h->useDrudeNH) etaDotDot[(G + 1) * M + i] = (h->etaMass[(G + 1) * M + i - 1] * 0.0 - drudekbT) / h->etaMass[(G + 1) * M + i];
     }
 
-    // ---- descriptors and residue-aligned tiles ----
-    const int descLen = (N + 3) & ~3;
-    std::vector<uint32_t> desc(descLen, 0u);
-    for (int i = 0; i < N; i++) {
-        const int r = p->particle_res_id[i];
-        if (partner[i] < -128 || partner[i] > 127) return bail(fail(TGNH_ERR_UNSUPPORTED, "Drude pair partner of particle %d is %d particles away (limit 127)", i, partner[i]));
-        const bool big = resLast[r] - resFirst[r] + 1 > MAX_RES;      // COM velocity from the pre-pass table, not from the tile
-        desc[i] = big ? desc_pack(p->particle_temp_group[i], role[i], 0, 0, partner[i], true)
-                      : desc_pack(p->particle_temp_group[i], role[i], i - resFirst[r], resLast[r] - i, partner[i]);
-    }
-    // split points inside big residues must not separate a Drude pair: unsafe[s] != 0 <=> some pair (a < b) has a < s <= b
-    std::vector<int> unsafe(N + 2, 0);
-    for (int i = 0; i < N; i++)
-        if (partner[i] > 0) { unsafe[i + 1]++; unsafe[i + partner[i] + 1]--; }
-    for (int i = 1; i <= N; i++) unsafe[i] += unsafe[i - 1];
-    std::vector<int> bigFirst, bigLast;
-    std::vector<int> tileStart;
-    tileStart.push_back(0);
-    {
-        int cur = 0;                          // particles in the open tile
-        int r = p->particle_res_id[0];
-        int i = 0;
-        while (i < N) {
-            r = p->particle_res_id[i];
-            const int len = resLast[r] - resFirst[r] + 1;
-            if (len > MAX_RES) {
-                // big residue: its own tiles, cut where no Drude pair is separated (nothing else ties its particles to a tile)
-                bigFirst.push_back(i); bigLast.push_back(resLast[r]);
-                if (cur > 0) { tileStart.push_back(i); cur = 0; }
-                const int end = resLast[r] + 1;
-                int segStart = i;
-                while (end - segStart > TILE) {
-                    int cut = segStart + TILE;
-                    while (cut > segStart && unsafe[cut]) cut--;
-                    if (cut == segStart)
-                        return bail(fail(TGNH_ERR_UNSUPPORTED, "residue %d: no place to cut %d..%d without separating a Drude pair", r, segStart, segStart + TILE));
-                    tileStart.push_back(cut);
-                    segStart = cut;
-                }
-                if (end < N) tileStart.push_back(end);
-                cur = 0;
-                i = end;
-                continue;
-            }
-            if (cur + len > TILE) { tileStart.push_back(i); cur = 0; }
-            cur += len;
-            i += len;
-        }
-        tileStart.push_back(N);
-    }
     h->numTiles = (int)tileStart.size() - 1;
-    // residues in particle order (tiles are residue-aligned, so each tile owns a contiguous slice of this list)
-    std::vector<int> resStart, tileFirstRes;
-    {
-        size_t t = 0;
-        for (int i = 0; i < N;) {
-            if (t < tileStart.size() && tileStart[t] == i) { tileFirstRes.push_back((int)resStart.size()); t++; }
-            resStart.push_back(i);
-            int next = resLast[p->particle_res_id[i]] + 1;
-            if (t < tileStart.size() && tileStart[t] < next) next = tileStart[t];     // a big residue continues in the next tile
-            i = next;
-        }
-        tileFirstRes.push_back((int)resStart.size());
-        resStart.push_back(N);
-        while (resStart.size() & 3) resStart.push_back(N);
-    }
     h->kindB = uniform ? KIND_BU : KIND_B;
     h->kindKE = uniform ? KIND_KU : KIND_KE;
 
@@ -645,6 +690,23 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
     if (!dmalloc((void**)&h->dPartials, (size_t)maxGrid * T * 8)) return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the partial sums failed"));
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(TGNH_ERR_CUDA, "device error during tgnh_create: %s", cudaGetErrorString(cudaGetLastError())));
     *out = h;
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_plan_tiles(const tgnh_params* p, int32_t* tile_start, int32_t capacity, int32_t* num_tiles, int32_t* num_big_residues,
+                               int32_t* residue_uniform) {
+    if (!p) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = validate_params(p)) return rc;
+    HostPlan hp;
+    if (int rc = build_plan(p, hp)) return rc;
+    const int n = (int)hp.tileStart.size() - 1;
+    if (num_tiles) *num_tiles = n;
+    if (num_big_residues) *num_big_residues = (int)hp.bigFirst.size();
+    if (residue_uniform) *residue_uniform = hp.uniform ? 1 : 0;
+    if (tile_start) {
+        if (capacity < n + 1) return fail(TGNH_ERR_INVALID_ARGUMENT, "tile_start holds %d entries, %d are needed", capacity, n + 1);
+        for (int i = 0; i <= n; i++) tile_start[i] = hp.tileStart[i];
+    }
     return TGNH_OK;
 }
 

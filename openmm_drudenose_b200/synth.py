@@ -239,6 +239,14 @@ def build(templates, mol_types, mol_groups, num_temp_groups, *, seed=SEED, first
     u_center = np.empty((nmol, 3)); n_mol = np.empty((nmol, kmax, 9))
     g0 = first_molecule
     j = 0
+    if kmax > 64:
+        # big molecules (polymers): one Philox stream per global molecule instead of a [_CHUNK, kmax, 9] block per chunk
+        for j in range(nmol):
+            rng = np.random.Generator(np.random.Philox(key=[seed, (1 << 40) + g0 + j]))
+            u_center[j] = rng.random(3)
+            n_mol[j, :msize[j]] = rng.standard_normal((int(msize[j]), 9))
+            n_mol[j, msize[j]:] = 0.0
+        j = nmol
     while j < nmol:
         chunk = (g0 + j) // _CHUNK
         lo = chunk * _CHUNK

@@ -127,3 +127,95 @@ def test_sharded_kinetic_energy_reduction_gloo(tmp_path):
                          capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "OK" in out.stdout
+
+
+# ---- the host-side plan (tgnh_plan_tiles): table checks and tiling, no device needed -----------------------------------
+def _assert_plan_invariants(s, ts, nbig):
+    n = s.num_particles
+    assert ts[0] == 0 and ts[-1] == n and np.all(np.diff(ts) > 0) and np.all(np.diff(ts) <= 512)
+    first = np.full(s.num_residues, n, np.int64); last = np.full(s.num_residues, -1, np.int64)
+    np.minimum.at(first, s.res_id, np.arange(n)); np.maximum.at(last, s.res_id, np.arange(n))
+    size = last - first + 1
+    tile_of = np.searchsorted(ts, np.arange(n), side="right") - 1
+    small = size <= 128
+    assert np.all(tile_of[first[small]] == tile_of[last[small]]), "a residue of <= 128 particles was split"
+    assert nbig == int(np.sum(~small))
+    if len(s.pair_drude):
+        assert np.all(tile_of[s.pair_drude] == tile_of[s.pair_parent]), "a Drude pair was separated"
+    for r in np.nonzero(~small)[0]:          # a big residue starts its own tile and ends one
+        assert first[r] in ts and (last[r] + 1) in ts
+
+
+def test_plan_tiles_on_the_synthetic_systems():
+    for s in (synth.water_box(3000, 4), synth.nacl_box(), synth.ionic_liquid(200), synth.polymer_in_water(1500, (300, 700), 2),
+              synth.build([synth.WATER4, synth.SOD, synth.SWM4], np.arange(1501) % 3, np.arange(1501) % 2, 2)):
+        ts, nbig, uniform = capi.plan_tiles(s)
+        _assert_plan_invariants(s, ts, nbig)
+        assert uniform
+
+
+def test_plan_tiles_random_topologies():
+    """Random mixtures of residue sizes from 1 to 1500 particles with random Drude pairs up to 100 indices apart."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.sampled_from([1, 2, 3, 4, 5, 7, 35, 127, 128, 129, 300, 513, 1500]), min_size=1, max_size=40), st.integers(0, 2 ** 31 - 1))
+    def run(sizes, seed):
+        import types
+        rng = np.random.default_rng(seed)
+        res_id, pd, pp, base = [], [], [], 0
+        for k, size in enumerate(sizes):
+            used = set()
+            for _ in range(size // 3):
+                a = int(rng.integers(0, size)); b = a + int(rng.integers(1, 101))
+                if b < size and a not in used and b not in used:
+                    used.update((a, b)); pd.append(base + b); pp.append(base + a)
+            res_id += [k] * size
+            base += size
+        res_id = np.array(res_id, np.int32)
+        s = types.SimpleNamespace(
+            num_particles=base, masses=rng.uniform(1.0, 20.0, base), pair_drude=np.array(pd, np.int32), pair_parent=np.array(pp, np.int32),
+            temp_group=(res_id % 2).astype(np.int32), res_id=res_id, constraints=np.zeros((0, 2), np.int32), num_residues=len(sizes),
+            num_temp_groups=2, num_nh_chains=3, drude_steps=20, use_drude_nh_chains=True, use_com_temp_group=True, temperature=300.0,
+            coupling_time=0.1, drude_temperature=1.0, drude_coupling_time=0.005, step_size=0.001, max_drude_distance=0.02)
+        try:
+            ts, nbig, _ = capi.plan_tiles(s)
+        except capi.TgnhError as e:
+            assert e.code == capi.ERR_UNSUPPORTED and "without separating a Drude pair" in str(e)     # legal refusal, never a bad plan
+            return
+        _assert_plan_invariants(s, ts, nbig)
+    run()
+
+
+def test_plan_reports_the_reference_table_errors():
+    """The reference's two exceptions (CudaDrudeTGNHKernels.cpp:146, 193) and this library's own checks, all before any device is touched."""
+    def err(mut):
+        s = synth.water_box(64, 2)
+        mut(s)
+        with pytest.raises(capi.TgnhError) as e:
+            capi.plan_tiles(s)
+        return e.value
+
+    def drude_group(s): s.temp_group = s.temp_group.copy(); s.temp_group[s.pair_drude[0]] ^= 1
+    e = err(drude_group)
+    assert e.code == capi.ERR_TEMP_GROUP and "Temperature group for drude particle must be the same as the parent particle" in str(e)
+
+    def constraint_group(s):
+        s.temp_group = s.temp_group.copy(); s.temp_group[2] ^= 1
+        s.constraints = np.array([[0, 2]], np.int32)
+    assert err(constraint_group).code == capi.ERR_TEMP_GROUP
+
+    def scattered(s): s.res_id = s.res_id.copy(); s.res_id[[1, 5]] = s.res_id[[5, 1]]
+    assert "not a contiguous particle range" in str(err(scattered))
+
+    def far_pair(s): s.res_id = np.zeros_like(s.res_id); s.num_residues = 1; s.pair_drude = s.pair_drude.copy(); s.pair_drude[0] = 250
+    assert err(far_pair).code == capi.ERR_UNSUPPORTED
+
+    def cross_residue(s): s.pair_parent = s.pair_parent.copy(); s.pair_parent[0] = 8        # molecule 2: same group, other residue
+    assert "spans two residues" in str(err(cross_residue))
+
+    def twice(s): s.pair_parent = s.pair_parent.copy(); s.pair_parent[1] = s.pair_parent[0]
+    assert "more than one pair" in str(err(twice))
+
+    def bad_group(s): s.temp_group = s.temp_group.copy(); s.temp_group[3] = 7
+    assert err(bad_group).code == capi.ERR_INVALID_ARGUMENT
