@@ -135,7 +135,8 @@ int tgnh_flush(tgnh_handle* h, void* stream, void* velm);
  * synthetic forces).  Internally defers/folds the scaling between steps; velm is consistent on return. */
 int tgnh_step(tgnh_handle* h, void* stream, void* velm, void* posq, const void* force, int nsteps);
 /* Host-buffer convenience (end-to-end path): copies velm/posq/force from pinned or pageable HOST memory,
- * runs nsteps, copies velm/posq back and the 2*KE vector into ke2_host ([G+2], may be NULL). Blocking. */
+ * runs nsteps, copies velm/posq back and the 2*KE vector into ke2_host ([G+2], may be NULL). Blocking.
+ * Single and double layouts (mixed also needs the posqCorrection array: use the device-buffer calls). */
 int tgnh_step_host(tgnh_handle* h, void* velm_host, void* posq_host, const void* force_host, int nsteps, double* ke2_host);
 /* Mixed precision: the float4[paddedN] residual array of the positions (cu.getPosqCorrection()). */
 int tgnh_set_posq_correction(tgnh_handle* h, void* posq_correction);

@@ -968,22 +968,29 @@ extern "C" int tgnh_invalidate(tgnh_handle* h) {
 extern "C" int tgnh_step_host(tgnh_handle* h, void* velm_host, void* posq_host, const void* force_host, int nsteps, double* ke2_host) {
     if (!h || !velm_host || !posq_host || !force_host) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->prec == TGNH_PRECISION_MIXED)
+        return fail(TGNH_ERR_UNSUPPORTED, "tgnh_step_host covers the single and double layouts (mixed needs the posqCorrection array: use device buffers)");
     const size_t fbytes = (size_t)3 * h->paddedN * (h->ffmt == TGNH_FORCE_I64_SOA ? 8 : 4);
-    if (!h->hsStream) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->hsStream, cudaStreamNonBlocking));
-        if (h->prec) return fail(TGNH_ERR_UNSUPPORTED, "tgnh_step_host covers the single-precision layout only");
-        CUDA_TRY(cudaMalloc(&h->hsVelm, (size_t)h->paddedN * 16));
-        CUDA_TRY(cudaMalloc(&h->hsPosq, (size_t)h->paddedN * 16));
-        CUDA_TRY(cudaMalloc(&h->hsForce, fbytes));
+    const size_t vb = h->prec ? 32 : 16;                 // bytes per velm / posq element
+    if (!h->hsVelm) {
+        if (!h->hsStream) CUDA_TRY(cudaStreamCreateWithFlags(&h->hsStream, cudaStreamNonBlocking));
+        void *v = nullptr, *x = nullptr, *f = nullptr;
+        if (cudaMalloc(&v, (size_t)h->paddedN * vb) != cudaSuccess || cudaMalloc(&x, (size_t)h->paddedN * vb) != cudaSuccess ||
+            cudaMalloc(&f, fbytes) != cudaSuccess) {
+            cudaFree(v); cudaFree(x); cudaFree(f);
+            (void)cudaGetLastError();
+            return fail(TGNH_ERR_CUDA, "cudaMalloc of the staging buffers failed");
+        }
+        h->hsVelm = v; h->hsPosq = x; h->hsForce = f;
     }
     cudaStream_t s = h->hsStream;
-    CUDA_TRY(cudaMemcpyAsync(h->hsVelm, velm_host, (size_t)h->N * 16, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->hsPosq, posq_host, (size_t)h->N * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->hsVelm, velm_host, (size_t)h->N * vb, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->hsPosq, posq_host, (size_t)h->N * vb, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(h->hsForce, force_host, fbytes, cudaMemcpyHostToDevice, s));
     h->keValid = false;
     if (int rc = tgnh_step(h, s, h->hsVelm, h->hsPosq, h->hsForce, nsteps)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(velm_host, h->hsVelm, (size_t)h->N * 16, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(posq_host, h->hsPosq, (size_t)h->N * 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(velm_host, h->hsVelm, (size_t)h->N * vb, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(posq_host, h->hsPosq, (size_t)h->N * vb, cudaMemcpyDeviceToHost, s));
     if (ke2_host) CUDA_TRY(cudaMemcpyAsync(ke2_host, h->chain.ke2Used, h->T * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return TGNH_OK;

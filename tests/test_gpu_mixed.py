@@ -203,3 +203,26 @@ def test_statistical_acceptance_like_the_reference_tests(cuda, prec):
     print("mean temperatures", prec, t)
     assert dmax <= s.max_drude_distance * (1 + 1e-6)
     h.close()
+
+
+@pytest.mark.parametrize("prec", [capi.PRECISION_SINGLE, capi.PRECISION_DOUBLE])
+def test_step_host_equals_device_path(cuda, prec):
+    """tgnh_step_host (host buffers in, state out: bench.py's e2e leg) gives what the device-buffer calls give; the mixed
+    layout, which needs a third array, is refused with a message."""
+    import torch
+    s = synth.water_box(3000, 3)
+    st = DeviceState(s, cuda, precision=prec)
+    h = _handle(s, st)
+    hv, hx, hf = st.velm.cpu().pin_memory(), st.posq.cpu().pin_memory(), st.force.cpu().pin_memory()
+    h2 = capi.Handle(s, precision=prec, padded=st.padded)
+    for _ in range(3):
+        ke_host = h2.step_host(hv.data_ptr(), hx.data_ptr(), hf.data_ptr(), 2)
+        h.step(*st.ptrs, nsteps=2)
+        h.invalidate()                                     # tgnh_step_host starts every call from the uploaded velocities
+    assert torch.equal(hv, st.velm.cpu()) and torch.equal(hx, st.posq.cpu())
+    np.testing.assert_allclose(ke_host, h.kinetic_energies(), rtol=1e-12)
+    hm = capi.Handle(s, precision=capi.PRECISION_MIXED, padded=st.padded)
+    with pytest.raises(capi.TgnhError) as e:
+        hm.step_host(hv.data_ptr(), hx.data_ptr(), hf.data_ptr(), 1)
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    h.close(); h2.close(); hm.close()
