@@ -2,7 +2,7 @@
 //
 // Host half of the hot path: what CudaIntegrateDrudeTGNHStepKernel::initialize / execute /
 // propagateNHChain do in the reference (platforms/cuda/src/CudaDrudeTGNHKernels.cpp:75-282, 284-408,
-// 433-652), re-designed so that a step is two streaming launches with the Nose-Hoover chain resident
+// 433-652), re-designed so that a step is two streaming launches plus the Nose-Hoover chain, resident
 // on the device: no D2H/H2D on the step path, no runtime kernel compilation.
 #include "../../include/tgnh.h"
 

@@ -1,4 +1,4 @@
-// The three streaming kernels of the TGNH step, as one persistent, TMA-fed template.
+// The streaming kernels of the TGNH step (nine kinds of one pass over the particles), as one persistent, TMA-fed template.
 //
 //   KIND_A  (first half)   = integrateDrudeTGNHChain + integrateDrudeTGNHVelocities(updatePosDelta) +
 //                            integrateDrudeTGNHPositions + applyHardWallConstraints
