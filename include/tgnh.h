@@ -169,6 +169,11 @@ int tgnh_get_thermostat_params(const tgnh_handle* h, double* dof, double* nkbt, 
  * a Drude pair nor a residue of up to 128 particles. */
 int tgnh_plan_tiles(const tgnh_params* p, int32_t* tile_start, int32_t capacity, int32_t* num_tiles, int32_t* num_big_residues,
                     int32_t* residue_uniform);
+/* The per-particle descriptor words tgnh_create uploads (temperature group, role, offsets inside the residue, offset to the
+ * pair partner), host-only.  Two particles are interchangeable for this library exactly when their words and masses are
+ * equal: what a CudaForceInfo::areParticlesIdentical must answer so that OpenMM's atom reordering (cu.reorderAtoms) only
+ * swaps molecules whose tables agree ("Atom reordering"). */
+int tgnh_plan_descriptors(const tgnh_params* p, uint32_t* desc_out /*[num_particles]*/);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t tgnh_launch_count(const tgnh_handle* h);
 /* Per-launch device timing: while enabled every streaming launch is bracketed by CUDA events on its stream.

@@ -23,7 +23,7 @@ SYMBOLS = [
     "tgnh_thermostat", "tgnh_half2", "tgnh_flush",
     "tgnh_step", "tgnh_step_host", "tgnh_set_posq_correction", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
     "tgnh_kinetic_energy", "tgnh_compute_kinetic_energies", "tgnh_get_chain_state", "tgnh_set_chain_state",
-    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_plan_tiles", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
+    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_plan_tiles", "tgnh_plan_descriptors", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
     "tgnh_comm_create", "tgnh_comm_destroy",
 ]
 
@@ -87,6 +87,7 @@ def lib():
         L.tgnh_exchange_kind.argtypes = [vp]
         ip32 = C.POINTER(C.c_int32)
         L.tgnh_plan_tiles.argtypes = [C.POINTER(Params), ip32, C.c_int32, ip32, ip32, ip32]
+        L.tgnh_plan_descriptors.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint32)]
         L.tgnh_set_profiling.argtypes = [vp, C.c_int]
         L.tgnh_get_profile.argtypes = [vp, dp, C.POINTER(C.c_int64)]
         L.tgnh_comm_get_unique_id.argtypes = [vp]
@@ -168,6 +169,14 @@ def plan_tiles(system, **kw):
     ts = np.zeros(nt.value + 1, np.int32)
     check(lib().tgnh_plan_tiles(C.byref(p), ts.ctypes.data_as(C.POINTER(C.c_int32)), len(ts), C.byref(nt), C.byref(nb), C.byref(uni)))
     return ts, nb.value, bool(uni.value)
+
+
+def plan_descriptors(system, **kw):
+    """tgnh_plan_descriptors: the per-particle descriptor words (uint32[N]), host-only."""
+    p, keep, _ = make_params(system, **kw)
+    out = np.zeros(system.num_particles, np.uint32)
+    check(lib().tgnh_plan_descriptors(C.byref(p), out.ctypes.data_as(C.POINTER(C.c_uint32))))
+    return out
 
 
 class Handle:

@@ -710,6 +710,15 @@ extern "C" int tgnh_plan_tiles(const tgnh_params* p, int32_t* tile_start, int32_
     return TGNH_OK;
 }
 
+extern "C" int tgnh_plan_descriptors(const tgnh_params* p, uint32_t* desc_out) {
+    if (!p || !desc_out) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = validate_params(p)) return rc;
+    HostPlan hp;
+    if (int rc = build_plan(p, hp)) return rc;
+    for (int i = 0; i < p->num_particles; i++) desc_out[i] = hp.desc[i];
+    return TGNH_OK;
+}
+
 extern "C" void tgnh_destroy(tgnh_handle* h) {
     if (!h) return;
     for (int r = 0; r < MAX_PEERS; r++)

@@ -32,6 +32,22 @@ public:
         v.device = cu.getDeviceIndex();
         return v;
     }
+    /** Keeps cu.reorderAtoms() from swapping molecules whose per-particle tables differ (temperature group, role, offsets):
+     *  the kernels' tables are indexed by atom slot and are not permuted (nor are the reference's, which registers nothing). */
+    void registerForceInfo(const std::vector<unsigned int>& descriptors, const std::vector<int>& residueOf) {
+        class Info : public CudaForceInfo {
+        public:
+            Info(const std::vector<unsigned int>& d, const std::vector<int>& r) : CudaForceInfo(0), desc(d), res(r) {}
+            bool areParticlesIdentical(int i, int j) { return desc[i] == desc[j]; }
+            int getNumParticleGroups() { return 0; }          // molecules are already held together by bonds / the DrudeForce
+            void getParticlesInGroup(int, std::vector<int>&) {}
+            bool areGroupsIdentical(int, int) { return true; }
+        private:
+            std::vector<unsigned int> desc;
+            std::vector<int> res;
+        };
+        cu.addForce(new Info(descriptors, residueOf));
+    }
     void applyConstraints(double tol) { cu.getIntegrationUtilities().applyConstraints(tol); }
     void computeVirtualSites() { cu.getIntegrationUtilities().computeVirtualSites(); }
     void applyVelocityConstraints(double tol) { cu.getIntegrationUtilities().applyVelocityConstraints(tol); }

@@ -77,6 +77,10 @@ void B200IntegrateDrudeTGNHStepKernel::initialize(const System& system, const Dr
     tgnh_destroy(handle);
     handle = NULL;
     check(tgnh_create(&p, &handle));
+    // atom reordering (cu.reorderAtoms): only molecules whose per-particle tables agree may trade places
+    std::vector<unsigned int> descriptors(n);
+    check(tgnh_plan_descriptors(&p, descriptors.data()));
+    device.registerForceInfo(descriptors, std::vector<int>(resId.begin(), resId.end()));
 }
 
 // CudaIntegrateDrudeTGNHStepKernel::execute (CudaDrudeTGNHKernels.cpp:284-408)

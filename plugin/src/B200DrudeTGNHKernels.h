@@ -37,6 +37,9 @@ public:
     virtual void applyConstraints(double tol) {}          // integration.applyConstraints: acts on posDelta
     virtual void computeVirtualSites() {}                 // integration.computeVirtualSites
     virtual void applyVelocityConstraints(double tol) {}  // integration.applyVelocityConstraints: acts on velm
+    /** Tell the platform which particles are interchangeable for this integrator (equal descriptor words, tgnh_plan_descriptors),
+     *  so that its atom reordering leaves the kernels' slot-indexed tables valid.  No-op where atoms are never reordered. */
+    virtual void registerForceInfo(const std::vector<unsigned int>& descriptors, const std::vector<int>& residueOf) {}
 };
 
 class B200IntegrateDrudeTGNHStepKernel : public IntegrateDrudeTGNHStepKernel {

@@ -219,3 +219,16 @@ def test_plan_reports_the_reference_table_errors():
 
     def bad_group(s): s.temp_group = s.temp_group.copy(); s.temp_group[3] = 7
     assert err(bad_group).code == capi.ERR_INVALID_ARGUMENT
+
+
+def test_descriptors_say_which_particles_are_interchangeable():
+    """What a CudaForceInfo built on tgnh_plan_descriptors would tell OpenMM's atom reordering: molecules of the same kind and
+    temperature group have equal words particle by particle, molecules in different groups do not."""
+    s = synth.water_box(8, 2)                     # molecule k -> group k % 2
+    d = capi.plan_descriptors(s).reshape(8, 4)
+    assert np.array_equal(d[0], d[2]) and np.array_equal(d[1], d[3])
+    assert not np.array_equal(d[0], d[1])
+    tg, role, partner = d & 0x7f, (d >> 8) & 3, d.astype(np.int32) >> 24
+    assert np.array_equal(tg, np.repeat((np.arange(8) % 2)[:, None], 4, 1))
+    assert np.array_equal(role[0], [2, 1, 0, 0]) and np.array_equal(partner[0], [1, -1, 0, 0])       # parent, Drude, H, H
+    assert np.array_equal((d[0] >> 10) & 0x7f, [0, 1, 2, 3]) and np.array_equal((d[0] >> 17) & 0x7f, [3, 2, 1, 0])
