@@ -486,3 +486,21 @@ def test_system_without_drude_pairs(cuda):
     np.testing.assert_allclose(h.kinetic_energies()[2], o.ke2[2], rtol=TOL_THERMO)
     assert np.all(np.abs(h.kinetic_energies()[[0, 1, 3]]) <= 1e-7 * o.ke2[2])      # m|v|^2 - |P|^2/M with fp32 products: cancellation noise
     h.close()
+
+
+def test_thirty_temperature_groups(cuda):
+    """The largest supported group count (G = 30, 32 thermostats = one warp of the chain kernel): the per-group energy columns
+    take 120 KB of shared memory, so the reducing kernels run one CTA per SM; results as for any other G."""
+    s = synth.water_box(3000, 30, quantize_masses=True)
+    st = DeviceState(s, cuda)
+    h = capi.Handle(s)
+    o = O.Oracle(s, O.TG)
+    p, v, f = s.positions.copy(), s.velocities.copy(), s.forces.copy()
+    h.step(*st.ptrs, nsteps=3)
+    o.step(p, v, f, 3)
+    assert rel_err(st.vel(), v) < 3 * TOL_STEP and rel_err(st.pos(), p) < TOL_STEP
+    assert ke_err(h.kinetic_energies(), o.ke2, o.thermostat_params()[1]) < TOL_THERMO
+    np.testing.assert_allclose(h.vscale(), o.vscale, rtol=TOL_THERMO)
+    with pytest.raises(capi.TgnhError):
+        capi.Handle(synth.water_box(3000, 31))               # 33 thermostats: refused with a message
+    h.close()
