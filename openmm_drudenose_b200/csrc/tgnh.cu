@@ -437,6 +437,8 @@ static int build_plan(const tgnh_params* p, HostPlan& hp) {
         if (p->particle_res_id[d] != p->particle_res_id[q])
             return fail(TGNH_ERR_UNSUPPORTED, "Drude pair %d spans two residues", i);
         if (p->masses[d] == 0.0) return fail(TGNH_ERR_INVALID_ARGUMENT, "Drude particle %d is massless", d);
+        if (p->masses[q] == 0.0)      // the reference's pair transform (drudeTGNH.cu:270-300, 330-364) divides by both masses: NaN there
+            return fail(TGNH_ERR_UNSUPPORTED, "parent particle %d of Drude pair %d is massless; the pair transform is undefined for it", q, i);
         role[d] = ROLE_DRUDE; role[q] = ROLE_PARENT;
         partner[d] = q - d; partner[q] = d - q;
         dofv[p->particle_temp_group[d]] -= 3;

@@ -217,6 +217,9 @@ def test_plan_reports_the_reference_table_errors():
     def twice(s): s.pair_parent = s.pair_parent.copy(); s.pair_parent[1] = s.pair_parent[0]
     assert "more than one pair" in str(err(twice))
 
+    def massless_parent(s): s.masses = s.masses.copy(); s.masses[s.pair_parent[0]] = 0.0
+    assert "massless" in str(err(massless_parent))       # the reference's pair transform yields NaN there; refused instead
+
     def bad_group(s): s.temp_group = s.temp_group.copy(); s.temp_group[3] = 7
     assert err(bad_group).code == capi.ERR_INVALID_ARGUMENT
 
