@@ -174,6 +174,16 @@ int tgnh_plan_tiles(const tgnh_params* p, int32_t* tile_start, int32_t capacity,
  * equal: what a CudaForceInfo::areParticlesIdentical must answer so that OpenMM's atom reordering (cu.reorderAtoms) only
  * swaps molecules whose tables agree ("Atom reordering"). */
 int tgnh_plan_descriptors(const tgnh_params* p, uint32_t* desc_out /*[num_particles]*/);
+/* The plan of the warp-chunk kernels (csrc/tgnh_v2.cuh), host-only: residue-aligned chunks of at most 32 consecutive particles
+ * (chunk_start receives num_chunks + 1 particle indices, num_chunks a multiple of 15 = the chunks of one tile, the tail
+ * padded with empty chunks), one species byte per particle, and the species table (256 rows of 8 floats: m_hi, m_lo,
+ * 1/M_residue hi, meta bits, mu_hi, mu_lo, 1/M_residue lo, m_partner/(m + m_partner); row 255 = "no particle").
+ * TGNH_ERR_UNSUPPORTED when the system does not qualify (mixed / double layout, a residue of more than 32 particles, more than
+ * 255 species): such systems run through the first-generation kernels (tgnh_plan_tiles).  Any output pointer may be NULL. */
+int tgnh_plan_chunks(const tgnh_params* p, int32_t* chunk_start, int32_t capacity, int32_t* num_chunks, uint8_t* species_out /*[N]*/,
+                     float* table_out /*[256*8]*/, int32_t* num_species, int32_t* max_residue);
+/* 2 when the handle's two halves run through the warp-chunk kernels, 1 otherwise (environment TGNH_V2=0 forces 1) */
+int tgnh_kernel_generation(const tgnh_handle* h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t tgnh_launch_count(const tgnh_handle* h);
 /* Per-launch device timing: while enabled every streaming launch is bracketed by CUDA events on its stream.

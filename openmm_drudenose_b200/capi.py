@@ -23,7 +23,7 @@ SYMBOLS = [
     "tgnh_thermostat", "tgnh_half2", "tgnh_flush",
     "tgnh_step", "tgnh_step_host", "tgnh_set_posq_correction", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
     "tgnh_kinetic_energy", "tgnh_compute_kinetic_energies", "tgnh_get_chain_state", "tgnh_set_chain_state",
-    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_plan_tiles", "tgnh_plan_descriptors", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
+    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_plan_tiles", "tgnh_plan_descriptors", "tgnh_plan_chunks", "tgnh_kernel_generation", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
     "tgnh_comm_create", "tgnh_comm_destroy",
 ]
 
@@ -88,6 +88,8 @@ def lib():
         ip32 = C.POINTER(C.c_int32)
         L.tgnh_plan_tiles.argtypes = [C.POINTER(Params), ip32, C.c_int32, ip32, ip32, ip32]
         L.tgnh_plan_descriptors.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint32)]
+        L.tgnh_plan_chunks.argtypes = [C.POINTER(Params), ip32, C.c_int32, ip32, C.POINTER(C.c_uint8), C.POINTER(C.c_float), ip32, ip32]
+        L.tgnh_kernel_generation.argtypes = [vp]
         L.tgnh_set_profiling.argtypes = [vp, C.c_int]
         L.tgnh_get_profile.argtypes = [vp, dp, C.POINTER(C.c_int64)]
         L.tgnh_comm_get_unique_id.argtypes = [vp]
@@ -169,6 +171,22 @@ def plan_tiles(system, **kw):
     ts = np.zeros(nt.value + 1, np.int32)
     check(lib().tgnh_plan_tiles(C.byref(p), ts.ctypes.data_as(C.POINTER(C.c_int32)), len(ts), C.byref(nt), C.byref(nb), C.byref(uni)))
     return ts, nb.value, bool(uni.value)
+
+
+def plan_chunks(system, **kw):
+    """tgnh_plan_chunks: the warp-chunk plan (csrc/tgnh_v2.cuh), host-only.  Returns (chunk_start[num_chunks + 1],
+    species[N] uint8, table[256, 8] float32, number of species, longest residue); raises TgnhError(ERR_UNSUPPORTED) for
+    systems that run through the first-generation kernels."""
+    p, keep, _ = make_params(system, **kw)
+    nc, ns, mr = C.c_int32(), C.c_int32(), C.c_int32()
+    ip32 = C.POINTER(C.c_int32)
+    check(lib().tgnh_plan_chunks(C.byref(p), None, 0, C.byref(nc), None, None, C.byref(ns), C.byref(mr)))
+    cs = np.zeros(nc.value + 1, np.int32)
+    spec = np.zeros(system.num_particles, np.uint8)
+    table = np.zeros((256, 8), np.float32)
+    check(lib().tgnh_plan_chunks(C.byref(p), cs.ctypes.data_as(ip32), len(cs), C.byref(nc), spec.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                 table.ctypes.data_as(C.POINTER(C.c_float)), C.byref(ns), C.byref(mr)))
+    return cs, spec, table, ns.value, mr.value
 
 
 def plan_descriptors(system, **kw):
@@ -280,6 +298,11 @@ class Handle:
     @property
     def launch_count(self):
         return lib().tgnh_launch_count(self.h)
+
+    @property
+    def kernel_generation(self):
+        """2 = the two halves run through the warp-chunk kernels (tgnh_v2.cuh), 1 = first-generation kernels"""
+        return lib().tgnh_kernel_generation(self.h)
 
     @property
     def exchange_kind(self):

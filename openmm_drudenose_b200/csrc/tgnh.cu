@@ -19,6 +19,10 @@
 #include <vector>
 
 #include "tgnh_kernels.cuh"
+#include "tgnh_v2.cuh"
+
+#include <array>
+#include <map>
 
 using namespace tgnh;
 
@@ -151,6 +155,14 @@ struct tgnh_handle {
     int smemA = 0, smemB = 0, smemKE = 0, smemA1 = 0, smemA2 = 0, smemS = 0, smemK = 0;
     int kindKE = KIND_KE;         // KIND_KU when every residue lies in one temperature group
     bool fuseChain = false;       // small system: reducing launches run the chain update in their last CTA
+    // warp-chunk kernels (tgnh_v2.cuh): single-precision layout, every residue fits a warp, at most 255 species
+    bool v2 = false;
+    unsigned char* dSpec = nullptr;
+    int* dChunkStart = nullptr;
+    float4* dSpecTable = nullptr;
+    int numTiles2 = 0, maxRes = 1, numSpecies = 0;
+    int gridA2v = 0, gridB2v = 0, gridKE2v = 0, smemA2v = 0, smemB2v = 0, smemKE2v = 0;
+    bool earlyOK = false;         // set by tgnh_step around launches whose predecessors in the stream are its own
     // host copies of the thermostat parameters
     std::vector<double> dof, nkbt, etaMass;
     // state machine
@@ -382,7 +394,69 @@ struct HostPlan {
     std::vector<int> tileStart, resStart, tileFirstRes, bigFirst, bigLast;
     double drudeDof = 0, comDof = 0;
     bool uniform = true;
+    // warp-chunk plan (tgnh_v2.cuh); v2 == false when the system does not qualify (v2why says why)
+    bool v2 = false;
+    const char* v2why = "";
+    std::vector<int> chunkStart;
+    std::vector<unsigned char> spec;
+    std::vector<float> specTable;
+    int maxRes = 1, numTiles2 = 0, numSpecies = 0;
 };
+
+// Chunks, species bytes and the species table of the warp-chunk kernels.  Needs the legacy plan's resFirst/resLast/partner/role.
+static void build_plan_v2(const tgnh_params* p, HostPlan& hp) {
+    const int N = p->num_particles, R = p->num_residues;
+    hp.v2 = false;
+    if (p->precision != TGNH_PRECISION_SINGLE) { hp.v2why = "mixed / double precision layout"; return; }
+    int maxRes = 0;
+    for (int r = 0; r < R; r++) maxRes = std::max(maxRes, hp.resLast[r] - hp.resFirst[r] + 1);
+    if (maxRes > 32) { hp.v2why = "a residue has more than 32 particles"; return; }
+    hp.maxRes = maxRes;
+    // residue-aligned chunks of at most 32 particles
+    hp.chunkStart.assign(1, 0);
+    for (int i = 0, cur = 0; i < N;) {
+        const int r = p->particle_res_id[i], len = hp.resLast[r] - hp.resFirst[r] + 1;
+        if (cur + len > 32) { hp.chunkStart.push_back(i); cur = 0; }
+        cur += len;
+        i += len;
+    }
+    const int numChunks = (int)hp.chunkStart.size();
+    hp.numTiles2 = (numChunks + V2_NCONS - 1) / V2_NCONS;
+    hp.chunkStart.resize((size_t)V2_NCONS * hp.numTiles2 + 1, N);
+    // species: particles that agree in everything the kernels look up per particle
+    std::map<std::array<uint64_t, 4>, int> rows;
+    hp.spec.assign((size_t)((N + 15) & ~15) + 32, (unsigned char)V2_NULL);
+    hp.specTable.assign((size_t)V2_ROWS * V2_ROW_F4 * 4, 0.f);
+    auto bits = [](double x) { uint64_t b; memcpy(&b, &x, 8); return b; };
+    auto put_row = [&](int row, double m, double mu, double invM, double fpartner, uint32_t meta) {
+        float* q = &hp.specTable[(size_t)row * V2_ROW_F4 * 4];
+        const float mh = (float)m, muh = (float)mu, ih = (float)invM;
+        float metaf;
+        memcpy(&metaf, &meta, 4);
+        q[0] = mh; q[1] = (float)(m - (double)mh); q[2] = ih; q[3] = metaf;
+        q[4] = muh; q[5] = (float)(mu - (double)muh); q[6] = (float)(invM - (double)ih); q[7] = (float)fpartner;
+    };
+    put_row(V2_NULL, 0.0, 0.0, 0.0, 0.0, v2_meta_pack(0, ROLE_NORMAL, true, 0));
+    for (int i = 0; i < N; i++) {
+        const int r = p->particle_res_id[i];
+        const double m = p->masses[i], mj = hp.partner[i] ? p->masses[i + hp.partner[i]] : 0.0;
+        double M = 0.0;
+        for (int j = hp.resFirst[r]; j <= hp.resLast[r]; j++) M += p->masses[j];      // particle order, as calcCOMVelocities sums (:90-100)
+        const uint32_t meta = v2_meta_pack(p->particle_temp_group[i], hp.role[i], i == hp.resFirst[r], hp.partner[i]);
+        const std::array<uint64_t, 4> key = {bits(m), bits(mj), bits(M), (uint64_t)meta};
+        auto it = rows.find(key);
+        if (it == rows.end()) {
+            if ((int)rows.size() >= V2_NULL) { hp.v2why = "more than 255 particle species"; return; }
+            const int row = (int)rows.size();
+            it = rows.emplace(key, row).first;
+            const bool pair = hp.partner[i] != 0;
+            put_row(row, m, pair ? m * mj / (m + mj) : 0.0, M > 0.0 ? 1.0 / M : 0.0, pair ? mj / (m + mj) : 0.0, meta);
+        }
+        hp.spec[i] = (unsigned char)it->second;
+    }
+    hp.numSpecies = (int)rows.size();
+    hp.v2 = true;
+}
 
 static int build_plan(const tgnh_params* p, HostPlan& hp) {
     const int N = p->num_particles, P = p->num_pairs, R = p->num_residues, G = p->num_temp_groups;
@@ -519,7 +593,34 @@ static int build_plan(const tgnh_params* p, HostPlan& hp) {
         while (resStart.size() & 3) resStart.push_back(N);
     }
     (void)T;
+    build_plan_v2(p, hp);
     return TGNH_OK;
+}
+
+static StreamKernel pick_v2(int kind, int ffmt, bool useCOM, bool hardwall) {
+    if (kind == V2_A) {
+        if (ffmt) return useCOM ? (hardwall ? tgnh_v2_kernel<V2_A, 1, true, true> : tgnh_v2_kernel<V2_A, 1, true, false>)
+                                : (hardwall ? tgnh_v2_kernel<V2_A, 1, false, true> : tgnh_v2_kernel<V2_A, 1, false, false>);
+        return useCOM ? (hardwall ? tgnh_v2_kernel<V2_A, 0, true, true> : tgnh_v2_kernel<V2_A, 0, true, false>)
+                      : (hardwall ? tgnh_v2_kernel<V2_A, 0, false, true> : tgnh_v2_kernel<V2_A, 0, false, false>);
+    }
+    if (kind == V2_B) {
+        if (ffmt) return useCOM ? tgnh_v2_kernel<V2_B, 1, true, false> : tgnh_v2_kernel<V2_B, 1, false, false>;
+        return useCOM ? tgnh_v2_kernel<V2_B, 0, true, false> : tgnh_v2_kernel<V2_B, 0, false, false>;
+    }
+    return useCOM ? tgnh_v2_kernel<V2_KE, 0, true, false> : tgnh_v2_kernel<V2_KE, 0, false, false>;
+}
+static StreamKernel pick_v2_fused(int kind, int ffmt, bool useCOM) {
+    if (kind == V2_B) {
+        if (ffmt) return useCOM ? tgnh_v2_chain_kernel<V2_B, 1, true> : tgnh_v2_chain_kernel<V2_B, 1, false>;
+        return useCOM ? tgnh_v2_chain_kernel<V2_B, 0, true> : tgnh_v2_chain_kernel<V2_B, 0, false>;
+    }
+    return useCOM ? tgnh_v2_chain_kernel<V2_KE, 0, true> : tgnh_v2_chain_kernel<V2_KE, 0, false>;
+}
+static int smem_v2(int kind, int ffmt, int T) {
+    if (kind == V2_A) return ffmt ? V2Layout<V2_A, 1>::bytes(T) : V2Layout<V2_A, 0>::bytes(T);
+    if (kind == V2_B) return ffmt ? V2Layout<V2_B, 1>::bytes(T) : V2Layout<V2_B, 0>::bytes(T);
+    return V2Layout<V2_KE, 0>::bytes(T);
 }
 
 extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
@@ -685,7 +786,54 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
                 }
             }
     }
+    // ---- warp-chunk kernels ----
+    {
+        const char* e = getenv("TGNH_V2");
+        h->v2 = hp.v2 && !(e && atoi(e) == 0);
+        if (h->v2) {
+            h->numTiles2 = hp.numTiles2; h->maxRes = hp.maxRes; h->numSpecies = hp.numSpecies;
+            if (!dmalloc((void**)&h->dSpec, hp.spec.size()) || !dmalloc((void**)&h->dChunkStart, hp.chunkStart.size() * 4) ||
+                !dmalloc((void**)&h->dSpecTable, hp.specTable.size() * 4))
+                return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the species tables failed"));
+            cudaMemcpy(h->dSpec, hp.spec.data(), hp.spec.size(), cudaMemcpyHostToDevice);
+            cudaMemcpy(h->dChunkStart, hp.chunkStart.data(), hp.chunkStart.size() * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(h->dSpecTable, hp.specTable.data(), hp.specTable.size() * 4, cudaMemcpyHostToDevice);
+            int* grids[3] = {&h->gridA2v, &h->gridB2v, &h->gridKE2v};
+            int* smems[3] = {&h->smemA2v, &h->smemB2v, &h->smemKE2v};
+            for (int kind = 0; kind < 3 && h->v2; kind++) {
+                StreamKernel k = pick_v2(kind, h->ffmt, h->useCOM, h->hardwall);
+                const int smem = smem_v2(kind, h->ffmt, h->T);
+                int occ = 0;
+                if (smem > 227 * 1024 || cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, 512, smem) != cudaSuccess || occ < 1) {
+                    (void)cudaGetLastError();
+                    h->v2 = false;              // e.g. 30 temperature groups: the energy columns do not fit beside the ring
+                    break;
+                }
+                int g = occ * h->numSMs;
+                if (g > h->numTiles2) g = h->numTiles2;
+                *grids[kind] = g < 1 ? 1 : g;
+                *smems[kind] = smem;
+            }
+            if (h->v2 && h->fuseChain) {
+                h->fuseChain = h->numTiles2 <= h->numSMs;
+                for (int kind : {V2_B, V2_KE}) {
+                    if (!h->fuseChain) break;
+                    if (cudaFuncSetAttribute((const void*)pick_v2_fused(kind, h->ffmt, h->useCOM), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             smem_v2(kind, h->ffmt, h->T)) != cudaSuccess) {
+                        (void)cudaGetLastError();
+                        h->fuseChain = false;
+                    }
+                }
+            }
+        }
+    }
     int maxGrid = h->gridA > h->gridB ? h->gridA : h->gridB;
+    if (h->gridA2v > maxGrid) maxGrid = h->gridA2v;
+    if (h->gridB2v > maxGrid) maxGrid = h->gridB2v;
+    if (h->gridKE2v > maxGrid) maxGrid = h->gridKE2v;
+    if (h->numTiles2 > maxGrid && h->fuseChain) maxGrid = h->numTiles2;
+    if (h->numTiles > maxGrid && h->fuseChain) maxGrid = h->numTiles;
     if (h->gridKE > maxGrid) maxGrid = h->gridKE;
     if (h->gridA1 > maxGrid) maxGrid = h->gridA1;
     if (h->gridA2 > maxGrid) maxGrid = h->gridA2;
@@ -721,12 +869,36 @@ extern "C" int tgnh_plan_descriptors(const tgnh_params* p, uint32_t* desc_out) {
     return TGNH_OK;
 }
 
+extern "C" int tgnh_plan_chunks(const tgnh_params* p, int32_t* chunk_start, int32_t capacity, int32_t* num_chunks, uint8_t* species_out,
+                                float* table_out, int32_t* num_species, int32_t* max_residue) {
+    if (!p) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    if (int rc = validate_params(p)) return rc;
+    HostPlan hp;
+    if (int rc = build_plan(p, hp)) return rc;
+    if (!hp.v2) return fail(TGNH_ERR_UNSUPPORTED, "the warp-chunk kernels do not cover this system: %s", hp.v2why);
+    const int n = V2_NCONS * hp.numTiles2;
+    if (num_chunks) *num_chunks = n;
+    if (num_species) *num_species = hp.numSpecies;
+    if (max_residue) *max_residue = hp.maxRes;
+    if (chunk_start) {
+        if (capacity < n + 1) return fail(TGNH_ERR_INVALID_ARGUMENT, "chunk_start holds %d entries, %d are needed", capacity, n + 1);
+        for (int i = 0; i <= n; i++) chunk_start[i] = hp.chunkStart[i];
+    }
+    if (species_out) memcpy(species_out, hp.spec.data(), p->num_particles);
+    if (table_out)
+        for (int r = 0; r < V2_ROWS; r++) memcpy(table_out + 8 * r, &hp.specTable[(size_t)r * V2_ROW_F4 * 4], 32);
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_kernel_generation(const tgnh_handle* h) { return h ? (h->v2 ? 2 : 1) : 0; }
+
 extern "C" void tgnh_destroy(tgnh_handle* h) {
     if (!h) return;
     for (int r = 0; r < MAX_PEERS; r++)
         if (h->peers.inbox[r] && h->peers.inbox[r] != h->dInbox) cudaIpcCloseMemHandle(h->peers.inbox[r]);
     cudaFree(h->dInbox);
     cudaFree(h->dDesc); cudaFree(h->dTileStart); cudaFree(h->dResStart); cudaFree(h->dTileFirstRes); cudaFree(h->dBigFirst); cudaFree(h->dBigLast); cudaFree(h->dBigCom); cudaFree(h->dChain); cudaFree(h->dPartials); cudaFree(h->dTicket);
+    cudaFree(h->dSpec); cudaFree(h->dChunkStart); cudaFree(h->dSpecTable);
     cudaFree(h->hsVelm); cudaFree(h->hsPosq); cudaFree(h->hsForce);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     if (h->hsStream) cudaStreamDestroy(h->hsStream);
@@ -774,7 +946,7 @@ static int launch_chain(tgnh_handle* h, cudaStream_t s, int mode, bool gather = 
 // kinetic-energy vector when sharded and by the chain update `chainMode` asks for
 static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, void* posq, const void* force, int applyScale, int chainMode,
                          void* posDelta = nullptr) {
-    StreamArgs a;
+    StreamArgs a{};
     a.velm = velm; a.posq = posq; a.posqCorrection = (float4*)h->posqCorrection; a.force = force; a.posDelta = posDelta;
     if (h->prec == TGNH_PRECISION_MIXED && posq != nullptr && h->posqCorrection == nullptr)
         return fail(TGNH_ERR_INVALID_ARGUMENT, "mixed precision: register the posqCorrection array with tgnh_set_posq_correction first");
@@ -833,7 +1005,17 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     }
     const bool fused = h->fuseChain && reduces && chainMode != CHAIN_NONE && (kind == h->kindB || (kind == h->kindKE && !applyScale));
     a.fusedChainMode = fused ? chainMode : CHAIN_NONE;
-    if (fused) CUDA_TRY(launch_pdl(pick_fused(kind, h->ffmt, h->prec, h->useCOM), h->numTiles, TILE, smem, s, (const StreamArgs)a));
+    a.earlyLoads = h->earlyOK ? 1 : 0;
+    // the two halves and the plain reduction run through the warp-chunk kernels where the system qualifies
+    const int kind2 = !h->v2 ? -1 : kind == KIND_A ? V2_A : kind == h->kindB ? V2_B : (kind == h->kindKE && !applyScale) ? V2_KE : -1;
+    if (kind2 >= 0) {
+        a.spec = h->dSpec; a.chunkStart = h->dChunkStart; a.specTable = h->dSpecTable; a.maxRes = h->maxRes;
+        a.numTiles = h->numTiles2;
+        const int grid2 = kind2 == V2_A ? h->gridA2v : kind2 == V2_B ? h->gridB2v : h->gridKE2v;
+        const int smem2 = kind2 == V2_A ? h->smemA2v : kind2 == V2_B ? h->smemB2v : h->smemKE2v;
+        if (fused) CUDA_TRY(launch_pdl(pick_v2_fused(kind2, h->ffmt, h->useCOM), h->numTiles2, 512, smem2, s, (const StreamArgs)a));
+        else CUDA_TRY(launch_pdl(pick_v2(kind2, h->ffmt, h->useCOM, h->hardwall), grid2, 512, smem2, s, (const StreamArgs)a));
+    } else if (fused) CUDA_TRY(launch_pdl(pick_fused(kind, h->ffmt, h->prec, h->useCOM), h->numTiles, TILE, smem, s, (const StreamArgs)a));
     else CUDA_TRY(launch_pdl(k, grid, TILE, smem, s, (const StreamArgs)a));
     if (e1) CUDA_TRY(cudaEventRecord(e1, s));
     h->launches++;
@@ -950,8 +1132,12 @@ extern "C" int tgnh_step(tgnh_handle* h, void* stream, void* velm, void* posq, c
         return TGNH_OK;
     }
     if (int rc = ensure_ke(h, s, velm, CHAIN_FIRST)) return rc;
+    struct EarlyGuard { tgnh_handle* h; ~EarlyGuard() { h->earlyOK = false; } } guard{h};
     for (int i = 0; i < nsteps; i++) {
+        // from the second launch on, everything that can still be running ahead of a launch is this loop's own work, which
+        // writes velm only (and posq in first-half launches that have completed by then): see StreamArgs::earlyLoads
         if (int rc = launch_stream(h, s, KIND_A, velm, posq, force, 1, CHAIN_NONE)) return rc;
+        h->earlyOK = true;
         // the thermostat half-step that ends step i and the one that begins step i+1 run back to back in one
         // chain launch; their scale factors are applied together by the next first-half pass
         const int mode = (i + 1 < nsteps) ? CHAIN_SECOND_FIRST : CHAIN_SECOND;

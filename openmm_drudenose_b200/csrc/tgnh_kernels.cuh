@@ -24,6 +24,9 @@
 //                            reporters) read velocities between steps; residue-uniform groups only, where the scaled
 //                            kinetic energies are s_g^2 KE_g and need no second reduction
 //
+// (The two halves and the plain reduction of single-precision systems whose residues fit a warp run through the second
+// generation of these kernels, tgnh_v2.cuh; this template serves every other case.)
+//
 // Data movement: every CTA is persistent and walks residue-aligned tiles of <= 512 consecutive
 // particles.  One elected thread streams each tile's velm / posq / force / descriptor slices into a
 // ring of shared-memory stages with cp.async.bulk (TMA) completing on a "full" mbarrier; warps hand a
@@ -86,6 +89,13 @@ struct StreamArgs {
     int reverse;              // walk the tiles from the last to the first (see "L2 hand-over" below)
     int prologuePrefetch;     // tiles per CTA whose read-only inputs are prefetched into L2 before griddepcontrol.wait
     int fusedChainMode;       // tgnh_stream_chain_kernel: the chain update the last CTA runs (ChainMode)
+    int earlyLoads;           // the launches that precede this one in the stream are this library's own and write neither
+                              // posq, forces nor posqCorrection: those tiles may be requested before griddepcontrol.wait
+    // warp-chunk kernels (tgnh_v2.cuh)
+    const unsigned char* spec;   // [roundup16(N) + 32] species-table row of every particle
+    const int* chunkStart;       // [15 * numTiles + 1] first particle of every chunk (tail padded with N)
+    const float4* specTable;     // [256 * 3] species table (q0, q1, pad)
+    int maxRes;                  // particles in the longest residue (<= 32)
     double* partials;         // [gridDim.x][T]
     unsigned int* ticket;     // last-CTA-done counter (self-resetting)
     ChainView chain;
@@ -445,13 +455,16 @@ __device__ __forceinline__ bool stream_body(const StreamArgs& a) {
             if (St::HAS_P) bulk_g2s(st + St::OFF_P, gdelta + start, n * St::VB, bar, polOnce);   // written by the caller's constraint kernels
         }
     };
-    if (tid == 0) {
+    // Only inside tgnh_step's own launch sequence (a.earlyLoads) are forces / posq known not to be written by the launches
+    // this one may overlap with; behind foreign kernels (OpenMM's force, constraint, virtual-site kernels) every input is
+    // requested after the wait.
+    if (tid == 0 && a.earlyLoads) {
         for (int it = 0; it < NS && it < myTiles; it++) issue(it, 1);
         for (int it = NS; it < NS + a.prologuePrefetch; it++) prefetch(it);
     }
     pdl_wait();                                         // everything below reads what earlier launches wrote
     if (tid == 0)
-        for (int it = 0; it < NS && it < myTiles; it++) issue(it, 2);
+        for (int it = 0; it < NS && it < myTiles; it++) issue(it, a.earlyLoads ? 2 : 3);
     if (tid < T) {
         const double sg = (KIND == KIND_B || KIND == KIND_BU || KIND == KIND_A2 || KIND == KIND_K || KIND == KIND_KU) ? 1.0 : a.chain.scaleA[tid];
         ssq[tid] = sg * sg;

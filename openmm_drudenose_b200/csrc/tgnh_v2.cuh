@@ -1,0 +1,381 @@
+// Second generation of the streaming kernels of the TGNH step ("warp-chunk" kernels), single-precision layout.
+//
+// Same operators as tgnh_kernels.cuh (reference: platforms/cuda/src/kernels/drudeTGNH.cu)
+//   V2_A   first half   = integrateDrudeTGNHChain + integrateDrudeTGNHVelocities(updatePosDelta) +
+//                         integrateDrudeTGNHPositions + applyHardWallConstraints          (:249-301, 307-365, 435-466, 471-574)
+//   V2_B   second half  = integrateDrudeTGNHVelocities + calcCOMVelocities + normalizeVelocities +
+//                         computeNormalizedKineticEnergies + sumNormalizedKineticEnergies (:307-365, 82-133, 138-242)
+//   V2_KE  reduce       = the kinetic-energy reduction alone                              (:82-242)
+// with a different decomposition of the work, chosen from the round-1 profile of the second-half kernel (58.8 M warp
+// instructions, 40 % XU pipe, 7.5 M shared-memory bank conflicts, all warps of a CTA coupled through the slowest one):
+//
+//  * WARP-CHUNKS.  The particles are cut into residue-aligned chunks of at most 32 consecutive particles, one per warp
+//    and tile (15 chunks = at most 480 particles per tile).  A Drude pair lies inside a residue, a residue inside a
+//    chunk, so the pair partner and all members of the residue are lanes of the same warp: partner values travel by
+//    one shuffle, residue sums by a segmented warp scan.  No thread reads another warp's particles, nothing is gathered
+//    from shared memory with a stride (no bank conflicts), and no warp waits for another one inside a tile.
+//  * SPECIES TABLE.  Everything that is constant per kind of particle — mass, reduced mass of its Drude pair, mass
+//    fraction of the partner, inverse mass of its residue, temperature group, role, partner offset, "first particle of
+//    the residue" — sits in a table of at most 255 rows in shared memory, indexed by ONE BYTE per particle (instead
+//    of a 4-byte descriptor word per particle and kernel).  Masses are stored as float pairs (hi + lo = the double the
+//    caller passed in System::getParticleMass): the kinetic-energy sums are unbiased per species (a mass rounded to
+//    fp32 would shift a thermostat's energy systematically and the Nose-Hoover chain integrates that), yet the inner
+//    loop contains no reciprocal, no float<->double conversion and no fp64 instruction at all.
+//  * PRODUCER WARP.  Warp 15 only streams: it waits for a stage to be released by the 15 consumer warps and requests the
+//    next tile (cp.async.bulk / UBLKCP completing on the stage's mbarrier).  No consumer ever blocks on a refill.
+//  * fp32 running sums per thread, moved into the thread's fp64 column every 16 tiles; fp64 from there on (warp
+//    shuffles -> CTA -> fixed-order sum over the CTAs by the last one), bit-reproducible run to run.
+//
+// Kinetic energies, in the reference's own form (:152-188) with V the residue's centre-of-mass velocity:
+//     group tg:   sum_i m_i |v_i - V|^2  -  sum_pairs mu |v_d - v_p|^2      (= sum (m_d+m_p) |cm - V|^2 + normal particles)
+//     COM group:  sum_res |P|^2 / M ,  P = sum_i m_i v_i
+//     Drude:      sum_pairs mu |v_d - v_p|^2
+// valid whether or not a residue lies in one temperature group.
+#pragma once
+#include "tgnh_kernels.cuh"
+
+namespace tgnh {
+
+enum { V2_A = 0, V2_B = 1, V2_KE = 2 };
+constexpr int V2_NCONS = 15;                  // consumer warps per CTA (warp 15 is the producer)
+constexpr int V2_TILE = V2_NCONS * 32;        // particles per tile, at most
+constexpr int V2_FW = V2_TILE + 8;            // 4-aligned window of force components that covers any tile
+constexpr int V2_SW = V2_TILE + 32;           // 16-aligned window of species bytes that covers any tile
+constexpr int V2_ROWS = 256;                  // species table rows (row 255 = "no particle")
+constexpr int V2_NULL = 255;
+constexpr int V2_ROW_F4 = 3;                  // float4 per row: q0, q1, pad (48 B stride: neighbouring rows fall into different banks)
+
+// species-table row
+//   q0 = { m_hi, m_lo, 1/M_res (hi), meta }          meta: [4:0] temperature group, [6:5] role, [7] first particle of its
+//   q1 = { mu_hi, mu_lo, 1/M_res (lo), f_partner }         residue, [15:8] signed offset to the pair partner (0 = none)
+__host__ __device__ inline uint32_t v2_meta_pack(int tg, uint32_t role, bool first, int partner) {
+    return (uint32_t)(tg & 31) | (role << 5) | (first ? 0x80u : 0u) | ((uint32_t)(partner & 0xff) << 8);
+}
+__device__ __forceinline__ int v2_tg(uint32_t m) { return m & 31; }
+__device__ __forceinline__ uint32_t v2_role(uint32_t m) { return (m >> 5) & 3; }
+__device__ __forceinline__ bool v2_first(uint32_t m) { return (m & 0x80u) != 0; }
+__device__ __forceinline__ int v2_partner(uint32_t m) { return ((int32_t)(m << 16)) >> 24; }
+
+template <int KIND, int FFMT>
+struct V2Layout {
+    static constexpr bool HAS_X = (KIND == V2_A);
+    static constexpr bool HAS_F = (KIND != V2_KE);
+    static constexpr bool HAS_KE = (KIND != V2_A);
+    static constexpr int FBYTES = FFMT == 1 ? 8 : 4;
+    static constexpr int NSTAGE = HAS_X ? 3 : 4;
+    static constexpr int OFF_V = 0;
+    static constexpr int OFF_X = OFF_V + V2_TILE * 16;
+    static constexpr int OFF_F = OFF_X + (HAS_X ? V2_TILE * 16 : 0);
+    static constexpr int OFF_S = OFF_F + (HAS_F ? 3 * V2_FW * FBYTES : 0);
+    static constexpr int OFF_HDR = OFF_S + V2_SW;            // int start, pad[3]; uint16 chunkOff[16]; pad
+    static constexpr int STAGE = OFF_HDR + 64;
+    static constexpr int OFF_BAR = NSTAGE * STAGE;            // full[NS], empty[NS]
+    static constexpr int OFF_TAB = OFF_BAR + 128;
+    static constexpr int OFF_SCALE = OFF_TAB + V2_ROWS * V2_ROW_F4 * 16;   // double[MAX_T] s^2 (unused), double[MAX_T] s - 1
+    static constexpr int OFF_MISC = OFF_SCALE + MAX_T * 16;
+    static constexpr int OFF_WARP = OFF_MISC + 16;            // double[T][16]
+    static constexpr int OFF_KE = OFF_WARP + (HAS_KE ? MAX_T * 16 * 8 : 0);
+    static int bytes(int T) { return OFF_KE + (HAS_KE ? T * V2_TILE * 8 : 0); }
+};
+
+template <int FFMT>
+__device__ __forceinline__ V3<float> v2_force(const unsigned char* sF, int idx) {
+    if (FFMT == 1) {
+        const long long* f = reinterpret_cast<const long long*>(sF);
+        return v3((float)f[idx], (float)f[V2_FW + idx], (float)f[2 * V2_FW + idx]);
+    }
+    const float* f = reinterpret_cast<const float*>(sF);
+    return v3(f[idx], f[V2_FW + idx], f[2 * V2_FW + idx]);
+}
+
+// (hi + lo) * x with one rounding of the large term: hi * x + lo * x
+__device__ __forceinline__ float mul2(float hi, float lo, float x) { return fmaf(hi, x, lo * x); }
+
+// Inclusive segmented scan of a vector over the lanes of a warp.  Segments are the residues of the chunk (contiguous
+// lanes, the first lane of each flagged in firstMask); on return the LAST lane of every segment holds the segment's sum.
+__device__ __forceinline__ void seg_scan(V3<float>& p, int lane, int segStart, int maxRes) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        if (o < maxRes) {                               // warp-uniform: no residue of this system is longer
+            const float tx = __shfl_up_sync(0xffffffffu, p.x, o), ty = __shfl_up_sync(0xffffffffu, p.y, o), tz = __shfl_up_sync(0xffffffffu, p.z, o);
+            if (lane - o >= segStart) { p.x += tx; p.y += ty; p.z += tz; }
+        }
+    }
+}
+
+// Body of the warp-chunk kernels.  Returns true in the one CTA that finished the grid-wide energy reduction (all threads of it).
+template <int KIND, int FFMT, bool USE_COM, bool HARDWALL>
+__device__ __forceinline__ bool v2_body(const StreamArgs& a) {
+    using L = V2Layout<KIND, FFMT>;
+    constexpr int NS = L::NSTAGE;
+    constexpr bool IS_A = (KIND == V2_A);
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    uint64_t* empty = full + NS;
+    float4* stab = reinterpret_cast<float4*>(smem + L::OFF_TAB);
+    double* seps = reinterpret_cast<double*>(smem + L::OFF_SCALE) + MAX_T;      // s_g - 1
+    int* smisc = reinterpret_cast<int*>(smem + L::OFF_MISC);
+    double* swarp = reinterpret_cast<double*>(smem + L::OFF_WARP);
+    double* ske = reinterpret_cast<double*>(smem + L::OFF_KE);
+    float4* gvelm = static_cast<float4*>(a.velm);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = a.chain.T, G = a.chain.G;
+    const int myTiles = blockIdx.x < a.numTiles ? (a.numTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto tile_of = [&](int it) {
+        const int t = blockIdx.x + it * gridDim.x;
+        return a.reverse ? a.numTiles - 1 - t : t;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], V2_NCONS); }
+        fence_mbar_init();
+    }
+    for (int i = tid; i < V2_ROWS * V2_ROW_F4; i += 512) stab[i] = __ldg(a.specTable + i);     // static table: safe before pdl_wait
+    if (L::HAS_KE && tid < V2_TILE)
+        for (int g = 0; g < T; g++) ske[g * V2_TILE + tid] = 0.0;
+    __syncthreads();
+
+    const uint64_t polOnce = policy_evict_first();
+    // Producer: request tile `it` of this CTA into its stage (the whole warp calls; lane 0 issues the copies).
+    // parts: 1 = header + everything no launch of this library writes (posq, forces, species bytes), arms the barrier with
+    // the full byte count; 2 = velm; 3 = both.  `cs` = chunkStart[15 * tile + lane] for lanes 0..15.
+    auto issue = [&](int it, int parts, int cs) {
+        const int start = __shfl_sync(0xffffffffu, cs, 0), end = __shfl_sync(0xffffffffu, cs, V2_NCONS);
+        const int n = end - start;
+        unsigned char* st = smem + (it % NS) * L::STAGE;
+        uint64_t* bar = &full[it % NS];
+        const int f0 = start & ~3, fn = ((end + 3) & ~3) - f0;            // 16-byte aligned windows
+        const int s0 = start & ~15, sn = ((end + 15) & ~15) - s0;
+        if (parts & 1) {
+            if (lane == 0) *reinterpret_cast<int*>(st + L::OFF_HDR) = start;
+            if (lane <= V2_NCONS) reinterpret_cast<unsigned short*>(st + L::OFF_HDR + 16)[lane] = (unsigned short)(cs - start);
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t bytes = n * 16 + sn;
+                if (L::HAS_X) bytes += n * 16;
+                if (L::HAS_F) bytes += 3 * fn * L::FBYTES;
+                mbar_arrive_expect_tx(bar, bytes);
+                if (L::HAS_X) bulk_g2s(st + L::OFF_X, static_cast<const float4*>(a.posq) + start, n * 16, bar, polOnce);
+                if (L::HAS_F) {
+                    const unsigned char* f = static_cast<const unsigned char*>(a.force);
+                    for (int c = 0; c < 3; c++)
+                        bulk_g2s(st + L::OFF_F + c * V2_FW * L::FBYTES, f + ((size_t)c * a.paddedN + f0) * L::FBYTES, fn * L::FBYTES, bar, polOnce);
+                }
+                bulk_g2s(st + L::OFF_S, a.spec + s0, sn, bar, polOnce);
+            }
+        }
+        if ((parts & 2) && lane == 0) bulk_g2s(st + L::OFF_V, gvelm + start, n * 16, bar, polOnce);
+    };
+    auto chunk_bounds = [&](int it) { return lane <= V2_NCONS ? __ldg(a.chunkStart + V2_NCONS * tile_of(it) + lane) : 0; };
+
+    const bool producer = warp == V2_NCONS;
+    // prologue: inputs that no earlier launch of this stream can still be writing may be requested before griddepcontrol.wait
+    // (only when the host knows that the preceding launches are this library's own and do not write them: a.earlyLoads)
+    if (producer && a.earlyLoads)
+        for (int it = 0; it < NS && it < myTiles; it++) issue(it, 1, chunk_bounds(it));
+    pdl_wait();                                         // everything below reads what earlier launches wrote
+    if (tid < T) seps[tid] = (IS_A ? a.chain.scaleA[tid] : 1.0) - 1.0;
+    __syncthreads();
+
+    float accT = 0.f, accCOM = 0.f, accDrude = 0.f;    // this thread's running sums (fp32, flushed every 16 tiles)
+    int curTg = -1;
+    auto flush = [&]() {
+        if (curTg >= 0) ske[curTg * V2_TILE + tid] += (double)accT;
+        ske[G * V2_TILE + tid] += (double)accCOM;
+        ske[(G + 1) * V2_TILE + tid] += (double)accDrude;
+        accT = accCOM = accDrude = 0.f;
+    };
+
+    if (producer) {
+        for (int it = 0; it < myTiles; it++) {
+            const int cs = chunk_bounds(it);
+            if (it >= NS) mbar_wait(&empty[it % NS], ((it / NS) - 1) & 1);
+            issue(it, (a.earlyLoads && it < NS) ? 2 : 3, cs);
+        }
+    } else {
+        const float eCOM = IS_A ? (float)seps[G] : 0.f, eDrude = IS_A ? (float)seps[G + 1] : 0.f;
+        const float dt = (float)a.dt, fscale = (float)a.fscale, rmax = (float)a.rmax, rmax2 = rmax * rmax;
+        const int maxRes = USE_COM ? a.maxRes : 1;
+        for (int it = 0; it < myTiles; it++) {
+            const int stg = it % NS;
+            unsigned char* st = smem + stg * L::STAGE;
+            const float4* sv = reinterpret_cast<const float4*>(st + L::OFF_V);
+            const float4* sx = reinterpret_cast<const float4*>(st + L::OFF_X);
+            const unsigned char* sF = st + L::OFF_F;
+            const unsigned char* sS = st + L::OFF_S;
+            mbar_wait(&full[stg], (it / NS) & 1);
+            const int start = *reinterpret_cast<const int*>(st + L::OFF_HDR);
+            const unsigned short* co = reinterpret_cast<const unsigned short*>(st + L::OFF_HDR + 16);
+            const int c0 = co[warp], cn = co[warp + 1] - c0;
+            const bool active = lane < cn;
+            const int i = c0 + lane;                                 // index inside the tile
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            int sp = V2_NULL;
+            V3<float> F = v3(0.f, 0.f, 0.f);
+            if (active) {
+                v4 = sv[i];
+                sp = sS[(start & 15) + i];
+                if (L::HAS_F) F = v2_force<FFMT>(sF, (start & 3) + i);
+            }
+            const float4 q0 = stab[sp * V2_ROW_F4];
+            const uint32_t meta = __float_as_uint(q0.w);
+            const int tg = v2_tg(meta);
+            const uint32_t role = v2_role(meta);
+            const int pl = lane + v2_partner(meta);                   // lane of the pair partner (this lane for ordinary particles)
+            const V3<float> v = xyz(v4);
+            const float w = v4.w;
+            const bool massive = w != 0.f;
+            const float fw = fscale * w;
+            // residue segments of this chunk
+            const uint32_t firstMask = __ballot_sync(0xffffffffu, v2_first(meta));
+            const uint32_t below = firstMask & (0xffffffffu >> (31 - lane)), above = firstMask & ~(0xffffffffu >> (31 - lane));
+            const int segStart = 31 - __clz(below);
+            const int lastLane = above ? __ffs(above) - 2 : 31;
+
+            if (IS_A) {
+                // thermostat scaling (integrateDrudeTGNHChain, drudeTGNH.cu:255-300) in the unified form of tgnh_kernels.cuh,
+                // half kick (:314-364), drift (:438-465), hard wall (:474-573)
+                const float4 q1 = stab[sp * V2_ROW_F4 + 1];
+                V3<float> V = v3(0.f, 0.f, 0.f);
+                if (USE_COM) {
+                    V3<float> p = q0.x * v;                          // V only feeds the corrections (sT-1)(v-V), (sCOM-1)V: fp32 masses are ample
+                    seg_scan(p, lane, segStart, maxRes);
+                    V = v3(__shfl_sync(0xffffffffu, p.x, lastLane), __shfl_sync(0xffffffffu, p.y, lastLane), __shfl_sync(0xffffffffu, p.z, lastLane));
+                    V = q0.z * V;
+                }
+                const V3<float> vj = v3(__shfl_sync(0xffffffffu, v.x, pl), __shfl_sync(0xffffffffu, v.y, pl), __shfl_sync(0xffffffffu, v.z, pl));
+                const V3<float> rel = vj - v;
+                const float eT = (float)seps[tg];
+                V3<float> vn = scaled_velocity(v, eT, v - V, eCOM, V, (eT - eDrude) * q1.w, rel);
+                vn = kicked(vn, fw, F);
+                float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active) x4 = sx[i];
+                const V3<float> x = xyz(x4);
+                V3<float> xn = axpy(dt, vn, x);
+                if (HARDWALL) {
+                    // the partner's new velocity and old position, as its own lane computed them: both lanes of a pair see
+                    // bit-identical operands and take the same side of the wall test
+                    V3<float> vjn = v3(__shfl_sync(0xffffffffu, vn.x, pl), __shfl_sync(0xffffffffu, vn.y, pl), __shfl_sync(0xffffffffu, vn.z, pl));
+                    const V3<float> xj = v3(__shfl_sync(0xffffffffu, x.x, pl), __shfl_sync(0xffffffffu, x.y, pl), __shfl_sync(0xffffffffu, x.z, pl));
+                    const float wj = __shfl_sync(0xffffffffu, w, pl);
+                    if (role != ROLE_NORMAL) {
+                        // displacement from the exact difference of the old positions plus the relative drift (no cancellation
+                        // of two rounded box-sized coordinates); the parent forms -(that) with the operands swapped, bit for bit
+                        const V3<float> dDP = role == ROLE_DRUDE ? axpy(dt, vn - vjn, x - xj) : axpy(dt, vjn - vn, xj - x);   // Drude minus parent
+                        const float r2 = dot3(dDP);
+                        if (r2 > rmax2) {                             // rInv*maxDrudeDistance < 1  (drudeTGNH.cu:490)
+                            V3<float> xjn = axpy(dt, vjn, xj);
+                            if (role == ROLE_DRUDE) hard_wall(dDP, r2, xn, xjn, vn, vjn, w, wj, rmax, (float)a.hardwallScale, dt);
+                            else hard_wall(dDP, r2, xjn, xn, vjn, vn, wj, w, rmax, (float)a.hardwallScale, dt);
+                        }
+                    }
+                }
+                if (active && massive) {
+                    st_global(gvelm + start + i, pack4(vn, w));
+                    st_stream(static_cast<float4*>(a.posq) + start + i, make_float4(xn.x, xn.y, xn.z, x4.w));
+                }
+            } else {
+                // half kick (integrateDrudeTGNHVelocities, :314-364; V2_KE: F = 0, nothing stored), then the energies of
+                // what was stored
+                const V3<float> vn = kicked(v, fw, F);
+                if (KIND == V2_B && active && massive) st_global(gvelm + start + i, pack4(vn, w));
+                V3<float> V = v3(0.f, 0.f, 0.f);
+                float keC = 0.f;
+                const bool first = v2_first(meta);
+                const bool needQ1 = role == ROLE_DRUDE || (USE_COM && first);
+                float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (needQ1) q1 = stab[sp * V2_ROW_F4 + 1];
+                if (USE_COM) {
+                    // calcCOMVelocities (:86-105): P = sum m v over the residue, V = P / M
+                    V3<float> p = v3(mul2(q0.x, q0.y, vn.x), mul2(q0.x, q0.y, vn.y), mul2(q0.x, q0.y, vn.z));
+                    seg_scan(p, lane, segStart, maxRes);
+                    const V3<float> P = v3(__shfl_sync(0xffffffffu, p.x, lastLane), __shfl_sync(0xffffffffu, p.y, lastLane), __shfl_sync(0xffffffffu, p.z, lastLane));
+                    V = q0.z * P;
+                    if (first) keC = mul2(q0.z, q1.z, dot3(P));      // |P|^2 / M  (:154), carried by the residue's first particle
+                }
+                // computeNormalizedKineticEnergies (:161-186)
+                const V3<float> r = vn - V;                           // normalizeVelocities (:126-128)
+                float ke = mul2(q0.x, q0.y, dot3(r));
+                const V3<float> vjn = v3(__shfl_sync(0xffffffffu, vn.x, pl), __shfl_sync(0xffffffffu, vn.y, pl), __shfl_sync(0xffffffffu, vn.z, pl));
+                if (role == ROLE_DRUDE) {
+                    const float keD = mul2(q1.x, q1.y, dot3(vjn - vn));   // mu |rel|^2 (:185)
+                    ke -= keD;                                        // m_d |r_d|^2 + m_p |r_p|^2 - mu |rel|^2 = (m_d + m_p) |cm|^2 (:184)
+                    accDrude += keD;
+                }
+                accCOM += keC;
+                if (active && massive) {
+                    if (tg != curTg) {
+                        if (curTg >= 0) { ske[curTg * V2_TILE + tid] += (double)accT; accT = 0.f; }
+                        curTg = tg;
+                    }
+                    accT += ke;
+                }
+                if ((it & 15) == 15) flush();
+            }
+            // hand the stage back: one arrival per consumer warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stg]);
+        }
+    }
+    pdl_launch_dependents();
+    if (!L::HAS_KE) return false;
+
+    // ---- deterministic reduction: thread columns -> warp -> CTA -> (last CTA) grid ----
+    if (!producer) {
+        flush();
+        for (int g = 0; g < T; g++) {
+            double x = ske[g * V2_TILE + tid];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            if (lane == 0) swarp[g * 16 + warp] = x;
+        }
+    }
+    __syncthreads();
+    if (tid < T) {
+        double x = 0.0;
+        for (int w = 0; w < V2_NCONS; w++) x += swarp[tid * 16 + w];
+        a.partials[(size_t)blockIdx.x * T + tid] = x;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        smisc[0] = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!smisc[0]) return false;
+    __threadfence();
+    // last CTA: warp g sums column g of the partials over all CTAs in a fixed order
+    double* out = a.useLocalKE ? a.chain.ke2Local : a.chain.ke2;
+    for (int g = warp; g < T; g += 16) {
+        double x = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) x += __ldcg(a.partials + (size_t)b * T + g);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) out[g] = x;
+    }
+    if (a.peers.world > 1) {
+        // sharded: hand this rank's sums to every rank (this one included) over NVLink
+        __syncthreads();
+        if (tid < a.peers.world) peer_publish(a.peers, out, T, tid);
+    }
+    if (tid == 0) *a.ticket = 0u;
+    return true;
+}
+
+template <int KIND, int FFMT, bool USE_COM, bool HARDWALL>
+__global__ void __launch_bounds__(512, 2) tgnh_v2_kernel(const __grid_constant__ StreamArgs a) {
+    v2_body<KIND, FFMT, USE_COM, HARDWALL>(a);
+}
+
+// Small systems (every CTA owns at most one tile): the CTA that finishes the energy reduction runs the Nose-Hoover chain
+// update itself instead of a separate chain launch (see tgnh_stream_chain_kernel).
+template <int KIND, int FFMT, bool USE_COM>
+__global__ void __launch_bounds__(512, 1) tgnh_v2_chain_kernel(const __grid_constant__ StreamArgs a) {
+    if (!v2_body<KIND, FFMT, USE_COM, false>(a)) return;
+    __syncthreads();                                   // the energy vector written by this CTA's warps
+    if (threadIdx.x < 32) chain_phase(a.chain, a.fusedChainMode, threadIdx.x);
+}
+
+}  // namespace tgnh
