@@ -179,7 +179,7 @@ def run_reference(args):
         "impl": "reference", "metric": "TGNH step particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "sample": sample},
+        "config": {"workload": WORKLOADS[args.workload]},
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -212,24 +212,25 @@ def run_ours(args):
 
     system = make_system(args.workload, rank, world)
     n = system.num_particles
-    padded = ((n + 31) // 32) * 32
-    h_velm = torch.zeros((padded, 4), dtype=torch.float32).pin_memory()
-    h_posq = torch.zeros((padded, 4), dtype=torch.float32).pin_memory()
-    h_force = torch.zeros((3, padded), dtype=torch.float32).pin_memory()
-    h_velm[:n] = torch.from_numpy(system.velm_f32())
-    h_posq[:n] = torch.from_numpy(system.posq_f32())
-    h_force[:, :n] = torch.from_numpy(np.ascontiguousarray(system.forces.T, np.float32))
-    velm, posq, force = h_velm.to(dev), h_posq.to(dev), h_force.to(dev)
+    padded, (h_velm, h_posq, h_force), (velm, posq, force) = device_buffers(torch, system, dev, pinned=True)
     h = capi.Handle(system, padded=padded, device=local, comm=comm)
     tstream = torch.cuda.Stream(device=dev)            # the step runs on its own (non-default) stream
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
+    ptrs = [velm.data_ptr(), posq.data_ptr(), force.data_ptr()]
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps ----
     # The GPU has idled for seconds while the host generated the system; 3 warm-up steps are < 1 ms and do not bring
@@ -246,12 +247,12 @@ def run_ours(args):
             scratch.copy_(velm)
         torch.cuda.synchronize()
     del scratch
-    h.step(velm.data_ptr(), posq.data_ptr(), force.data_ptr(), max(args.warmup, 3), stream)
+    h.step(*ptrs, max(args.warmup, 3), stream)
     launches0 = h.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    h.step(velm.data_ptr(), posq.data_ptr(), force.data_ptr(), args.steps, stream)
+    h.step(*ptrs, args.steps, stream)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -260,37 +261,80 @@ def run_ours(args):
     # CUDA events on the launching stream (kept out of the pass above: an event between two launches serialises
     # them and removes the programmatic-dependent-launch overlap the product path runs with)
     h.set_profiling(True)
-    h.step(velm.data_ptr(), posq.data_ptr(), force.data_ptr(), args.steps, stream)
+    h.step(*ptrs, args.steps, stream)
     barrier()
     prof = h.profile()
     h.set_profiling(False)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms)
     total_particles = n * world
     value = total_particles * args.steps / (ms * 1e-3)
+    generation = h.kernel_generation
 
     # ---- end to end through the C-ABI with HOST buffers: every step copies velm/posq/force in from pinned
     #      memory, runs one step, and copies velm/posq + the 2*KE vector back (tgnh_step_host) ----
     e2e_steps = 0 if args.no_e2e else max(3, min(args.steps, 10))
     ke2 = h.kinetic_energies()
-    if e2e_steps:
-        h.step_host(h_velm.data_ptr(), h_posq.data_ptr(), h_force.data_ptr(), 1)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ke2 = h.step_host(h_velm.data_ptr(), h_posq.data_ptr(), h_force.data_ptr(), 1)
-    barrier()
-    e2e_s = max(time.perf_counter() - t0, 1e-9)
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = total_particles * e2e_steps / e2e_s
-    h2d = n * 16 * 2 + 3 * padded * 4
+
+    def e2e_leg(forces_unchanged):
+        if not e2e_steps:
+            return 0.0
+        k = h.step_host2(h_velm.data_ptr(), h_posq.data_ptr(), h_force.data_ptr(), 1, forces_unchanged=forces_unchanged)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            k = h.step_host2(h_velm.data_ptr(), h_posq.data_ptr(), h_force.data_ptr(), 1, forces_unchanged=forces_unchanged)
+        barrier()
+        nonlocal ke2
+        ke2 = k
+        return total_particles * e2e_steps / max_over_ranks(max(time.perf_counter() - t0, 1e-9))
+
+    e2e_full = e2e_leg(False)          # velm + posq + forces up, velm + posq + energies down, every step
+    e2e_value = e2e_leg(True)          # the bench's forces are fixed: uploaded once, the caller vouches they are unchanged
+    h2d = n * 16 * 2
     d2h = n * 16 * 2 + 8 * h.T
+
+    # ---- further legs, all after the headline's timed region (none of them changes `value`) ----
+    extra = {}
+    if args.workload == "c4" and not args.quick:
+        extra["openmm_call_pattern_ms"] = call_pattern_leg(torch, capi, h, ptrs, stream, barrier)
+        if world > 1:
+            # independent replicas, one full system per GPU, no communication (the reference's only multi-GPU mode,
+            # CudaDrudeTGNHKernelFactory.cpp:62 takes contexts[0])
+            hr = capi.Handle(system, padded=padded, device=local)
+            rms = max_over_ranks(timed_steps(torch, hr, ptrs, args.steps, stream, barrier))
+            hr.close()
+            extra["replicas"] = {"replicas": world, "particles_each": n, "ms_per_step": rms / args.steps, "value": total_particles * args.steps / (rms * 1e-3),
+                                 "what": "independent replicas, one handle per GPU, no exchange"}
+    h_T = h.T
+    exchange_kind = h.exchange_kind
+    if world > 1 and exchange_kind == 2 and not args.quick:
+        # where does the time between the second half and the next first half go?  50 single steps, device timer stamps of the
+        # exchange on every rank: the rank that publishes last waits only for the NVLink latency, the others also for the skew
+        waits, gaps = [], []
+        for _ in range(50):
+            h.step(*ptrs, 1, stream)
+            w, g = h.exchange_timing(stream)
+            waits.append(w); gaps.append(g)
+        allw = [None] * world
+        dist.all_gather_object(allw, (waits, gaps))
+        if rank == 0:
+            wm = np.array([a[0] for a in allw]); gm = np.array([a[1] for a in allw])        # [rank][step]
+            extra["exchange_timing_us"] = {
+                "steps": 50, "what": "wait of the chain launch for all ranks' energy partials (peer inboxes), per step",
+                "latency_min_over_ranks_median": float(np.median(wm.min(axis=0))), "wait_max_over_ranks_median": float(np.median(wm.max(axis=0))),
+                "skew_median": float(np.median(wm.max(axis=0) - wm.min(axis=0))), "per_rank_median": [float(x) for x in np.median(wm, axis=1)],
+                "publish_to_wait_start_median": float(np.median(gm))}
+    h.close()
+    if args.workload == "c4" and not args.quick:
+        del velm, posq, force
+        torch.cuda.empty_cache()
+        if world > 1:
+            extra["shard_check"] = shard_check_leg(torch, capi, dev, local, comm, rank, world, stream, dist)
+        extra["c5_strong"] = c5_leg(torch, capi, dev, local, comm, rank, world, stream, barrier, dist, min(args.steps, 20))
+        torch.cuda.empty_cache()
+        if world == 1:
+            extra["small_systems"] = small_systems_leg(torch, capi, dev, local, stream, barrier)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -305,17 +349,20 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "particles_per_gpu": n, "total_particles": total_particles,
                        "parallelism": f"particle-range shards x{world}" if world > 1 else "single GPU",
-                       "exchange": {0: "none", 1: "ncclAllReduce of double[T] per step", 2: "peer-mapped inboxes over NVLink (no collective launch)"}[h.exchange_kind],
+                       "exchange": {0: "none", 1: "ncclAllReduce of double[T] per step", 2: "peer-mapped inboxes over NVLink (no collective launch)"}[exchange_kind],
+                       "kernels": "warp-chunk kernels (tgnh_v2.cuh)" if generation == 2 else "first-generation kernels (tgnh_kernels.cuh)",
                        "l2": "inputs larger than L2 (>=440 MB working set per GPU vs 126 MB L2)",
                        "spin_up": "0.5 s of device-to-device copies before the warm-up steps (clock ramp after the host-side set-up)",
                        "accumulation": "fp32 state (OpenMM single-precision layouts), fp64 KE reductions and NH chain",
                        "step_achieved_gbs": ALG_BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9,
                        "step_frac_of_peak": ALG_BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "tgnh_step_host: pinned host velm/posq/force -> device, 1 step, velm/posq/KE back, per step"},
+                    "what": "tgnh_step_host2 per step: pinned host velm/posq -> device in 8 pipelined particle ranges (the fixed synthetic forces are "
+                            "uploaded once: TGNH_HOST_FORCES_UNCHANGED), 1 step, velm/posq/2KE back; H2D and D2H overlap on the two copy engines",
+                    "with_force_upload_every_step": {"value": e2e_full, "h2d_bytes_per_step": n * 16 * 2 + 3 * padded * 4}},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "tgnh_stream_kernel<KIND_A> (scale+kick+drift+hard wall)",
+            "roofline": {"bound": "hbm", "kernel": ("tgnh_v2_kernel<V2_A>" if generation == 2 else "tgnh_stream_kernel<KIND_A>") + " (scale+kick+drift+hard wall)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_particle": ALG_BYTES_HALF1,
                          "avg_launch_ms": a_ms / max(a_cnt, 1),
@@ -323,6 +370,13 @@ def run_ours(args):
                          "half2_achieved": (ALG_BYTES_HALF2 * n / (b_ms / max(b_cnt, 1) * 1e-3) / 1e9) if b_cnt else None},
             "ke2_last": [float(x) for x in ke2],
         }
+        out["config"].update(extra)
+        if world == 1 and args.workload == "c4" and not args.quick and not args.no_reference_cuda:
+            # the reference's own CUDA kernels on the same system, same box (an extra measured baseline; never on the product path)
+            try:
+                out["reference_cuda"] = reference_cuda_leg(system, 10)
+            except Exception as e:      # noqa: BLE001 - a baseline leg must not take the bench line down
+                out["reference_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
         # CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same generator, 1 core (the
         # reference platform is serial)
         if world == 1 and not args.no_cpu_baseline:
@@ -335,10 +389,170 @@ def run_ours(args):
                                                 else "oracle-tg port, serial fp64"),
                                    "port_all_cores": cpu_port_all_cores(sysb, 20)}
         print(json.dumps(out))
-    h.close()
     if comm is not None:
         comm.close()
         dist.destroy_process_group()
+
+
+def device_buffers(torch, system, dev, pinned=False):
+    n = system.num_particles
+    padded = ((n + 31) // 32) * 32
+    mk = (lambda *shape: torch.zeros(shape, dtype=torch.float32).pin_memory()) if pinned else (lambda *shape: torch.zeros(shape, dtype=torch.float32))
+    h_velm, h_posq, h_force = mk(padded, 4), mk(padded, 4), mk(3, padded)
+    h_velm[:n] = torch.from_numpy(system.velm_f32())
+    h_posq[:n] = torch.from_numpy(system.posq_f32())
+    h_force[:, :n] = torch.from_numpy(np.ascontiguousarray(system.forces.T, np.float32))
+    return padded, (h_velm, h_posq, h_force), (h_velm.to(dev), h_posq.to(dev), h_force.to(dev))
+
+
+def timed_steps(torch, h, ptrs, steps, stream, barrier, warmup=3):
+    """W warm-up steps, then `steps` steps in one tgnh_step call between CUDA events on the launching stream."""
+    h.step(*ptrs, warmup, stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    h.step(*ptrs, steps, stream)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def small_systems_leg(torch, capi, dev, local, stream, barrier):
+    """C1-C3 (BASELINE.json configs[0..2]): launch- and chain-latency bound; microseconds and launches per step."""
+    out = {}
+    for w in ("c1", "c2", "c3"):
+        system = make_system(w, 0, 1)
+        padded, _, bufs = device_buffers(torch, system, dev)
+        h = capi.Handle(system, padded=padded, device=local)
+        ptrs = [b.data_ptr() for b in bufs]
+        l0 = None
+        h.step(*ptrs, 20, stream)
+        l0 = h.launch_count
+        ms = timed_steps(torch, h, ptrs, 500, stream, barrier, warmup=20)
+        launches = (h.launch_count - l0 - 0) / 520.0
+        out[w] = {"particles": system.num_particles, "us_per_step": 1e3 * ms / 500, "launches_per_step": round(launches, 2),
+                  "kernel_generation": h.kernel_generation}
+        h.close()
+    return out
+
+
+def call_pattern_leg(torch, capi, h, ptrs, stream, barrier, steps=20):
+    """The OpenMM-facing call sequence tgnh_half1 / tgnh_half2 per step on the C4 buffers (what the KernelImpl issues), in its three
+    modes: reference semantics (energies reduced from velm at the start of every step, scaling applied at its end), energies carried
+    over, and carried over + scaling deferred into the next step.  ms per step."""
+    velm, posq, force = ptrs
+    out = {}
+    for name, invalidate, flags in (("reference_semantics", True, capi.HALF2_DEFAULT), ("carry_over", False, capi.HALF2_DEFAULT),
+                                    ("carry_over_deferred", False, capi.HALF2_DEFER_SCALE)):
+        def run(k):
+            for _ in range(k):
+                if invalidate:
+                    h.invalidate()
+                h.half1(velm, posq, force, stream)
+                h.half2(velm, force, flags, stream)
+            h.flush(velm, stream)
+        run(3)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        run(steps)
+        e1.record()
+        barrier()
+        out[name] = e0.elapsed_time(e1) / steps
+    return out
+
+
+def c5_leg(torch, capi, dev, local, comm, rank, world, stream, barrier, dist, steps):
+    """BASELINE.json configs[4]: ONE 200M-particle system split over the ranks (strong scaling).  Every rank tiles its 200M / N
+    particles from a 10M-particle block of the C4 generator (the host generator makes 1M particles per second; the throughput of the
+    integrator does not depend on the values) and builds the full index tables for its range."""
+    per_mol = C5_MOLECULES // world
+    block_mol = min(per_mol, C4_MOLECULES)
+    reps = per_mol // block_mol
+    per_mol = reps * block_mol
+    block = synth.water_box(block_mol, 4, first_molecule=rank * per_mol, box_molecules=C5_MOLECULES)
+    nb = block.num_particles
+    n = nb * reps
+    system = synth.tile(block, reps)
+    padded = ((n + 31) // 32) * 32
+    velm = torch.zeros((padded, 4), dtype=torch.float32, device=dev)
+    posq = torch.zeros((padded, 4), dtype=torch.float32, device=dev)
+    force = torch.zeros((3, padded), dtype=torch.float32, device=dev)
+    bv, bx = torch.from_numpy(block.velm_f32()).to(dev), torch.from_numpy(block.posq_f32()).to(dev)
+    bf = torch.from_numpy(np.ascontiguousarray(block.forces.T, np.float32)).to(dev)
+    for r in range(reps):
+        velm[r * nb:(r + 1) * nb] = bv
+        posq[r * nb:(r + 1) * nb] = bx
+        force[:, r * nb:(r + 1) * nb] = bf
+    del bv, bx, bf
+    h = capi.Handle(system, padded=padded, device=local, comm=comm)
+    del system
+    ptrs = [velm.data_ptr(), posq.data_ptr(), force.data_ptr()]
+    ms = timed_steps(torch, h, ptrs, steps, stream, barrier)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    h.close()
+    total = n * world
+    peak, _ = peaks()
+    return {"total_particles": total, "particles_per_gpu": n, "ms_per_step": ms / steps, "value": total * steps / (ms * 1e-3),
+            "frac_of_peak_per_gpu": ALG_BYTES_STEP * n * steps / (ms * 1e-3) / 1e9 / peak, "steps": steps, "scaling": "strong"}
+
+
+def shard_check_leg(torch, capi, dev, local, comm, rank, world, stream, dist):
+    """Untimed: a 160k-particle system sharded over the ranks for 25 steps; every rank must hold the same thermostat state, and it must
+    equal the state of the same system stepped on ONE GPU (rank 0) up to the summation order of the energy partials."""
+    mol, g, steps = 40000, 4, 25
+    per = mol // world
+    shard = synth.water_box(per, g, first_molecule=rank * per, box_molecules=per * world, quantize_masses=True)
+    padded, _, bufs = device_buffers(torch, shard, dev)
+    h = capi.Handle(shard, padded=padded, device=local, comm=comm)
+    h.step(*[b.data_ptr() for b in bufs], steps, stream)
+    torch.cuda.synchronize()
+    state = (h.kinetic_energies().tolist(), h.vscale().tolist(), h.chain_state()[1].tolist())
+    vel = bufs[0][:shard.num_particles, :3].double().cpu().numpy()
+    h.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, state)
+    res = None
+    if rank == 0:
+        same = all(other == gathered[0] for other in gathered[1:])
+        whole = synth.water_box(per * world, g, quantize_masses=True)
+        padded1, _, bufs1 = device_buffers(torch, whole, dev)
+        h1 = capi.Handle(whole, padded=padded1, device=local)
+        h1.step(*[b.data_ptr() for b in bufs1], steps, stream)
+        torch.cuda.synchronize()
+        ke1, vs1, ed1 = h1.kinetic_energies(), h1.vscale(), h1.chain_state()[1]
+        rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - b) / np.maximum(np.abs(b), 1e-300 + 1e-12 * np.abs(b).max())))
+        dv = float(np.max(np.abs(vel - bufs1[0][:shard.num_particles, :3].double().cpu().numpy())))
+        res = {"ranks_identical": bool(same), "ke_vs_single_gpu": rel(state[0], ke1), "vscale_vs_single_gpu": rel(state[1], vs1),
+               "eta_dot_vs_single_gpu": rel(state[2], ed1), "max_abs_dv_rank0": dv, "particles": per * world * 4, "steps": steps}
+        res["ok"] = bool(same and res["ke_vs_single_gpu"] < 1e-11 and res["vscale_vs_single_gpu"] < 1e-11 and res["eta_dot_vs_single_gpu"] < 1e-8 and dv < 1e-5)
+        h1.close()
+    return res
+
+
+def reference_cuda_leg(system, steps):
+    """The same-box GPU baseline: the reference's OWN CUDA platform (oracle/_refcuda: platforms/cuda sources and kernel strings compiled
+    unmodified, NVRTC, OpenMM's launch rule; mixed precision, int64 forces, ~16 launches + 2 blocking downloads + 2 uploads per step) on the
+    same C4 system, through the reference's DrudeTGNHIntegrator.step.  Test infrastructure used as a measured baseline, like cpu_baseline."""
+    from oracle import refcuda as RC
+    if not RC.available("reference"):
+        return {"unavailable": "oracle/_refcuda/librefcuda.so was not built (no /root/reference at build time)"}
+    t0 = time.perf_counter()
+    sim = RC.CudaSim(system, "reference", "mixed")
+    sim.set_state(system.positions, system.velocities, np.rint(system.forces * 4294967296.0) / 4294967296.0)
+    setup = time.perf_counter() - t0
+    sim.step(3)
+    c0 = sim.counters()["launches"]
+    ms = sim.time_steps(steps)
+    launches = (sim.counters()["launches"] - c0) / steps
+    sim.close()
+    n = system.num_particles
+    return {"value": n * steps / (ms * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms / steps, "launches_per_step": launches, "steps": steps,
+            "precision": "mixed (the reference's single mode reads its double scale factors as floats)", "setup_s": round(setup, 1),
+            "what": "reference platforms/cuda sources + kernel strings, unmodified, behind the CUDA-platform stand-in (shim/cuda)"}
 
 
 def ncu_traffic(workload, n):
@@ -366,6 +580,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--quick", action="store_true", help="headline only: skip the call-pattern, replica, shard-check, C5 and small-system legs")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip the reference-CUDA-kernel baseline leg")
     ap.add_argument("--molecules", type=int, default=0, help="override molecules per GPU of the c4 generator (profiling runs)")
     args = ap.parse_args()
     global MOLECULES_OVERRIDE

@@ -138,6 +138,15 @@ int tgnh_step(tgnh_handle* h, void* stream, void* velm, void* posq, const void* 
  * runs nsteps, copies velm/posq back and the 2*KE vector into ke2_host ([G+2], may be NULL). Blocking.
  * Single and double layouts (mixed also needs the posqCorrection array: use the device-buffer calls). */
 int tgnh_step_host(tgnh_handle* h, void* velm_host, void* posq_host, const void* force_host, int nsteps, double* ke2_host);
+/* The same with (a) the mixed layout's posqCorrection array (NULL otherwise), (b) flags:
+ *   TGNH_HOST_FORCES_UNCHANGED  the caller vouches that force_host holds what it held in the previous call with this pointer
+ *                               (fixed synthetic forces): the upload of the forces is skipped.
+ * Single-precision systems that run through the warp-chunk kernels are pipelined: the state is cut into 8 particle ranges; the
+ * kinetic energies of a range are reduced as soon as its velocities have landed, its two halves run as soon as its positions and
+ * forces have landed, and its new positions travel back over the second copy engine while later ranges are still being uploaded. */
+enum { TGNH_HOST_FORCES_UNCHANGED = 1 };
+int tgnh_step_host2(tgnh_handle* h, void* velm_host, void* posq_host, void* posq_correction_host, const void* force_host, int nsteps, int flags,
+                    double* ke2_host);
 /* Mixed precision: the float4[paddedN] residual array of the positions (cu.getPosqCorrection()). */
 int tgnh_set_posq_correction(tgnh_handle* h, void* posq_correction);
 /* The velocities were changed behind the integrator's back (DrudeTGNHIntegrator::stateChanged,
@@ -206,6 +215,13 @@ void tgnh_comm_destroy(tgnh_comm* c);
 enum { TGNH_EXCHANGE_NONE = 0, TGNH_EXCHANGE_NCCL = 1, TGNH_EXCHANGE_PEER = 2 };
 /* how this handle exchanges the kinetic-energy partial sums (TGNH_EXCHANGE_*); environment TGNH_P2P=0 forces NCCL */
 int tgnh_exchange_kind(const tgnh_handle* h);
+
+/* Diagnostics of the peer-inbox exchange (device %globaltimer stamps of the most recent reduction on this rank), microseconds:
+ *   us[0]  time the chain launch spent waiting for all ranks' partial sums (on the rank that finishes last this is the pure
+ *          exchange latency, on the others it also contains the skew between the ranks)
+ *   us[1]  time between this rank's publish (end of its reducing launch) and the start of its wait (launch hand-over)
+ * Both are 0 for handles that do not use the inboxes. */
+int tgnh_get_exchange_timing(tgnh_handle* h, void* stream, double* us /*[2]*/);
 
 #ifdef __cplusplus
 }

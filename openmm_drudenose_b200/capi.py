@@ -14,6 +14,7 @@ OK, ERR_INVALID_ARGUMENT, ERR_TEMP_GROUP, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, E
 FORCE_F32_SOA, FORCE_I64_SOA = 0, 1
 PRECISION_SINGLE, PRECISION_MIXED, PRECISION_DOUBLE = 0, 1, 2
 HALF2_DEFAULT, HALF2_DEFER_SCALE, HALF2_KICK_ONLY = 0, 1, 2
+HOST_FORCES_UNCHANGED = 1
 UNIQUE_ID_BYTES = 128
 BOLTZ = 1.380649e-23 * 6.02214076e23 / 1000.0
 
@@ -21,9 +22,9 @@ BOLTZ = 1.380649e-23 * 6.02214076e23 / 1000.0
 SYMBOLS = [
     "tgnh_create", "tgnh_destroy", "tgnh_last_error", "tgnh_build_info", "tgnh_half1", "tgnh_half1_kick", "tgnh_half1_drift",
     "tgnh_thermostat", "tgnh_half2", "tgnh_flush",
-    "tgnh_step", "tgnh_step_host", "tgnh_set_posq_correction", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
+    "tgnh_step", "tgnh_step_host", "tgnh_step_host2", "tgnh_set_posq_correction", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
     "tgnh_kinetic_energy", "tgnh_compute_kinetic_energies", "tgnh_get_chain_state", "tgnh_set_chain_state",
-    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_plan_tiles", "tgnh_plan_descriptors", "tgnh_plan_chunks", "tgnh_kernel_generation", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
+    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_get_exchange_timing", "tgnh_plan_tiles", "tgnh_plan_descriptors", "tgnh_plan_chunks", "tgnh_kernel_generation", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
     "tgnh_comm_create", "tgnh_comm_destroy",
 ]
 
@@ -71,6 +72,7 @@ def lib():
         L.tgnh_flush.argtypes = [vp, vp, vp]
         L.tgnh_step.argtypes = [vp, vp, vp, vp, vp, C.c_int]
         L.tgnh_step_host.argtypes = [vp, vp, vp, vp, C.c_int, dp]
+        L.tgnh_step_host2.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, dp]
         L.tgnh_set_posq_correction.argtypes = [vp, vp]
         L.tgnh_invalidate.argtypes = [vp]
         L.tgnh_num_thermostats.argtypes = [vp]
@@ -85,6 +87,7 @@ def lib():
         L.tgnh_launch_count.argtypes = [vp]
         L.tgnh_launch_count.restype = C.c_int64
         L.tgnh_exchange_kind.argtypes = [vp]
+        L.tgnh_get_exchange_timing.argtypes = [vp, vp, dp]
         ip32 = C.POINTER(C.c_int32)
         L.tgnh_plan_tiles.argtypes = [C.POINTER(Params), ip32, C.c_int32, ip32, ip32, ip32]
         L.tgnh_plan_descriptors.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint32)]
@@ -252,6 +255,14 @@ class Handle:
         check(lib().tgnh_step_host(self.h, as_ptr(velm_host), as_ptr(posq_host), as_ptr(force_host), nsteps, _dp(ke2)))
         return ke2
 
+    def step_host2(self, velm_host, posq_host, force_host, nsteps=1, posq_correction_host=None, forces_unchanged=False):
+        """tgnh_step_host2: as step_host, plus the mixed layout's posqCorrection array and the forces-unchanged promise"""
+        ke2 = np.zeros(self.T)
+        as_ptr = lambda a: None if a is None else (a if isinstance(a, int) else a.ctypes.data)
+        check(lib().tgnh_step_host2(self.h, as_ptr(velm_host), as_ptr(posq_host), as_ptr(posq_correction_host), as_ptr(force_host), nsteps,
+                                    HOST_FORCES_UNCHANGED if forces_unchanged else 0, _dp(ke2)))
+        return ke2
+
     def set_posq_correction(self, ptr):
         check(lib().tgnh_set_posq_correction(self.h, ptr))
 
@@ -298,6 +309,10 @@ class Handle:
     @property
     def launch_count(self):
         return lib().tgnh_launch_count(self.h)
+
+    def exchange_timing(self, stream=0):
+        """(wait for all ranks' sums, publish -> wait start) of the most recent reduction, microseconds"""
+        out = np.zeros(2); check(lib().tgnh_get_exchange_timing(self.h, stream, _dp(out))); return float(out[0]), float(out[1])
 
     @property
     def kernel_generation(self):

@@ -163,6 +163,12 @@ struct tgnh_handle {
     int numTiles2 = 0, maxRes = 1, numSpecies = 0;
     int gridA2v = 0, gridB2v = 0, gridKE2v = 0, smemA2v = 0, smemB2v = 0, smemKE2v = 0;
     bool earlyOK = false;         // set by tgnh_step around launches whose predecessors in the stream are its own
+    std::vector<int> hChunkStart; // host copy of dChunkStart (chunk boundaries of the pipelined host-buffer path)
+    // pipelined host-buffer path (tgnh_step_host2)
+    cudaStream_t hsIn = nullptr, hsOut = nullptr;
+    std::vector<cudaEvent_t> hsEvents;
+    void* hsCorr = nullptr;
+    const void* hsForceHost = nullptr;   // host pointer whose contents hsForce holds
     // host copies of the thermostat parameters
     std::vector<double> dof, nkbt, etaMass;
     // state machine
@@ -437,22 +443,29 @@ static void build_plan_v2(const tgnh_params* p, HostPlan& hp) {
         q[4] = muh; q[5] = (float)(mu - (double)muh); q[6] = (float)(invM - (double)ih); q[7] = (float)fpartner;
     };
     put_row(V2_NULL, 0.0, 0.0, 0.0, 0.0, v2_meta_pack(0, ROLE_NORMAL, true, 0));
+    // a tiny direct-mapped cache in front of the map: consecutive molecules repeat the same few species (200 M particles in C5)
+    struct Slot { std::array<uint64_t, 4> key; int row; };
+    std::vector<Slot> cache(256, Slot{{~0ull, ~0ull, ~0ull, ~0ull}, -1});
     for (int i = 0; i < N; i++) {
         const int r = p->particle_res_id[i];
         const double m = p->masses[i], mj = hp.partner[i] ? p->masses[i + hp.partner[i]] : 0.0;
-        double M = 0.0;
-        for (int j = hp.resFirst[r]; j <= hp.resLast[r]; j++) M += p->masses[j];      // particle order, as calcCOMVelocities sums (:90-100)
+        const double M = hp.resMass[r];                                   // summed in particle order, as calcCOMVelocities does (:90-100)
         const uint32_t meta = v2_meta_pack(p->particle_temp_group[i], hp.role[i], i == hp.resFirst[r], hp.partner[i]);
         const std::array<uint64_t, 4> key = {bits(m), bits(mj), bits(M), (uint64_t)meta};
-        auto it = rows.find(key);
-        if (it == rows.end()) {
-            if ((int)rows.size() >= V2_NULL) { hp.v2why = "more than 255 particle species"; return; }
-            const int row = (int)rows.size();
-            it = rows.emplace(key, row).first;
-            const bool pair = hp.partner[i] != 0;
-            put_row(row, m, pair ? m * mj / (m + mj) : 0.0, M > 0.0 ? 1.0 / M : 0.0, pair ? mj / (m + mj) : 0.0, meta);
+        Slot& slot = cache[(size_t)((key[0] * 0x9E3779B97F4A7C15ull ^ key[1] * 0xC2B2AE3D27D4EB4Full ^ key[2] ^ key[3] * 0x165667B19E3779F9ull) >> 56)];
+        if (slot.row < 0 || slot.key != key) {
+            auto it = rows.find(key);
+            if (it == rows.end()) {
+                if ((int)rows.size() >= V2_NULL) { hp.v2why = "more than 255 particle species"; return; }
+                const int row = (int)rows.size();
+                it = rows.emplace(key, row).first;
+                const bool pair = hp.partner[i] != 0;
+                put_row(row, m, pair ? m * mj / (m + mj) : 0.0, M > 0.0 ? 1.0 / M : 0.0, pair ? mj / (m + mj) : 0.0, meta);
+            }
+            slot.key = key;
+            slot.row = it->second;
         }
-        hp.spec[i] = (unsigned char)it->second;
+        hp.spec[i] = (unsigned char)slot.row;
     }
     hp.numSpecies = (int)rows.size();
     hp.v2 = true;
@@ -792,6 +805,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         h->v2 = hp.v2 && !(e && atoi(e) == 0);
         if (h->v2) {
             h->numTiles2 = hp.numTiles2; h->maxRes = hp.maxRes; h->numSpecies = hp.numSpecies;
+            h->hChunkStart = hp.chunkStart;
             if (!dmalloc((void**)&h->dSpec, hp.spec.size()) || !dmalloc((void**)&h->dChunkStart, hp.chunkStart.size() * 4) ||
                 !dmalloc((void**)&h->dSpecTable, hp.specTable.size() * 4))
                 return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the species tables failed"));
@@ -899,7 +913,10 @@ extern "C" void tgnh_destroy(tgnh_handle* h) {
     cudaFree(h->dInbox);
     cudaFree(h->dDesc); cudaFree(h->dTileStart); cudaFree(h->dResStart); cudaFree(h->dTileFirstRes); cudaFree(h->dBigFirst); cudaFree(h->dBigLast); cudaFree(h->dBigCom); cudaFree(h->dChain); cudaFree(h->dPartials); cudaFree(h->dTicket);
     cudaFree(h->dSpec); cudaFree(h->dChunkStart); cudaFree(h->dSpecTable);
-    cudaFree(h->hsVelm); cudaFree(h->hsPosq); cudaFree(h->hsForce);
+    cudaFree(h->hsVelm); cudaFree(h->hsPosq); cudaFree(h->hsForce); cudaFree(h->hsCorr);
+    for (cudaEvent_t e : h->hsEvents) cudaEventDestroy(e);
+    if (h->hsIn) cudaStreamDestroy(h->hsIn);
+    if (h->hsOut) cudaStreamDestroy(h->hsOut);
     for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
     if (h->hsStream) cudaStreamDestroy(h->hsStream);
     delete h;
@@ -1162,32 +1179,175 @@ extern "C" int tgnh_invalidate(tgnh_handle* h) {
     return TGNH_OK;
 }
 
+extern "C" int tgnh_step_host2(tgnh_handle* h, void* velm_host, void* posq_host, void* posq_correction_host, const void* force_host, int nsteps,
+                               int flags, double* ke2_host);
 extern "C" int tgnh_step_host(tgnh_handle* h, void* velm_host, void* posq_host, const void* force_host, int nsteps, double* ke2_host) {
+    if (h && h->prec == TGNH_PRECISION_MIXED)
+        return fail(TGNH_ERR_UNSUPPORTED, "mixed precision also needs the posqCorrection array: use tgnh_step_host2");
+    return tgnh_step_host2(h, velm_host, posq_host, nullptr, force_host, nsteps, 0, ke2_host);
+}
+
+// One launch of a warp-chunk kernel over the tiles [tileBegin, tileBegin + tileCount): the building block of the pipelined
+// host-buffer path.  `accumulate`: add the energy sums to those of the previous sub-range; `last`: the launch that completes the
+// reduction (publishes to the peers when sharded).
+static int launch_v2_range(tgnh_handle* h, cudaStream_t s, int kind2, void* velm, void* posq, const void* force, int tileBegin, int tileCount,
+                           bool accumulate, bool last) {
+    StreamArgs a{};
+    a.velm = velm; a.posq = posq; a.force = force;
+    a.desc = h->dDesc; a.tileStart = h->dTileStart; a.paddedN = h->paddedN;
+    a.dt = h->dt;
+    a.fscale = h->ffmt == TGNH_FORCE_I64_SOA ? 0.5 * h->dt / 4294967296.0 : 0.5 * h->dt;
+    a.rmax = h->rmax;
+    a.hardwallScale = std::sqrt(h->kTD);
+    a.useLocalKE = sharded(h) ? 1 : 0;
+    a.partials = h->dPartials; a.ticket = h->dTicket; a.chain = h->chain;
+    a.peers = h->peers;
+    const bool reduces = kind2 != V2_A;
+    if (h->peers.world > 1 && reduces && last) a.peers.seq = ++h->reduceSeq; else a.peers.world = 0;
+    a.spec = h->dSpec; a.chunkStart = h->dChunkStart; a.specTable = h->dSpecTable; a.maxRes = h->maxRes;
+    a.numTiles = tileCount; a.tileBegin = tileBegin; a.accumulate = accumulate ? 1 : 0;
+    int grid = kind2 == V2_A ? h->gridA2v : kind2 == V2_B ? h->gridB2v : h->gridKE2v;
+    if (grid > tileCount) grid = tileCount;
+    const int smem = kind2 == V2_A ? h->smemA2v : kind2 == V2_B ? h->smemB2v : h->smemKE2v;
+    CUDA_TRY(launch_pdl(pick_v2(kind2, h->ffmt, h->useCOM, h->hardwall), grid, 512, smem, s, (const StreamArgs)a));
+    h->launches++;
+    return TGNH_OK;
+}
+
+// One step with the state in HOST memory, pipelined over HS_CHUNKS particle ranges and three streams:
+//   copy-in :  velm chunks first, then posq + force chunks                          (host -> device engine)
+//   compute :  energies of chunk c as soon as its velm has landed; chain; then first half + second half of chunk c as soon
+//              as its posq / forces have landed; chain; scaling
+//   copy-out:  posq of chunk c as soon as its first half is done (device -> host engine, concurrent with the uploads that are
+//              still running); velm after the scaling
+// upload / download: whether this step starts from / ends in the host buffers (the inner steps of a multi-step call do neither).
+static constexpr int HS_CHUNKS = 8;
+static int pipelined_host_step(tgnh_handle* h, void* velm_host, void* posq_host, const void* force_host, bool upload, bool uploadForce, bool download,
+                               double* ke2_host) {
+    cudaStream_t sc = h->hsStream, si = h->hsIn, so = h->hsOut;
+    const int nt = h->numTiles2, K = nt < HS_CHUNKS ? nt : HS_CHUNKS;
+    const size_t fb = h->ffmt == TGNH_FORCE_I64_SOA ? 8 : 4;
+    float4* dv = (float4*)h->hsVelm;
+    float4* dx = (float4*)h->hsPosq;
+    unsigned char* df = (unsigned char*)h->hsForce;
+    auto tile0 = [&](int c) { return (int)((long long)nt * c / K); };
+    auto part0 = [&](int c) { return h->hChunkStart[(size_t)V2_NCONS * tile0(c)]; };     // first particle of chunk c (c == K: N)
+    cudaEvent_t* ev = h->hsEvents.data();            // [0,K) velm in, [K,2K) posq+force in, [2K,3K) first half done, [3K] compute ready, [3K+1] scaled
+    if (upload) {
+        CUDA_TRY(cudaEventRecord(ev[3 * K], sc));                      // the copies must not overtake earlier work on the compute stream
+        CUDA_TRY(cudaStreamWaitEvent(si, ev[3 * K], 0));
+        for (int c = 0; c < K; c++) {
+            const int p0 = part0(c), p1 = part0(c + 1);
+            CUDA_TRY(cudaMemcpyAsync(dv + p0, (const float4*)velm_host + p0, (size_t)(p1 - p0) * 16, cudaMemcpyHostToDevice, si));
+            CUDA_TRY(cudaEventRecord(ev[c], si));
+        }
+        for (int c = 0; c < K; c++) {
+            const int p0 = part0(c), p1 = part0(c + 1);
+            CUDA_TRY(cudaMemcpyAsync(dx + p0, (const float4*)posq_host + p0, (size_t)(p1 - p0) * 16, cudaMemcpyHostToDevice, si));
+            if (uploadForce) {
+                // forces are SoA: three slices per chunk, rounded outwards to the 16-byte windows the kernels fetch
+                const int f0 = p0 & ~3, f1 = c + 1 == K ? h->paddedN : ((p1 + 3) & ~3);
+                for (int k = 0; k < 3; k++)
+                    CUDA_TRY(cudaMemcpyAsync(df + ((size_t)k * h->paddedN + f0) * fb, (const unsigned char*)force_host + ((size_t)k * h->paddedN + f0) * fb,
+                                             (size_t)(f1 - f0) * fb, cudaMemcpyHostToDevice, si));
+            }
+            CUDA_TRY(cudaEventRecord(ev[K + c], si));
+        }
+        h->keValid = false;
+    }
+    // thermostat half-step that begins the step
+    if (!h->keValid) {
+        for (int c = 0; c < K; c++) {
+            if (upload) CUDA_TRY(cudaStreamWaitEvent(sc, ev[c], 0));
+            if (int rc = launch_v2_range(h, sc, V2_KE, dv, nullptr, nullptr, tile0(c), tile0(c + 1) - tile0(c), c > 0, c + 1 == K)) return rc;
+        }
+        h->keValid = true;
+        if (int rc = launch_chain(h, sc, CHAIN_FIRST, h->peers.world > 1)) return rc;
+    } else if (int rc = launch_chain(h, sc, CHAIN_FIRST)) return rc;
+    if (sharded(h) && h->peers.world <= 1) return fail(TGNH_ERR_UNSUPPORTED, "pipelined host path needs the peer-inbox exchange when sharded");
+    h->scalePending = false;
+    h->keValid = false;
+    for (int c = 0; c < K; c++) {
+        if (upload) CUDA_TRY(cudaStreamWaitEvent(sc, ev[K + c], 0));
+        const int t0 = tile0(c), tn = tile0(c + 1) - t0;
+        if (int rc = launch_v2_range(h, sc, V2_A, dv, dx, df, t0, tn, false, false)) return rc;
+        if (download) {
+            CUDA_TRY(cudaEventRecord(ev[2 * K + c], sc));
+            CUDA_TRY(cudaStreamWaitEvent(so, ev[2 * K + c], 0));
+            const int p0 = part0(c), p1 = part0(c + 1);
+            CUDA_TRY(cudaMemcpyAsync((float4*)posq_host + p0, dx + p0, (size_t)(p1 - p0) * 16, cudaMemcpyDeviceToHost, so));
+        }
+        if (int rc = launch_v2_range(h, sc, V2_B, dv, nullptr, df, t0, tn, c > 0, c + 1 == K)) return rc;
+    }
+    if (int rc = launch_chain(h, sc, CHAIN_SECOND, h->peers.world > 1)) return rc;
+    h->keValid = true;
+    h->scalePending = true;
+    if (int rc = flush_scale(h, sc, dv)) return rc;
+    if (download) {
+        CUDA_TRY(cudaMemcpyAsync(velm_host, dv, (size_t)h->N * 16, cudaMemcpyDeviceToHost, sc));
+        if (ke2_host) CUDA_TRY(cudaMemcpyAsync(ke2_host, h->chain.ke2Used, h->T * 8, cudaMemcpyDeviceToHost, sc));
+        CUDA_TRY(cudaStreamSynchronize(so));
+    }
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_step_host2(tgnh_handle* h, void* velm_host, void* posq_host, void* posq_correction_host, const void* force_host, int nsteps,
+                               int flags, double* ke2_host) {
     if (!h || !velm_host || !posq_host || !force_host) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    if (nsteps < 1) return fail(TGNH_ERR_INVALID_ARGUMENT, "nsteps must be >= 1");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (h->prec == TGNH_PRECISION_MIXED)
-        return fail(TGNH_ERR_UNSUPPORTED, "tgnh_step_host covers the single and double layouts (mixed needs the posqCorrection array: use device buffers)");
+    const bool mixed = h->prec == TGNH_PRECISION_MIXED;
+    if (mixed && !posq_correction_host) return fail(TGNH_ERR_INVALID_ARGUMENT, "mixed precision: posq_correction_host is required");
     const size_t fbytes = (size_t)3 * h->paddedN * (h->ffmt == TGNH_FORCE_I64_SOA ? 8 : 4);
-    const size_t vb = h->prec ? 32 : 16;                 // bytes per velm / posq element
+    const size_t vb = h->prec ? 32 : 16;                                      // bytes per velm element
+    const size_t xb = h->prec == TGNH_PRECISION_DOUBLE ? 32 : 16;             // bytes per posq element
     if (!h->hsVelm) {
         if (!h->hsStream) CUDA_TRY(cudaStreamCreateWithFlags(&h->hsStream, cudaStreamNonBlocking));
-        void *v = nullptr, *x = nullptr, *f = nullptr;
-        if (cudaMalloc(&v, (size_t)h->paddedN * vb) != cudaSuccess || cudaMalloc(&x, (size_t)h->paddedN * vb) != cudaSuccess ||
-            cudaMalloc(&f, fbytes) != cudaSuccess) {
-            cudaFree(v); cudaFree(x); cudaFree(f);
+        void *v = nullptr, *x = nullptr, *f = nullptr, *c = nullptr;
+        if (cudaMalloc(&v, (size_t)h->paddedN * vb) != cudaSuccess || cudaMalloc(&x, (size_t)h->paddedN * xb) != cudaSuccess ||
+            cudaMalloc(&f, fbytes) != cudaSuccess || (mixed && cudaMalloc(&c, (size_t)h->paddedN * 16) != cudaSuccess)) {
+            cudaFree(v); cudaFree(x); cudaFree(f); cudaFree(c);
             (void)cudaGetLastError();
             return fail(TGNH_ERR_CUDA, "cudaMalloc of the staging buffers failed");
         }
-        h->hsVelm = v; h->hsPosq = x; h->hsForce = f;
+        h->hsVelm = v; h->hsPosq = x; h->hsForce = f; h->hsCorr = c;
+        h->hsForceHost = nullptr;
     }
+    if (mixed) CUDA_TRY((cudaError_t)(tgnh_set_posq_correction(h, h->hsCorr) == TGNH_OK ? cudaSuccess : cudaErrorInvalidValue));
+    // forces: skipped when the caller vouches that this host array has not changed since the call that uploaded it
+    const bool uploadForce = !((flags & TGNH_HOST_FORCES_UNCHANGED) && h->hsForceHost == force_host);
     cudaStream_t s = h->hsStream;
+    if (h->v2 && h->numTiles2 >= 2 * HS_CHUNKS && h->uniformGroups) {
+        if (!h->hsIn) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->hsIn, cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->hsOut, cudaStreamNonBlocking));
+            h->hsEvents.resize(3 * HS_CHUNKS + 2);
+            for (cudaEvent_t& e : h->hsEvents) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        for (int i = 0; i < nsteps; i++) {
+            const bool first = i == 0, last = i + 1 == nsteps;
+            if (!first && !last) {
+                if (int rc = tgnh_step(h, s, h->hsVelm, h->hsPosq, h->hsForce, nsteps - 2)) return rc;
+                i = nsteps - 2;
+                continue;
+            }
+            if (int rc = pipelined_host_step(h, velm_host, posq_host, force_host, first, first && uploadForce, last, ke2_host)) return rc;
+        }
+        h->hsForceHost = force_host;
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return TGNH_OK;
+    }
+    // every other layout: upload, step, download on one stream
     CUDA_TRY(cudaMemcpyAsync(h->hsVelm, velm_host, (size_t)h->N * vb, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->hsPosq, posq_host, (size_t)h->N * vb, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->hsForce, force_host, fbytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->hsPosq, posq_host, (size_t)h->N * xb, cudaMemcpyHostToDevice, s));
+    if (mixed) CUDA_TRY(cudaMemcpyAsync(h->hsCorr, posq_correction_host, (size_t)h->N * 16, cudaMemcpyHostToDevice, s));
+    if (uploadForce) CUDA_TRY(cudaMemcpyAsync(h->hsForce, force_host, fbytes, cudaMemcpyHostToDevice, s));
+    h->hsForceHost = force_host;
     h->keValid = false;
     if (int rc = tgnh_step(h, s, h->hsVelm, h->hsPosq, h->hsForce, nsteps)) return rc;
     CUDA_TRY(cudaMemcpyAsync(velm_host, h->hsVelm, (size_t)h->N * vb, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(posq_host, h->hsPosq, (size_t)h->N * vb, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(posq_host, h->hsPosq, (size_t)h->N * xb, cudaMemcpyDeviceToHost, s));
+    if (mixed) CUDA_TRY(cudaMemcpyAsync(posq_correction_host, h->hsCorr, (size_t)h->N * 16, cudaMemcpyDeviceToHost, s));
     if (ke2_host) CUDA_TRY(cudaMemcpyAsync(ke2_host, h->chain.ke2Used, h->T * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return TGNH_OK;
@@ -1212,6 +1372,19 @@ static int d2h(tgnh_handle* h, void* stream, double* dst, const double* src, siz
     if (h->dInbox) CUDA_TRY(cudaMemcpyAsync(&peerError, &h->dInbox->error, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     if (peerError) return fail(TGNH_ERR_NCCL, "a peer rank did not deliver its kinetic energies within 10 s");
+    return TGNH_OK;
+}
+
+extern "C" int tgnh_get_exchange_timing(tgnh_handle* h, void* stream, double* us) {
+    if (!h || !us) return fail(TGNH_ERR_INVALID_ARGUMENT, "null argument");
+    us[0] = us[1] = 0.0;
+    if (!h->dInbox) return TGNH_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long st[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(st, h->dInbox->stamp, sizeof st, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    us[0] = 1e-3 * (double)(long long)(st[2] - st[1]);
+    us[1] = 1e-3 * (double)(long long)(st[1] - st[0]);
     return TGNH_OK;
 }
 

@@ -132,16 +132,19 @@ struct ChainView {
 };
 
 // ---- sharded runs: the kinetic-energy exchange over NVLink peer memory -------------------------------------------
-// Every rank owns an inbox in its HBM that all peers map (CUDA IPC).  The last CTA of a reducing launch stores the
-// rank's partial sums into slot [seq & 1][rank] of EVERY inbox, fences, then publishes `seq` in the matching flag; the
-// chain launch that follows waits for all flags of its own inbox and adds the partials in rank order, so every rank
-// forms bit-identical sums and no collective launch sits between the two kernels.  Two slots suffice: a peer can only
-// be one reduction ahead, because its next one needs this rank's contribution to the current one.
+// Every rank owns an inbox in its HBM that all peers map (CUDA IPC).  The last CTA of a reducing launch writes the rank's partial
+// sums into slot [seq & 1][rank] of EVERY inbox; the chain launch that follows waits for all ranks' words in its own inbox and
+// adds the partials in rank order, so every rank forms bit-identical sums and no collective launch sits between the two kernels.
+// The words are self-validating (the layout of NCCL's LL protocol): each 8-byte word carries 32 bits of payload and the 32-bit
+// sequence number of the reduction, and an aligned 8-byte store is a single transaction, so a reader sees a word either
+// old or complete.  No fence, no separate flag: the exchange costs one NVLink write latency.  Two slots suffice: a peer can only be
+// one reduction ahead, because its next one needs this rank's contribution to the current one.
 constexpr int MAX_PEERS = 16;
 struct PeerInbox {
-    double slot[2][MAX_PEERS][MAX_T];
-    unsigned int flag[2][MAX_PEERS];
+    unsigned long long word[2][MAX_PEERS][2 * MAX_T];   // [slot][sending rank][2 g + half]: (payload << 32) | seq
     unsigned int error;           // set when a wait timed out (a peer died): reported by the next host-side query
+    unsigned int pad;
+    unsigned long long stamp[4];  // %globaltimer of this rank's most recent publish / gather start / gather end (diagnostics)
 };
 struct PeerView {
     int world, rank;              // world <= 1: not sharded (or the NCCL path is in use)
@@ -149,17 +152,12 @@ struct PeerView {
     PeerInbox* inbox[MAX_PEERS];  // inbox[r]: rank r's inbox as mapped into this process (inbox[rank] is local)
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -168,32 +166,38 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-// one thread per peer: publish this rank's partial sums `part[0..T)` (global memory, already visible to this thread)
-__device__ __forceinline__ void peer_publish(const PeerView& pv, const double* part, int T, int r) {
-    PeerInbox* in = pv.inbox[r];
-    const int b = pv.seq & 1;
-    for (int g = 0; g < T; g++) in->slot[b][pv.rank][g] = part[g];
-    __threadfence_system();
-    st_release_sys(&in->flag[b][pv.rank], pv.seq);
+// all threads of the publishing CTA: thread i writes word (i mod 2T) of this rank's sums part[0..T) into rank (i div 2T)'s inbox
+__device__ __forceinline__ void peer_publish(const PeerView& pv, const double* part, int T, int tid, int nthreads) {
+    const int b = pv.seq & 1, words = 2 * T;
+    for (int i = tid; i < pv.world * words; i += nthreads) {
+        const int r = i / words, w = i - r * words;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(part[w >> 1]);
+        const unsigned long long payload = (w & 1) ? (bits >> 32) : (bits & 0xffffffffull);
+        st_relaxed_sys(&pv.inbox[r]->word[b][pv.rank][w], (payload << 32) | pv.seq);
+    }
+    if (tid == 0) pv.inbox[pv.rank]->stamp[0] = global_timer_ns();
 }
 
 // one warp: wait for every rank's partial sums of reduction `seq`, add them in rank order into out[0..T)
 __device__ __forceinline__ void peer_gather(const PeerView& pv, double* out, int T, int lane) {
     PeerInbox* in = pv.inbox[pv.rank];
-    const int b = pv.seq & 1;
-    if (lane < pv.world) {
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(&in->flag[b][lane]) != pv.seq) {
+    const int b = pv.seq & 1, words = 2 * T;
+    const unsigned long long t0 = global_timer_ns();
+    for (int i = lane; i < pv.world * words; i += 32) {
+        const int r = i / words, w = i - r * words;
+        while ((unsigned int)ld_relaxed_sys(&in->word[b][r][w]) != pv.seq)
             if (global_timer_ns() - t0 > 10000000000ull) { in->error = 1u; break; }     // 10 s: a peer is gone
-            __nanosleep(100);
-        }
     }
     __syncwarp();
     if (lane < T) {
         double x = 0.0;
-        for (int r = 0; r < pv.world; r++) x += ld_relaxed_sys(&in->slot[b][r][lane]);
+        for (int r = 0; r < pv.world; r++) {
+            const unsigned long long lo = ld_relaxed_sys(&in->word[b][r][2 * lane]), hi = ld_relaxed_sys(&in->word[b][r][2 * lane + 1]);
+            x += __longlong_as_double((long long)((hi & 0xffffffff00000000ull) | (lo >> 32)));
+        }
         out[lane] = x;
     }
+    if (lane == 0) { in->stamp[1] = t0; in->stamp[2] = global_timer_ns(); }
     __syncwarp();
 }
 

@@ -96,6 +96,8 @@ struct StreamArgs {
     const int* chunkStart;       // [15 * numTiles + 1] first particle of every chunk (tail padded with N)
     const float4* specTable;     // [256 * 3] species table (q0, q1, pad)
     int maxRes;                  // particles in the longest residue (<= 32)
+    int tileBegin;               // first tile of this launch (launches over a sub-range of the tiles: the chunked host-buffer path)
+    int accumulate;              // add this launch's energy sums to what the previous launch over another sub-range left
     double* partials;         // [gridDim.x][T]
     unsigned int* ticket;     // last-CTA-done counter (self-resetting)
     ChainView chain;
@@ -781,7 +783,7 @@ __device__ __forceinline__ bool stream_body(const StreamArgs& a) {
     if (a.peers.world > 1) {
         // sharded: hand this rank's sums to every rank (this one included) over NVLink
         __syncthreads();
-        if (tid < a.peers.world) peer_publish(a.peers, out, T, tid);
+        peer_publish(a.peers, out, T, tid, (int)blockDim.x);
     }
     if (tid == 0) *a.ticket = 0u;
     if (KIND == KIND_KE && a.applyScale && tid < T) a.chain.pending[tid] = 1.0;   // the deferred scaling is now applied

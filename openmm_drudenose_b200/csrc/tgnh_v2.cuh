@@ -124,7 +124,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     const int myTiles = blockIdx.x < a.numTiles ? (a.numTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto tile_of = [&](int it) {
         const int t = blockIdx.x + it * gridDim.x;
-        return a.reverse ? a.numTiles - 1 - t : t;
+        return a.tileBegin + (a.reverse ? a.numTiles - 1 - t : t);
     };
 
     if (tid == 0) {
@@ -353,12 +353,12 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
         for (int b = lane; b < (int)gridDim.x; b += 32) x += __ldcg(a.partials + (size_t)b * T + g);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0) out[g] = x;
+        if (lane == 0) out[g] = a.accumulate ? out[g] + x : x;
     }
     if (a.peers.world > 1) {
         // sharded: hand this rank's sums to every rank (this one included) over NVLink
         __syncthreads();
-        if (tid < a.peers.world) peer_publish(a.peers, out, T, tid);
+        peer_publish(a.peers, out, T, tid, (int)blockDim.x);
     }
     if (tid == 0) *a.ticket = 0u;
     return true;

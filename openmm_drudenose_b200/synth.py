@@ -300,6 +300,26 @@ def build(templates, mol_types, mol_groups, num_temp_groups, *, seed=SEED, first
                        temperature=temperature, **params)
 
 
+def tile(block, reps):
+    """The index tables of `reps` copies of `block` laid end to end (masses, pairs, temperature groups, residue ids, constraints);
+    state arrays stay those of ONE block (callers tile them where they live, e.g. on the device).  For benchmark systems far larger
+    than the host generator can produce in reasonable time."""
+    n, r = block.num_particles, block.num_residues
+    off = (np.arange(reps, dtype=np.int64) * n)[:, None]
+    cons = block.constraints
+    if len(cons):
+        cons = (cons[None, :, :].astype(np.int64) + off[:, :, None]).reshape(-1, 2).astype(np.int32)
+    return DrudeSystem(
+        masses=np.tile(block.masses, reps), pair_drude=(block.pair_drude[None, :] + off).reshape(-1).astype(np.int32),
+        pair_parent=(block.pair_parent[None, :] + off).reshape(-1).astype(np.int32), temp_group=np.tile(block.temp_group, reps),
+        res_id=(block.res_id[None, :].astype(np.int64) + (np.arange(reps, dtype=np.int64) * r)[:, None]).reshape(-1).astype(np.int32),
+        positions=block.positions, velocities=block.velocities, forces=block.forces, k_spring=np.tile(block.k_spring, reps), constraints=cons,
+        num_temp_groups=block.num_temp_groups, num_residues=r * reps, temperature=block.temperature, coupling_time=block.coupling_time,
+        drude_temperature=block.drude_temperature, drude_coupling_time=block.drude_coupling_time, step_size=block.step_size,
+        drude_steps=block.drude_steps, num_nh_chains=block.num_nh_chains, use_drude_nh_chains=block.use_drude_nh_chains,
+        use_com_temp_group=block.use_com_temp_group, max_drude_distance=block.max_drude_distance)
+
+
 def water_box(num_molecules, num_temp_groups=4, *, first_molecule=0, box_molecules=None, **kw):
     """C4 / C5: 4-particle molecules [parent 15.6, drude 0.4, a 1.0, b 1.0]; group of molecule k = k mod G."""
     gidx = np.arange(first_molecule, first_molecule + num_molecules)

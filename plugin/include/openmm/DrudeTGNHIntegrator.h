@@ -69,6 +69,25 @@ public:
     double getResInvMass(int resid) const;
     int getParticleResId(int particle) const;
 
+    // ---- additions of this implementation (no counterpart in the reference; defaults reproduce its behaviour) ----
+    /**
+     * Let the kernel carry the kinetic energies over from the end of one step to the thermostat half-step that begins the next,
+     * instead of reducing them from the velocities again (what the reference does at the start of every step).  This integrator
+     * then tells the kernel about every velocity change it can see: Context::setVelocities (stateChanged) and any
+     * updateContextState() that returns true.  Forces that rewrite velocities in updateContextState and return false
+     * (CMMotionRemover, AndersenThermostat) are invisible to it — switch this on only for Systems without them, or where their
+     * correction is known to be at rounding level.  Set before the Context is created.  Default: off.
+     */
+    void setKineticEnergyCarryOver(bool on) { carryKineticEnergies = on; }
+    bool getKineticEnergyCarryOver() const { return carryKineticEnergies; }
+    /**
+     * Within one step(n) call, fold the velocity scaling that ends a step into the first pass of the next step (velocities are
+     * made consistent before step(n) returns).  Needs the carry-over and a System in which nothing reads or writes velocities
+     * between the steps of a step(n) call.  Set before the Context is created.  Default: off.
+     */
+    void setDeferScaling(bool on) { deferScaling = on; }
+    bool getDeferScaling() const { return deferScaling; }
+
 protected:
     void initialize(ContextImpl& context);
     void cleanup();
@@ -83,6 +102,8 @@ private:
     std::vector<int> particleTempGroup, tempGroups, particleResId;
     std::vector<double> residueMasses, residueInvMasses;
     Kernel kernel;
+    bool carryKineticEnergies, deferScaling;
+    class DrudeTGNHKernelExtensions* extensions;
 };
 
 }  // namespace OpenMM

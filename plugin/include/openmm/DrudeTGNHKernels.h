@@ -1,9 +1,11 @@
 #ifndef TGNH_B200_DRUDETGNH_KERNELS_H_
 #define TGNH_B200_DRUDETGNH_KERNELS_H_
 /*
- * The kernel interface DrudeTGNHIntegrator drives; same name, constructor and three pure virtuals as the reference
- * (/root/reference/openmmapi/include/openmm/DrudeTGNHKernels.h:48-74), so a platform plugin written for the
- * reference still satisfies it.  The two hooks at the end are additions with default bodies.
+ * The kernel interface DrudeTGNHIntegrator drives: the same name, constructor and exactly the three pure virtuals of the
+ * reference (/root/reference/openmmapi/include/openmm/DrudeTGNHKernels.h:48-74), in the same order — the vtable of a
+ * KernelImpl built against this header is the one a reference-built libOpenMMDrudeTGNH.so expects, and the other way round.
+ * What this repo's kernel offers beyond it lives in a separate interface (DrudeTGNHKernelExtensions.h) that an integrator may
+ * discover with dynamic_cast; the reference's integrator never looks for it and gets the reference's semantics.
  */
 #include <string>
 
@@ -25,10 +27,6 @@ public:
     virtual void execute(ContextImpl& context, const DrudeTGNHIntegrator& integrator) = 0;
     /** Kinetic energy for State::getKineticEnergy; isKESumValid = the cached sum of the last step may be used. */
     virtual double computeKineticEnergy(ContextImpl& context, const DrudeTGNHIntegrator& integrator, bool isKESumValid) = 0;
-    /** The state was modified outside the integrator (Context::setVelocities ...): drop cached kinetic energies. */
-    virtual void stateChanged() {}
-    /** step(n) is about to return: make the device state what a reader of the Context expects. */
-    virtual void finishSteps(ContextImpl& context) {}
 };
 
 }  // namespace OpenMM

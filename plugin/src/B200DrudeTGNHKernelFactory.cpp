@@ -10,7 +10,8 @@
 #include "openmm/internal/windowsExport.h"
 
 #ifdef TGNH_WITH_OPENMM
-// Real OpenMM: device arrays come from the CUDA platform's CudaContext (not compilable in this repo's container)
+// Real OpenMM: device arrays come from the CUDA platform's CudaContext.  OpenMM is not installed in this repo's container; the
+// block is compiled and run against the CUDA-platform stand-in of shim/cuda (oracle/Makefile, target _refcuda/libb200cuda.so).
 #include "CudaContext.h"
 #include "CudaPlatform.h"
 namespace OpenMM {
@@ -48,6 +49,8 @@ public:
         };
         cu.addForce(new Info(descriptors, residueOf));
     }
+    void initializeContexts(const System& system) { cu.getPlatformData().initializeContexts(system); }
+    bool atomsWereReordered() { return cu.getAtomsWereReordered(); }
     void applyConstraints(double tol) { cu.getIntegrationUtilities().applyConstraints(tol); }
     void computeVirtualSites() { cu.getIntegrationUtilities().computeVirtualSites(); }
     void applyVelocityConstraints(double tol) { cu.getIntegrationUtilities().applyVelocityConstraints(tol); }
@@ -82,7 +85,7 @@ KernelImpl* B200DrudeTGNHKernelFactory::createKernelImpl(std::string name, const
         throw OpenMMException((std::string("Tried to create kernel with illegal kernel name '") + name + "'").c_str());
 #ifdef TGNH_WITH_OPENMM
     CudaContext& cu = *static_cast<CudaPlatform::PlatformData*>(context.getPlatformData())->contexts[0];
-    return new B200IntegrateDrudeTGNHStepKernel(name, platform, *new CudaContextAccess(cu));   // lives as long as the context
+    return new B200IntegrateDrudeTGNHStepKernel(name, platform, *new CudaContextAccess(cu), true);
 #else
     // shim build: the platform data IS the device access object (plugin/tests/ShimCudaPlatform.h)
     TgnhDeviceAccess* access = static_cast<TgnhDeviceAccess*>(context.getPlatformData());

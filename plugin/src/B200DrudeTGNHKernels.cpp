@@ -12,7 +12,10 @@ void B200IntegrateDrudeTGNHStepKernel::check(int rc) const {
     if (rc != TGNH_OK) throw OpenMMException(std::string("DrudeTGNH (libtgnh): ") + tgnh_last_error());
 }
 
-B200IntegrateDrudeTGNHStepKernel::~B200IntegrateDrudeTGNHStepKernel() { tgnh_destroy(handle); }
+B200IntegrateDrudeTGNHStepKernel::~B200IntegrateDrudeTGNHStepKernel() {
+    tgnh_destroy(handle);
+    if (ownsDevice) delete &device;
+}
 
 // CudaIntegrateDrudeTGNHStepKernel::initialize (CudaDrudeTGNHKernels.cpp:75-282): gather the tables, hand them to tgnh_create
 void B200IntegrateDrudeTGNHStepKernel::initialize(const System& system, const DrudeTGNHIntegrator& integrator, const DrudeForce& force) {
@@ -74,13 +77,16 @@ void B200IntegrateDrudeTGNHStepKernel::initialize(const System& system, const Dr
     p.constraint_p = consA.data();
     p.constraint_p1 = consB.data();
     constrained = system.getNumConstraints() > 0;
-    tgnh_destroy(handle);
-    handle = NULL;
-    check(tgnh_create(&p, &handle));
-    // atom reordering (cu.reorderAtoms): only molecules whose per-particle tables agree may trade places
+    // atom reordering (cu.reorderAtoms): only molecules whose per-particle tables agree may trade places.  The CudaForceInfo
+    // has to be registered before OpenMM finishes setting up its contexts (cu.addForce, then initializeContexts, :76); the
+    // descriptor words come from the host-side plan, which needs no device.
     std::vector<unsigned int> descriptors(n);
     check(tgnh_plan_descriptors(&p, descriptors.data()));
     device.registerForceInfo(descriptors, std::vector<int>(resId.begin(), resId.end()));
+    device.initializeContexts(system);                                                                  // :76
+    tgnh_destroy(handle);
+    handle = NULL;
+    check(tgnh_create(&p, &handle));
 }
 
 // CudaIntegrateDrudeTGNHStepKernel::execute (CudaDrudeTGNHKernels.cpp:284-408)
@@ -88,7 +94,13 @@ void B200IntegrateDrudeTGNHStepKernel::execute(ContextImpl& context, const Drude
     const TgnhDeviceView dv = device.view();
     const double tol = integrator.getConstraintTolerance();
     if (dv.precision == TGNH_PRECISION_MIXED) check(tgnh_set_posq_correction(handle, dv.posqCorrection));
-    if (recomputeKE && !deferScale) check(tgnh_invalidate(handle));     // reference semantics: energies from velm, every step (:336)
+    // Reference semantics unless the integrator has announced that it reports every foreign velocity change: the kinetic
+    // energies are reduced from velm at the start of the step (:336, :471-490).  ContextImpl::updateContextState (barostat,
+    // AndersenThermostat, CMMotionRemover, custom forces) rewrites velocities without telling anybody.
+    if (!carryKE) check(tgnh_invalidate(handle));
+    // the previous step's cu.reorderAtoms() moved atoms: the force buffer belongs to the old order (:344-347).  The thermostat
+    // half-step that the reference runs before this test reads velocities only, so refreshing the forces first is equivalent.
+    if (device.atomsWereReordered()) context.calcForcesAndEnergy(true, false);
     if (!constrained) {
         // thermostat half-step, half kick, drift, hard wall in one launch (:336-376)
         check(tgnh_half1(handle, dv.stream, dv.velm, dv.posq, dv.force));
@@ -126,8 +138,20 @@ double B200IntegrateDrudeTGNHStepKernel::computeKineticEnergy(ContextImpl& conte
     return 0.5 * ke;
 }
 
-void B200IntegrateDrudeTGNHStepKernel::stateChanged() {
+void B200IntegrateDrudeTGNHStepKernel::velocitiesChanged() {
     if (handle != NULL) check(tgnh_invalidate(handle));
+}
+
+std::vector<double> B200IntegrateDrudeTGNHStepKernel::getScaleFactors() {
+    std::vector<double> v(tgnh_num_thermostats(handle));
+    check(tgnh_get_vscale(handle, device.view().stream, v.data()));
+    return v;
+}
+
+void B200IntegrateDrudeTGNHStepKernel::getThermostatParams(std::vector<double>& dof, std::vector<double>& nkbt, std::vector<double>& etaMass) {
+    const int T = tgnh_num_thermostats(handle), M = tgnh_num_nh_chains(handle);
+    dof.assign(T, 0.0); nkbt.assign(T, 0.0); etaMass.assign((size_t)T * M, 0.0);
+    check(tgnh_get_thermostat_params(handle, dof.data(), nkbt.data(), etaMass.data()));
 }
 
 void B200IntegrateDrudeTGNHStepKernel::finishSteps(ContextImpl& context) {

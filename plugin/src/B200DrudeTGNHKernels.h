@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/tgnh.h"
+#include "openmm/DrudeTGNHKernelExtensions.h"
 #include "openmm/DrudeTGNHKernels.h"
 
 namespace OpenMM {
@@ -37,38 +38,49 @@ public:
     virtual void applyConstraints(double tol) {}          // integration.applyConstraints: acts on posDelta
     virtual void computeVirtualSites() {}                 // integration.computeVirtualSites
     virtual void applyVelocityConstraints(double tol) {}  // integration.applyVelocityConstraints: acts on velm
+    /** cu.getPlatformData().initializeContexts(system) (CudaDrudeTGNHKernels.cpp:76): OpenMM finishes setting up its CudaContexts
+     *  (atom order, molecule groups for the reordering) once the last kernel has registered its CudaForceInfo */
+    virtual void initializeContexts(const System& system) {}
+    /** cu.getAtomsWereReordered() (CudaDrudeTGNHKernels.cpp:344): the previous step's cu.reorderAtoms() moved atoms to other
+     *  slots; the force buffer still belongs to the old order */
+    virtual bool atomsWereReordered() { return false; }
     /** Tell the platform which particles are interchangeable for this integrator (equal descriptor words, tgnh_plan_descriptors),
      *  so that its atom reordering leaves the kernels' slot-indexed tables valid.  No-op where atoms are never reordered. */
     virtual void registerForceInfo(const std::vector<unsigned int>& descriptors, const std::vector<int>& residueOf) {}
 };
 
-class B200IntegrateDrudeTGNHStepKernel : public IntegrateDrudeTGNHStepKernel {
+class B200IntegrateDrudeTGNHStepKernel : public IntegrateDrudeTGNHStepKernel, public DrudeTGNHKernelExtensions {
 public:
-    B200IntegrateDrudeTGNHStepKernel(std::string name, const Platform& platform, TgnhDeviceAccess& device)
-        : IntegrateDrudeTGNHStepKernel(name, platform), device(device), handle(NULL), deferScale(false), recomputeKE(false), constrained(false) {}
+    /** ownsDevice: delete `device` with the kernel (the access object the real-OpenMM factory creates per kernel) */
+    B200IntegrateDrudeTGNHStepKernel(std::string name, const Platform& platform, TgnhDeviceAccess& device, bool ownsDevice = false)
+        : IntegrateDrudeTGNHStepKernel(name, platform), device(device), ownsDevice(ownsDevice), handle(NULL), deferScale(false), carryKE(false), constrained(false) {}
     ~B200IntegrateDrudeTGNHStepKernel();
+    // ---- the reference's interface (openmmapi/include/openmm/DrudeTGNHKernels.h:48-74) ----
     void initialize(const System& system, const DrudeTGNHIntegrator& integrator, const DrudeForce& force);
     void execute(ContextImpl& context, const DrudeTGNHIntegrator& integrator);
     double computeKineticEnergy(ContextImpl& context, const DrudeTGNHIntegrator& integrator, bool isKESumValid);
-    void stateChanged();
+    // ---- DrudeTGNHKernelExtensions ----
+    void setKineticEnergyCarryOver(bool on) { carryKE = on; if (!on) deferScale = false; }
+    bool getKineticEnergyCarryOver() const { return carryKE; }
+    void velocitiesChanged();
+    void setDeferScaling(bool on) { deferScale = on && carryKE; }
     void finishSteps(ContextImpl& context);
-    /** thermostat state for checkpointing (the reference keeps it in host vectors and never saves it) */
     void getChainState(std::vector<double>& eta, std::vector<double>& etaDot, std::vector<double>& etaDotDot);
     void setChainState(const std::vector<double>& eta, const std::vector<double>& etaDot, const std::vector<double>& etaDotDot);
-    /** Leave the second half-step's scaling pending between the steps of one step(n) call.  Only safe when nothing else
-     *  (barostat, CMMotionRemover, reporters) touches velocities between steps; off by default. */
-    void setDeferScaling(bool on) { deferScale = on; }
-    /** Recompute the kinetic energies from velm at the start of every step, as the reference does, instead of carrying
-     *  them over from the end of the previous step.  Needed only when something rewrites velocities between steps without
-     *  going through Context::setVelocities (an AndersenThermostat; CMMotionRemover's correction is at rounding level once
-     *  the total momentum has been removed).  Costs one extra pass over velm per step; off by default. */
-    void setRecomputeKineticEnergies(bool on) { recomputeKE = on; }
+    // ---- diagnostics ----
+    /** vscaleFactorsVec of the most recent chain update */
+    std::vector<double> getScaleFactors();
+    /** dof (minus the COM share), N kT, thermostat masses [T*M] */
+    void getThermostatParams(std::vector<double>& dof, std::vector<double>& nkbt, std::vector<double>& etaMass);
+    long long getLaunchCount() const { return tgnh_launch_count(handle); }
+    int getKernelGeneration() const { return tgnh_kernel_generation(handle); }
 private:
     void check(int rc) const;
     TgnhDeviceAccess& device;
+    bool ownsDevice;
     tgnh_handle* handle;
     bool deferScale;
-    bool recomputeKE;
+    bool carryKE;        // the integrator announces velocity changes (DrudeTGNHKernelExtensions): energies are carried over
     bool constrained;    // the System has constraints: the split call sequence leaves room for OpenMM's constraint kernels
 };
 

@@ -5,6 +5,7 @@
 
 #include "openmm/Context.h"
 #include "openmm/DrudeForce.h"
+#include "openmm/DrudeTGNHKernelExtensions.h"
 #include "openmm/DrudeTGNHKernels.h"
 #include "openmm/OpenMMException.h"
 #include "openmm/System.h"
@@ -17,7 +18,7 @@ DrudeTGNHIntegrator::DrudeTGNHIntegrator(double temperature, double couplingTime
                                          int drudeStepsPerRealStep, int numNHChains, bool useDrudeNHChains, bool useCOMTempGroup)
     : temperature(temperature), couplingTime(couplingTime), drudeTemperature(drudeTemperature), drudeCouplingTime(drudeCouplingTime),
       maxDrudeDistance(0.0), drudeStepsPerRealStep(drudeStepsPerRealStep), numNHChains(numNHChains), useDrudeNHChains(useDrudeNHChains),
-      useCOMTempGroup(useCOMTempGroup), isKESumValid(false) {
+      useCOMTempGroup(useCOMTempGroup), isKESumValid(false), carryKineticEnergies(false), deferScaling(false), extensions(NULL) {
     setStepSize(stepSize);
     setConstraintTolerance(1e-5);
 }
@@ -98,15 +99,24 @@ void DrudeTGNHIntegrator::initialize(ContextImpl& contextRef) {
     owner = &contextRef.getOwner();
     kernel = context->getPlatform().createKernel(IntegrateDrudeTGNHStepKernel::Name(), contextRef);
     kernel.getAs<IntegrateDrudeTGNHStepKernel>().initialize(system, *this, *drude);
+    // a kernel that offers the extension interface is told what this integrator guarantees (the reference's integrator never asks)
+    extensions = dynamic_cast<DrudeTGNHKernelExtensions*>(&kernel.getImpl());
+    if (extensions != NULL) {
+        extensions->setKineticEnergyCarryOver(carryKineticEnergies);
+        extensions->setDeferScaling(carryKineticEnergies && deferScaling);
+    }
 }
 
-void DrudeTGNHIntegrator::cleanup() { kernel = Kernel(); }
+void DrudeTGNHIntegrator::cleanup() {
+    extensions = NULL;
+    kernel = Kernel();
+}
 
 void DrudeTGNHIntegrator::stateChanged(State::DataType changed) {
     // the step assumes valid forces on entry, so they are refreshed whenever the user touches the state
     isKESumValid = false;
     if (context != NULL) {
-        kernel.getAs<IntegrateDrudeTGNHStepKernel>().stateChanged();
+        if (extensions != NULL) extensions->velocitiesChanged();
         context->calcForcesAndEnergy(true, false);
     }
 }
@@ -123,9 +133,16 @@ void DrudeTGNHIntegrator::step(int steps) {
     if (context == NULL) throw OpenMMException("This Integrator is not bound to a context!");
     IntegrateDrudeTGNHStepKernel& k = kernel.getAs<IntegrateDrudeTGNHStepKernel>();
     for (int i = 0; i < steps; ++i) {
-        if (context->updateContextState() || context->getLastForceGroups() >= 0) context->calcForcesAndEnergy(true, false);
+        // openmmapi/src/DrudeTGNHIntegrator.cpp:186-189.  Forces that act in updateContextState may rewrite velocities whatever
+        // they return (CMMotionRemover and AndersenThermostat return false): with such forces in the System the carry-over is
+        // only as good as the user's promise (setKineticEnergyCarryOver), and a `true` always invalidates.
+        if (context->updateContextState()) {
+            if (extensions != NULL) extensions->velocitiesChanged();
+            context->calcForcesAndEnergy(true, false);
+        } else if (context->getLastForceGroups() >= 0)
+            context->calcForcesAndEnergy(true, false);
         k.execute(*context, *this);
         isKESumValid = true;
     }
-    k.finishSteps(*context);
+    if (extensions != NULL) extensions->finishSteps(*context);
 }

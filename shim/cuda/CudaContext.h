@@ -69,7 +69,8 @@ public:
     bool getAtomsWereReordered() const { return atomsWereReordered; }
     void setAtomsWereReordered(bool wereReordered) { atomsWereReordered = wereReordered; }
     int shimReorderInterval;
-    int shimReorderCount;
+    int shimReorderCount;      // reorders that moved atoms
+    int shimReorderAttempts;
     /** the source handed to NVRTC by the most recent createModule (tests look at the prelude) */
     std::string shimLastSource;
     long long shimKernelLaunches;

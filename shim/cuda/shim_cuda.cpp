@@ -6,7 +6,6 @@
 // reference builds against; its CMake pins no version, README.md:41-44 names 7.3/7.4) puts in front of every kernel source:
 // the `compilationDefines` of the precision mode, the real/mixed typedefs, `tileflags`, then the caller's defines.
 #include <cuda.h>
-#include <nvrtc.h>
 
 #include <cmath>
 #include <cstdio>
@@ -14,6 +13,7 @@
 #include <sstream>
 
 #include "CudaContext.h"
+#include "CudaKernelPrelude.h"
 #include "openmm/System.h"
 
 namespace OpenMM {
@@ -78,7 +78,7 @@ double CudaIntegrationUtilities::computeKineticEnergy(double) {
 
 // ------------------------------------------------------------------------------------------------ CudaContext
 CudaContext::CudaContext(const System& system, const std::string& precision, CudaPlatform::PlatformData& platformData)
-    : shimReorderInterval(0), shimReorderCount(0), shimKernelLaunches(0), system(system), platformData(platformData), cuContext(NULL), device(0),
+    : shimReorderInterval(0), shimReorderCount(0), shimReorderAttempts(0), shimKernelLaunches(0), system(system), platformData(platformData), cuContext(NULL), device(0),
       deviceIndex(0), numAtoms(system.getNumParticles()), paddedNumAtoms(0), numThreadBlocks(0), stepCount(0), useDoublePrecision(precision == "double"),
       useMixedPrecision(precision == "mixed"), atomsWereReordered(false), time(0.0), posq(NULL), posqCorrection(NULL), velm(NULL), force(NULL),
       atomIndexDevice(NULL), integration(NULL) {
@@ -113,37 +113,7 @@ CudaContext::CudaContext(const System& system, const std::string& precision, Cud
     atomIndexDevice->upload(&atomIndex[0]);
     integration = new CudaIntegrationUtilities(*this, system);
 
-    // compilationDefines, as OpenMM's CudaContext constructor sets them
-    if (useDoublePrecision) {
-        compilationDefines["USE_DOUBLE_PRECISION"] = "1";
-        compilationDefines["make_real2"] = "make_double2"; compilationDefines["make_real3"] = "make_double3"; compilationDefines["make_real4"] = "make_double4";
-        compilationDefines["make_mixed2"] = "make_double2"; compilationDefines["make_mixed3"] = "make_double3"; compilationDefines["make_mixed4"] = "make_double4";
-    } else if (useMixedPrecision) {
-        compilationDefines["USE_MIXED_PRECISION"] = "1";
-        compilationDefines["make_real2"] = "make_float2"; compilationDefines["make_real3"] = "make_float3"; compilationDefines["make_real4"] = "make_float4";
-        compilationDefines["make_mixed2"] = "make_double2"; compilationDefines["make_mixed3"] = "make_double3"; compilationDefines["make_mixed4"] = "make_double4";
-    } else {
-        compilationDefines["make_real2"] = "make_float2"; compilationDefines["make_real3"] = "make_float3"; compilationDefines["make_real4"] = "make_float4";
-        compilationDefines["make_mixed2"] = "make_float2"; compilationDefines["make_mixed3"] = "make_float3"; compilationDefines["make_mixed4"] = "make_float4";
-    }
-    const bool d = useDoublePrecision;
-    compilationDefines["SQRT"] = d ? "sqrt" : "sqrtf";
-    compilationDefines["RSQRT"] = d ? "rsqrt" : "rsqrtf";
-    compilationDefines["RECIP"] = d ? "1.0/" : "1.0f/";
-    compilationDefines["EXP"] = d ? "exp" : "expf";
-    compilationDefines["LOG"] = d ? "log" : "logf";
-    compilationDefines["POW"] = d ? "pow" : "powf";
-    compilationDefines["COS"] = d ? "cos" : "cosf";
-    compilationDefines["SIN"] = d ? "sin" : "sinf";
-    compilationDefines["TAN"] = d ? "tan" : "tanf";
-    compilationDefines["ACOS"] = d ? "acos" : "acosf";
-    compilationDefines["ASIN"] = d ? "asin" : "asinf";
-    compilationDefines["ATAN"] = d ? "atan" : "atanf";
-    compilationDefines["ERF"] = d ? "erf" : "erff";
-    compilationDefines["ERFC"] = d ? "erfc" : "erfcf";
-    compilationDefines["SYNC_WARPS"] = "__syncwarp();";
-    compilationDefines["SHFL(var, srcLane)"] = "__shfl_sync(0xffffffff, var, srcLane);";
-    compilationDefines["BALLOT(var)"] = "__ballot_sync(0xffffffff, var);";
+    compilationDefines = shimCompilationDefines(useDoublePrecision, useMixedPrecision);
 }
 
 CudaContext::~CudaContext() {
@@ -164,52 +134,11 @@ CUmodule CudaContext::createModule(const std::string source, const char* optimiz
 }
 
 CUmodule CudaContext::createModule(const std::string source, const std::map<std::string, std::string>& defines, const char* optimizationFlags) {
-    // OpenMM: options = optimizationFlags == NULL ? "--use_fast_math" : optimizationFlags  (the TGNH sources pass "")
     const std::string options = optimizationFlags == NULL ? "--use_fast_math" : std::string(optimizationFlags);
-    std::stringstream src;
-    if (!options.empty()) src << "// Compilation Options: " << options << "\n\n";
-    for (std::map<std::string, std::string>::const_iterator it = compilationDefines.begin(); it != compilationDefines.end(); ++it) {
-        if (defines.find(it->first) == defines.end()) {
-            src << "#define " << it->first;
-            if (!it->second.empty()) src << " " << it->second;
-            src << "\n";
-        }
-    }
-    src << "\n";
-    const char* r = useDoublePrecision ? "double" : "float";
-    const char* m = (useDoublePrecision || useMixedPrecision) ? "double" : "float";
-    src << "typedef " << r << " real;\ntypedef " << r << "2 real2;\ntypedef " << r << "3 real3;\ntypedef " << r << "4 real4;\n";
-    src << "typedef " << m << " mixed;\ntypedef " << m << "2 mixed2;\ntypedef " << m << "3 mixed3;\ntypedef " << m << "4 mixed4;\n";
-    src << "typedef unsigned int tileflags;\n";
-    for (std::map<std::string, std::string>::const_iterator it = defines.begin(); it != defines.end(); ++it) {
-        src << "#define " << it->first;
-        if (!it->second.empty()) src << " " << it->second;
-        src << "\n";
-    }
-    if (!defines.empty()) src << "\n";
-    src << source << "\n";
-    shimLastSource = src.str();
-
-    nvrtcProgram prog;
-    if (nvrtcCreateProgram(&prog, shimLastSource.c_str(), "openmm_kernel.cu", 0, NULL, NULL) != NVRTC_SUCCESS)
-        throw OpenMMException("CUDA shim: nvrtcCreateProgram failed");
-    std::vector<const char*> opts;
-    opts.push_back("--gpu-architecture=sm_100a");
-    if (options.find("--use_fast_math") != std::string::npos) opts.push_back("--use_fast_math");
-    const nvrtcResult res = nvrtcCompileProgram(prog, (int)opts.size(), &opts[0]);
-    if (res != NVRTC_SUCCESS) {
-        size_t logSize = 0;
-        nvrtcGetProgramLogSize(prog, &logSize);
-        std::string log(logSize, ' ');
-        if (logSize) nvrtcGetProgramLog(prog, &log[0]);
-        nvrtcDestroyProgram(&prog);
-        throw OpenMMException("Error compiling kernel: " + log);
-    }
-    size_t cubinSize = 0;
-    nvrtcGetCUBINSize(prog, &cubinSize);
-    std::vector<char> cubin(cubinSize);
-    nvrtcGetCUBIN(prog, &cubin[0]);
-    nvrtcDestroyProgram(&prog);
+    shimLastSource = shimBuildKernelSource(useDoublePrecision, useMixedPrecision, compilationDefines, source, defines, options);
+    std::vector<char> cubin;
+    std::string log;
+    if (!shimNvrtcCompile(shimLastSource, options, cubin, log)) throw OpenMMException("Error compiling kernel: " + log);
     setAsCurrent();
     CUmodule module;
     check(cuModuleLoadData(&module, &cubin[0]), "cuModuleLoadData");
@@ -260,7 +189,7 @@ void CudaContext::reorderAtoms() {
     // slot ranges of the molecules in the current order: molecules are contiguous index ranges and only whole, equal-sized,
     // identical molecules ever trade places, so slot ranges == original index ranges
     std::vector<std::pair<int, int> > swaps;
-    for (size_t k = (size_t)(shimReorderCount & 1); k + 1 < molecules.size(); k += 2) {
+    for (size_t k = (size_t)(shimReorderAttempts & 1); k + 1 < molecules.size(); k += 2) {
         const std::vector<int>&a = molecules[k], &b = molecules[k + 1];
         if (a.size() != b.size()) continue;
         bool same = true;
@@ -272,8 +201,9 @@ void CudaContext::reorderAtoms() {
         }
         if (same) swaps.push_back(std::make_pair(a[0], b[0] | ((int)a.size() << 24)));
     }
-    shimReorderCount++;
+    shimReorderAttempts++;
     if (swaps.empty()) return;
+    shimReorderCount++;
     auto permute = [&](CudaArray& arr) {
         const int es = arr.getElementSize();
         std::vector<char> h((size_t)arr.getSize() * es), t(es);

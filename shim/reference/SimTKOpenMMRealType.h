@@ -1,5 +1,6 @@
 #ifndef SHIM_SIMTK_REALTYPE_H_
 #define SHIM_SIMTK_REALTYPE_H_
+#include <cmath>   // as the original does (M_PI); the reference's sources rely on it for sqrt / exp / pow
 // OpenMM's physical constants (SimTKOpenMMRealType.h, 2019 SI values); BOLTZ is the one the integrator uses
 #define ANGSTROM     (1e-10)
 #define KILO         (1e3)

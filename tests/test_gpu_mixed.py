@@ -205,24 +205,57 @@ def test_statistical_acceptance_like_the_reference_tests(cuda, prec):
     h.close()
 
 
-@pytest.mark.parametrize("prec", [capi.PRECISION_SINGLE, capi.PRECISION_DOUBLE])
+@pytest.mark.parametrize("prec", [capi.PRECISION_SINGLE, capi.PRECISION_DOUBLE, capi.PRECISION_MIXED])
 def test_step_host_equals_device_path(cuda, prec):
-    """tgnh_step_host (host buffers in, state out: bench.py's e2e leg) gives what the device-buffer calls give; the mixed
-    layout, which needs a third array, is refused with a message."""
+    """tgnh_step_host / tgnh_step_host2 (host buffers in, state out: bench.py's e2e leg) give what the device-buffer calls give.
+    Single precision runs pipelined over 8 particle ranges with the scaling applied at the end of every step, while tgnh_step folds
+    it into the next step's first pass: the (exactly commuting) factors meet the fp32 velocities at different points, hence a
+    tolerance there; the double and mixed layouts take the plain upload - tgnh_step - download sequence and agree bit for bit."""
     import torch
     s = synth.water_box(3000, 3)
     st = DeviceState(s, cuda, precision=prec)
     h = _handle(s, st)
     hv, hx, hf = st.velm.cpu().pin_memory(), st.posq.cpu().pin_memory(), st.force.cpu().pin_memory()
+    hc = st.corr.cpu().pin_memory() if prec == capi.PRECISION_MIXED else None
     h2 = capi.Handle(s, precision=prec, padded=st.padded)
-    for _ in range(3):
-        ke_host = h2.step_host(hv.data_ptr(), hx.data_ptr(), hf.data_ptr(), 2)
+    for i in range(3):
+        ke_host = h2.step_host2(hv.data_ptr(), hx.data_ptr(), hf.data_ptr(), 2, posq_correction_host=None if hc is None else hc.data_ptr(),
+                                forces_unchanged=i > 0)
         h.step(*st.ptrs, nsteps=2)
         h.invalidate()                                     # tgnh_step_host starts every call from the uploaded velocities
-    assert torch.equal(hv, st.velm.cpu()) and torch.equal(hx, st.posq.cpu())
-    np.testing.assert_allclose(ke_host, h.kinetic_energies(), rtol=1e-12)
-    hm = capi.Handle(s, precision=capi.PRECISION_MIXED, padded=st.padded)
-    with pytest.raises(capi.TgnhError) as e:
-        hm.step_host(hv.data_ptr(), hx.data_ptr(), hf.data_ptr(), 1)
-    assert e.value.code == capi.ERR_UNSUPPORTED
-    h.close(); h2.close(); hm.close()
+    if prec == capi.PRECISION_SINGLE:
+        assert h2.kernel_generation == 2
+        n = s.num_particles
+        assert rel_err(hv[:n, :3].double().numpy(), st.vel()) < 5e-6 and rel_err(hx[:n, :3].double().numpy(), st.pos()) < 1e-6
+        np.testing.assert_allclose(ke_host, h.kinetic_energies(), rtol=1e-5)
+        assert torch.equal(hv[:, 3], st.velm.cpu()[:, 3]) and torch.equal(hx[:, 3], st.posq.cpu()[:, 3])
+    else:
+        assert torch.equal(hv, st.velm.cpu()) and torch.equal(hx, st.posq.cpu())
+        if hc is not None:
+            assert torch.equal(hc, st.corr.cpu())
+        np.testing.assert_allclose(ke_host, h.kinetic_energies(), rtol=1e-12)
+    if prec == capi.PRECISION_MIXED:
+        with pytest.raises(capi.TgnhError) as e:           # the old entry point has no room for the third array
+            h2.step_host(hv.data_ptr(), hx.data_ptr(), hf.data_ptr(), 1)
+        assert e.value.code == capi.ERR_UNSUPPORTED
+    h.close(); h2.close()
+
+
+def test_step_host_pipelined_one_step_against_oracle(cuda):
+    """One pipelined host-buffer step (8 particle ranges, three streams) against the oracle: the chunked launches cover every tile once
+    and the energy sums accumulate over the ranges."""
+    from oracle import oracle as O
+    s = synth.water_box(20000, 4, quantize_masses=True)
+    st = DeviceState(s, cuda)
+    hv, hx, hf = st.velm.cpu().pin_memory(), st.posq.cpu().pin_memory(), st.force.cpu().pin_memory()
+    h = capi.Handle(s, padded=st.padded)
+    o = O.Oracle(s, O.TG)
+    p, v, f = s.positions.copy(), s.velocities.copy(), s.forces.copy()
+    for _ in range(2):
+        ke = h.step_host2(hv.data_ptr(), hx.data_ptr(), hf.data_ptr(), 1)
+        o.step(p, v, f, 1)
+    n = s.num_particles
+    assert rel_err(hv[:n, :3].double().numpy(), v) < 2e-5 and rel_err(hx[:n, :3].double().numpy(), p) < 1e-5
+    np.testing.assert_allclose(ke, o.ke2, rtol=1e-6)
+    np.testing.assert_allclose(h.vscale(), o.vscale, rtol=1e-6)
+    h.close()
