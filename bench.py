@@ -36,10 +36,16 @@ C4_MOLECULES = 2_500_000  # x 4 particles = 10M
 C5_MOLECULES = 50_000_000 # x 4 particles = 200M
 
 MOLECULES_OVERRIDE = 0
+# generator options of the C4 family (synth.build): "c4" is a state the thermostats can hold for the length of a bench run
+C4_STATE = {"c4": dict(pair_force="common", cold_drudes=True, force_sigma=2.0), "c4-hot": dict(pair_force="common"),
+            "c4-wall": dict(pair_force="frozen_spring")}
 
 WORKLOADS = {
     "c4": "C4 synthetic 10M-particle Drude system (2.5M 4-particle molecules, 2.5M Drude pairs), G=4, M=3, S=20, "
-          "COM group on, hard wall 0.02 nm, fixed fp32 SoA forces",
+          "COM group on, hard wall 0.02 nm, fixed fp32 SoA forces (sigma 2 kJ/mol/nm), equilibrated dual-thermostat start "
+          "(300 K / Drude 1 K): thermostats hold their targets, ~0.5 % of the pairs meet the wall per step",
+    "c4-hot": "round 1's C4 state: independent 300 K velocities on every particle and fixed forces of sigma 200 kJ/mol/nm (the Drude "
+              "thermostat quenches all relative motion, group temperatures run to 2e4 K, the chain takes its full-range exp path)",
     "c4-wall": "C4 with the frozen-spring pair forces of SURVEY.md 8d: every Drude pair hits the hard wall on every step "
                "(hard-wall stress case)",
     "c5": "C5 synthetic 200M-particle Drude system sharded over the ranks, G=4",
@@ -94,13 +100,12 @@ class ClockSampler:
 
 
 def make_system(workload, rank, world):
-    if workload in ("c4", "c4-wall"):
+    if workload in ("c4", "c4-wall", "c4-hot"):
         mol = MOLECULES_OVERRIDE or C4_MOLECULES
-        return synth.water_box(mol, 4, first_molecule=rank * mol, box_molecules=world * mol,
-                               pair_force="frozen_spring" if workload == "c4-wall" else "common")
+        return synth.water_box(mol, 4, first_molecule=rank * mol, box_molecules=world * mol, **C4_STATE[workload])
     if workload == "c5":
         per = C5_MOLECULES // world
-        return synth.water_box(per, 4, first_molecule=rank * per, box_molecules=C5_MOLECULES)
+        return synth.water_box(per, 4, first_molecule=rank * per, box_molecules=C5_MOLECULES, **C4_STATE["c4"])
     if workload == "c1":
         return synth.nacl_box()
     if workload == "c2":
@@ -159,8 +164,8 @@ def cpu_port_all_cores(system, steps):
 
 def cpu_sample_system(workload):
     """Bounded sample of the workload for the CPU legs: 1M particles of the same generator (C4/C5), else the config itself."""
-    if workload in ("c4", "c4-wall", "c5"):
-        return synth.water_box(250_000, 4, box_molecules=C4_MOLECULES, pair_force="frozen_spring" if workload == "c4-wall" else "common")
+    if workload in ("c4", "c4-wall", "c4-hot", "c5"):
+        return synth.water_box(250_000, 4, box_molecules=C4_MOLECULES, **C4_STATE.get(workload, C4_STATE["c4"]))
     return make_system(workload, 0, 1)
 
 
@@ -470,7 +475,7 @@ def c5_leg(torch, capi, dev, local, comm, rank, world, stream, barrier, dist, st
     block_mol = min(per_mol, C4_MOLECULES)
     reps = per_mol // block_mol
     per_mol = reps * block_mol
-    block = synth.water_box(block_mol, 4, first_molecule=rank * per_mol, box_molecules=C5_MOLECULES)
+    block = synth.water_box(block_mol, 4, first_molecule=rank * per_mol, box_molecules=C5_MOLECULES, **C4_STATE["c4"])
     nb = block.num_particles
     n = nb * reps
     system = synth.tile(block, reps)

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtgnh.so")
+LIB_PATH = os.environ.get("TGNH_LIB") or os.path.join(_HERE, "libtgnh.so")      # TGNH_LIB: experimental builds of the same library
 
 OK, ERR_INVALID_ARGUMENT, ERR_TEMP_GROUP, ERR_UNSUPPORTED, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE = range(7)
 FORCE_F32_SOA, FORCE_I64_SOA = 0, 1

@@ -160,8 +160,8 @@ struct tgnh_handle {
     unsigned char* dSpec = nullptr;
     int* dChunkStart = nullptr;
     float4* dSpecTable = nullptr;
-    int numTiles2 = 0, maxRes = 1, numSpecies = 0;
-    int gridA2v = 0, gridB2v = 0, gridKE2v = 0, smemA2v = 0, smemB2v = 0, smemKE2v = 0;
+    int numTiles2 = 0, maxRes = 1, numSpecies = 0, butterfly = 0;
+    int gridA2v = 0, gridB2v = 0, gridKE2v = 0, gridS2v = 0, smemA2v = 0, smemB2v = 0, smemKE2v = 0, smemS2v = 0;
     bool earlyOK = false;         // set by tgnh_step around launches whose predecessors in the stream are its own
     std::vector<int> hChunkStart; // host copy of dChunkStart (chunk boundaries of the pipelined host-buffer path)
     // pipelined host-buffer path (tgnh_step_host2)
@@ -406,7 +406,7 @@ struct HostPlan {
     std::vector<int> chunkStart;
     std::vector<unsigned char> spec;
     std::vector<float> specTable;
-    int maxRes = 1, numTiles2 = 0, numSpecies = 0;
+    int maxRes = 1, numTiles2 = 0, numSpecies = 0, butterfly = 0;
 };
 
 // Chunks, species bytes and the species table of the warp-chunk kernels.  Needs the legacy plan's resFirst/resLast/partner/role.
@@ -431,8 +431,8 @@ static void build_plan_v2(const tgnh_params* p, HostPlan& hp) {
     hp.chunkStart.resize((size_t)V2_NCONS * hp.numTiles2 + 1, N);
     // species: particles that agree in everything the kernels look up per particle
     std::map<std::array<uint64_t, 4>, int> rows;
-    hp.spec.assign((size_t)((N + 15) & ~15) + 32, (unsigned char)V2_NULL);
-    hp.specTable.assign((size_t)V2_ROWS * V2_ROW_F4 * 4, 0.f);
+    hp.spec.assign((size_t)((N + 15) & ~15) + 32, (unsigned char)0);
+    hp.specTable.assign((size_t)(V2_MAX_SPECIES + 1) * V2_ROW_F4 * 4, 0.f);
     auto bits = [](double x) { uint64_t b; memcpy(&b, &x, 8); return b; };
     auto put_row = [&](int row, double m, double mu, double invM, double fpartner, uint32_t meta) {
         float* q = &hp.specTable[(size_t)row * V2_ROW_F4 * 4];
@@ -442,7 +442,6 @@ static void build_plan_v2(const tgnh_params* p, HostPlan& hp) {
         q[0] = mh; q[1] = (float)(m - (double)mh); q[2] = ih; q[3] = metaf;
         q[4] = muh; q[5] = (float)(mu - (double)muh); q[6] = (float)(invM - (double)ih); q[7] = (float)fpartner;
     };
-    put_row(V2_NULL, 0.0, 0.0, 0.0, 0.0, v2_meta_pack(0, ROLE_NORMAL, true, 0));
     // a tiny direct-mapped cache in front of the map: consecutive molecules repeat the same few species (200 M particles in C5)
     struct Slot { std::array<uint64_t, 4> key; int row; };
     std::vector<Slot> cache(256, Slot{{~0ull, ~0ull, ~0ull, ~0ull}, -1});
@@ -450,13 +449,13 @@ static void build_plan_v2(const tgnh_params* p, HostPlan& hp) {
         const int r = p->particle_res_id[i];
         const double m = p->masses[i], mj = hp.partner[i] ? p->masses[i + hp.partner[i]] : 0.0;
         const double M = hp.resMass[r];                                   // summed in particle order, as calcCOMVelocities does (:90-100)
-        const uint32_t meta = v2_meta_pack(p->particle_temp_group[i], hp.role[i], i == hp.resFirst[r], hp.partner[i]);
+        const uint32_t meta = v2_meta_pack(p->particle_temp_group[i], hp.role[i], hp.partner[i], i - hp.resFirst[r], hp.resLast[r] - i);
         const std::array<uint64_t, 4> key = {bits(m), bits(mj), bits(M), (uint64_t)meta};
         Slot& slot = cache[(size_t)((key[0] * 0x9E3779B97F4A7C15ull ^ key[1] * 0xC2B2AE3D27D4EB4Full ^ key[2] ^ key[3] * 0x165667B19E3779F9ull) >> 56)];
         if (slot.row < 0 || slot.key != key) {
             auto it = rows.find(key);
             if (it == rows.end()) {
-                if ((int)rows.size() >= V2_NULL) { hp.v2why = "more than 255 particle species"; return; }
+                if ((int)rows.size() >= V2_MAX_SPECIES) { hp.v2why = "more than 255 particle species"; return; }
                 const int row = (int)rows.size();
                 it = rows.emplace(key, row).first;
                 const bool pair = hp.partner[i] != 0;
@@ -468,6 +467,16 @@ static void build_plan_v2(const tgnh_params* p, HostPlan& hp) {
         hp.spec[i] = (unsigned char)slot.row;
     }
     hp.numSpecies = (int)rows.size();
+    put_row(hp.numSpecies, 0.0, 0.0, 0.0, 0.0, v2_meta_pack(0, ROLE_NORMAL, 0, 0, 0));     // "no particle": massless, alone in its residue
+    hp.specTable.resize((size_t)(hp.numSpecies + 1) * V2_ROW_F4 * 4);
+    // residues of one power-of-two size: chunks hold 32 / size whole residues at aligned lanes, a butterfly sums them
+    hp.butterfly = 0;
+    {
+        const int k = hp.resLast[0] - hp.resFirst[0] + 1;
+        bool same = (k & (k - 1)) == 0 && k <= 32;
+        for (int r = 0; r < R && same; r++) same = hp.resLast[r] - hp.resFirst[r] + 1 == k;
+        if (same) hp.butterfly = k;
+    }
     hp.v2 = true;
 }
 
@@ -621,6 +630,7 @@ static StreamKernel pick_v2(int kind, int ffmt, bool useCOM, bool hardwall) {
         if (ffmt) return useCOM ? tgnh_v2_kernel<V2_B, 1, true, false> : tgnh_v2_kernel<V2_B, 1, false, false>;
         return useCOM ? tgnh_v2_kernel<V2_B, 0, true, false> : tgnh_v2_kernel<V2_B, 0, false, false>;
     }
+    if (kind == V2_S) return useCOM ? tgnh_v2_kernel<V2_S, 0, true, false> : tgnh_v2_kernel<V2_S, 0, false, false>;
     return useCOM ? tgnh_v2_kernel<V2_KE, 0, true, false> : tgnh_v2_kernel<V2_KE, 0, false, false>;
 }
 static StreamKernel pick_v2_fused(int kind, int ffmt, bool useCOM) {
@@ -630,10 +640,11 @@ static StreamKernel pick_v2_fused(int kind, int ffmt, bool useCOM) {
     }
     return useCOM ? tgnh_v2_chain_kernel<V2_KE, 0, true> : tgnh_v2_chain_kernel<V2_KE, 0, false>;
 }
-static int smem_v2(int kind, int ffmt, int T) {
-    if (kind == V2_A) return ffmt ? V2Layout<V2_A, 1>::bytes(T) : V2Layout<V2_A, 0>::bytes(T);
-    if (kind == V2_B) return ffmt ? V2Layout<V2_B, 1>::bytes(T) : V2Layout<V2_B, 0>::bytes(T);
-    return V2Layout<V2_KE, 0>::bytes(T);
+static int smem_v2(int kind, int ffmt, int T, int rows) {
+    if (kind == V2_A) return ffmt ? V2Layout<V2_A, 1>::bytes(T, rows) : V2Layout<V2_A, 0>::bytes(T, rows);
+    if (kind == V2_B) return ffmt ? V2Layout<V2_B, 1>::bytes(T, rows) : V2Layout<V2_B, 0>::bytes(T, rows);
+    if (kind == V2_S) return V2Layout<V2_S, 0>::bytes(T, rows);
+    return V2Layout<V2_KE, 0>::bytes(T, rows);
 }
 
 extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
@@ -804,7 +815,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         const char* e = getenv("TGNH_V2");
         h->v2 = hp.v2 && !(e && atoi(e) == 0);
         if (h->v2) {
-            h->numTiles2 = hp.numTiles2; h->maxRes = hp.maxRes; h->numSpecies = hp.numSpecies;
+            h->numTiles2 = hp.numTiles2; h->maxRes = hp.maxRes; h->numSpecies = hp.numSpecies; h->butterfly = hp.butterfly;
             h->hChunkStart = hp.chunkStart;
             if (!dmalloc((void**)&h->dSpec, hp.spec.size()) || !dmalloc((void**)&h->dChunkStart, hp.chunkStart.size() * 4) ||
                 !dmalloc((void**)&h->dSpecTable, hp.specTable.size() * 4))
@@ -812,14 +823,14 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
             cudaMemcpy(h->dSpec, hp.spec.data(), hp.spec.size(), cudaMemcpyHostToDevice);
             cudaMemcpy(h->dChunkStart, hp.chunkStart.data(), hp.chunkStart.size() * 4, cudaMemcpyHostToDevice);
             cudaMemcpy(h->dSpecTable, hp.specTable.data(), hp.specTable.size() * 4, cudaMemcpyHostToDevice);
-            int* grids[3] = {&h->gridA2v, &h->gridB2v, &h->gridKE2v};
-            int* smems[3] = {&h->smemA2v, &h->smemB2v, &h->smemKE2v};
-            for (int kind = 0; kind < 3 && h->v2; kind++) {
+            int* grids[4] = {&h->gridA2v, &h->gridB2v, &h->gridKE2v, &h->gridS2v};
+            int* smems[4] = {&h->smemA2v, &h->smemB2v, &h->smemKE2v, &h->smemS2v};
+            for (int kind = 0; kind < 4 && h->v2; kind++) {
                 StreamKernel k = pick_v2(kind, h->ffmt, h->useCOM, h->hardwall);
-                const int smem = smem_v2(kind, h->ffmt, h->T);
+                const int smem = smem_v2(kind, h->ffmt, h->T, h->numSpecies + 1);
                 int occ = 0;
                 if (smem > 227 * 1024 || cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, 512, smem) != cudaSuccess || occ < 1) {
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k, V2_THREADS, smem) != cudaSuccess || occ < 1) {
                     (void)cudaGetLastError();
                     h->v2 = false;              // e.g. 30 temperature groups: the energy columns do not fit beside the ring
                     break;
@@ -834,7 +845,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
                 for (int kind : {V2_B, V2_KE}) {
                     if (!h->fuseChain) break;
                     if (cudaFuncSetAttribute((const void*)pick_v2_fused(kind, h->ffmt, h->useCOM), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             smem_v2(kind, h->ffmt, h->T)) != cudaSuccess) {
+                                             smem_v2(kind, h->ffmt, h->T, h->numSpecies + 1)) != cudaSuccess) {
                         (void)cudaGetLastError();
                         h->fuseChain = false;
                     }
@@ -899,8 +910,10 @@ extern "C" int tgnh_plan_chunks(const tgnh_params* p, int32_t* chunk_start, int3
         for (int i = 0; i <= n; i++) chunk_start[i] = hp.chunkStart[i];
     }
     if (species_out) memcpy(species_out, hp.spec.data(), p->num_particles);
-    if (table_out)
-        for (int r = 0; r < V2_ROWS; r++) memcpy(table_out + 8 * r, &hp.specTable[(size_t)r * V2_ROW_F4 * 4], 32);
+    if (table_out) {
+        memset(table_out, 0, 256 * 8 * sizeof(float));
+        for (int r = 0; r <= hp.numSpecies; r++) memcpy(table_out + 8 * r, &hp.specTable[(size_t)r * V2_ROW_F4 * 4], 32);
+    }
     return TGNH_OK;
 }
 
@@ -1024,14 +1037,14 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     a.fusedChainMode = fused ? chainMode : CHAIN_NONE;
     a.earlyLoads = h->earlyOK ? 1 : 0;
     // the two halves and the plain reduction run through the warp-chunk kernels where the system qualifies
-    const int kind2 = !h->v2 ? -1 : kind == KIND_A ? V2_A : kind == h->kindB ? V2_B : (kind == h->kindKE && !applyScale) ? V2_KE : -1;
+    const int kind2 = !h->v2 ? -1 : kind == KIND_A ? V2_A : kind == h->kindB ? V2_B : (kind == h->kindKE && !applyScale) ? V2_KE : kind == KIND_S ? V2_S : -1;
     if (kind2 >= 0) {
-        a.spec = h->dSpec; a.chunkStart = h->dChunkStart; a.specTable = h->dSpecTable; a.maxRes = h->maxRes;
+        a.spec = h->dSpec; a.chunkStart = h->dChunkStart; a.specTable = h->dSpecTable; a.maxRes = h->maxRes; a.butterfly = h->butterfly; a.tableRows = h->numSpecies + 1;
         a.numTiles = h->numTiles2;
-        const int grid2 = kind2 == V2_A ? h->gridA2v : kind2 == V2_B ? h->gridB2v : h->gridKE2v;
-        const int smem2 = kind2 == V2_A ? h->smemA2v : kind2 == V2_B ? h->smemB2v : h->smemKE2v;
-        if (fused) CUDA_TRY(launch_pdl(pick_v2_fused(kind2, h->ffmt, h->useCOM), h->numTiles2, 512, smem2, s, (const StreamArgs)a));
-        else CUDA_TRY(launch_pdl(pick_v2(kind2, h->ffmt, h->useCOM, h->hardwall), grid2, 512, smem2, s, (const StreamArgs)a));
+        const int grid2 = kind2 == V2_A ? h->gridA2v : kind2 == V2_B ? h->gridB2v : kind2 == V2_S ? h->gridS2v : h->gridKE2v;
+        const int smem2 = kind2 == V2_A ? h->smemA2v : kind2 == V2_B ? h->smemB2v : kind2 == V2_S ? h->smemS2v : h->smemKE2v;
+        if (fused) CUDA_TRY(launch_pdl(pick_v2_fused(kind2, h->ffmt, h->useCOM), h->numTiles2, V2_THREADS, smem2, s, (const StreamArgs)a));
+        else CUDA_TRY(launch_pdl(pick_v2(kind2, h->ffmt, h->useCOM, h->hardwall), grid2, V2_THREADS, smem2, s, (const StreamArgs)a));
     } else if (fused) CUDA_TRY(launch_pdl(pick_fused(kind, h->ffmt, h->prec, h->useCOM), h->numTiles, TILE, smem, s, (const StreamArgs)a));
     else CUDA_TRY(launch_pdl(k, grid, TILE, smem, s, (const StreamArgs)a));
     if (e1) CUDA_TRY(cudaEventRecord(e1, s));
@@ -1204,12 +1217,12 @@ static int launch_v2_range(tgnh_handle* h, cudaStream_t s, int kind2, void* velm
     a.peers = h->peers;
     const bool reduces = kind2 != V2_A;
     if (h->peers.world > 1 && reduces && last) a.peers.seq = ++h->reduceSeq; else a.peers.world = 0;
-    a.spec = h->dSpec; a.chunkStart = h->dChunkStart; a.specTable = h->dSpecTable; a.maxRes = h->maxRes;
+    a.spec = h->dSpec; a.chunkStart = h->dChunkStart; a.specTable = h->dSpecTable; a.maxRes = h->maxRes; a.butterfly = h->butterfly; a.tableRows = h->numSpecies + 1;
     a.numTiles = tileCount; a.tileBegin = tileBegin; a.accumulate = accumulate ? 1 : 0;
     int grid = kind2 == V2_A ? h->gridA2v : kind2 == V2_B ? h->gridB2v : h->gridKE2v;
     if (grid > tileCount) grid = tileCount;
     const int smem = kind2 == V2_A ? h->smemA2v : kind2 == V2_B ? h->smemB2v : h->smemKE2v;
-    CUDA_TRY(launch_pdl(pick_v2(kind2, h->ffmt, h->useCOM, h->hardwall), grid, 512, smem, s, (const StreamArgs)a));
+    CUDA_TRY(launch_pdl(pick_v2(kind2, h->ffmt, h->useCOM, h->hardwall), grid, V2_THREADS, smem, s, (const StreamArgs)a));
     h->launches++;
     return TGNH_OK;
 }

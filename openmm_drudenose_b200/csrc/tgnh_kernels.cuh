@@ -94,8 +94,10 @@ struct StreamArgs {
     // warp-chunk kernels (tgnh_v2.cuh)
     const unsigned char* spec;   // [roundup16(N) + 32] species-table row of every particle
     const int* chunkStart;       // [15 * numTiles + 1] first particle of every chunk (tail padded with N)
-    const float4* specTable;     // [256 * 3] species table (q0, q1, pad)
+    const float4* specTable;     // [tableRows * 3] species table (q0, q1, pad); the last row is "no particle"
+    int tableRows;
     int maxRes;                  // particles in the longest residue (<= 32)
+    int butterfly;               // > 0: every residue has this many particles (a power of two) and every chunk is full or ends the system
     int tileBegin;               // first tile of this launch (launches over a sub-range of the tiles: the chunked host-buffer path)
     int accumulate;              // add this launch's energy sums to what the previous launch over another sub-range left
     double* partials;         // [gridDim.x][T]
@@ -256,6 +258,18 @@ __device__ __forceinline__ V3<T> scaled_velocity(V3<T> v, T eT, V3<T> r, T eCOM,
               v.z + fma(c, rel.z, fma(eT, r.z, eCOM * V.z)));
 }
 template <typename T> __device__ __forceinline__ V3<T> kicked(V3<T> v, T fw, V3<T> F) { return axpy(fw, F, v); }
+
+// The same with the factors eT and eCOM as float PAIRS (hi + lo = the double s - 1).  A factor rounded to fp32 is off by up to
+// 6e-8 |s - 1|: when a thermostat works hard (|s - 1| ~ 1e-2: start-up transients, the Drude thermostat) that is a scale error of
+// 5e-10 on every particle of the group, with one sign, step after step — and a systematic scale error of 1e-9 per step moves the
+// group's chain velocities by 1e-6 relative (measured: scripts/dev_bias.py, DESIGN.md "Parity").
+struct F2 { float hi, lo; };
+__device__ __forceinline__ F2 split2(double x) { F2 r; r.hi = (float)x; r.lo = (float)(x - (double)r.hi); return r; }
+__device__ __forceinline__ V3<float> scaled_velocity2(V3<float> v, F2 eT, V3<float> r, F2 eCOM, V3<float> V, float c, V3<float> rel) {
+    const V3<float> t = v3(fmaf(eT.lo, r.x, eCOM.lo * V.x), fmaf(eT.lo, r.y, eCOM.lo * V.y), fmaf(eT.lo, r.z, eCOM.lo * V.z));
+    return v3(v.x + fmaf(c, rel.x, fmaf(eT.hi, r.x, fmaf(eCOM.hi, V.x, t.x))), v.y + fmaf(c, rel.y, fmaf(eT.hi, r.y, fmaf(eCOM.hi, V.y, t.y))),
+              v.z + fmaf(c, rel.z, fmaf(eT.hi, r.z, fmaf(eCOM.hi, V.z, t.z))));
+}
 
 // positions: single = posq; mixed = posq + posqCorrection in double (drudeTGNH.cu:441-448, 476-486)
 template <int PREC> struct PosTile;
@@ -622,7 +636,8 @@ __device__ __forceinline__ bool stream_body(const StreamArgs& a) {
         } else {
             // thermostat scaling (integrateDrudeTGNHChain, drudeTGNH.cu:255-300) in the unified form of the header comment
             r = v - V;
-            vn = scaled_velocity(v, eT, r, eCOM, V, coef * fj, rel);
+            if constexpr (PREC == 0) vn = scaled_velocity2(v, split2(seps[tg]), r, split2(seps[G]), V, coef * fj, rel);
+            else vn = scaled_velocity(v, eT, r, eCOM, V, coef * fj, rel);
         }
 
         if (LAB) {
@@ -710,7 +725,9 @@ __device__ __forceinline__ bool stream_body(const StreamArgs& a) {
                 // the partner's update, recomputed here so that both threads of a pair see the same wall test;
                 // seen from the partner, rel changes sign and the mass fraction is this particle's
                 const R3 rj = vj - V;
-                R3 vjn = kicked(scaled_velocity(vj, eT, rj, eCOM, V, coef * fi, -rel), fwj, Fj);
+                R3 vjn;
+                if constexpr (PREC == 0) vjn = kicked(scaled_velocity2(vj, split2(seps[tg]), rj, split2(seps[G]), V, coef * fi, -rel), fwj, Fj);
+                else vjn = kicked(scaled_velocity(vj, eT, rj, eCOM, V, coef * fi, -rel), fwj, Fj);
                 typename PosTile<PREC>::Q qj;
                 const R3 xj = pos.load(pj, qj);
                 // displacement from the exact difference of the old positions plus the relative drift: avoids the

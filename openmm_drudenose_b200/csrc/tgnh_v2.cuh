@@ -6,6 +6,7 @@
 //   V2_B   second half  = integrateDrudeTGNHVelocities + calcCOMVelocities + normalizeVelocities +
 //                         computeNormalizedKineticEnergies + sumNormalizedKineticEnergies (:307-365, 82-133, 138-242)
 //   V2_KE  reduce       = the kinetic-energy reduction alone                              (:82-242)
+//   V2_S   scale        = integrateDrudeTGNHChain alone                                   (:249-301)
 // with a different decomposition of the work, chosen from the round-1 profile of the second-half kernel (58.8 M warp
 // instructions, 40 % XU pipe, 7.5 M shared-memory bank conflicts, all warps of a CTA coupled through the slowest one):
 //
@@ -23,8 +24,13 @@
 //    loop contains no reciprocal, no float<->double conversion and no fp64 instruction at all.
 //  * PRODUCER WARP.  Warp 15 only streams: it waits for a stage to be released by the 15 consumer warps and requests the
 //    next tile (cp.async.bulk / UBLKCP completing on the stage's mbarrier).  No consumer ever blocks on a refill.
-//  * fp32 running sums per thread, moved into the thread's fp64 column every 16 tiles; fp64 from there on (warp
-//    shuffles -> CTA -> fixed-order sum over the CTAs by the last one), bit-reproducible run to run.
+//  * fp32 running sums per thread (the thread's group sum moves to its fp32 column when the group changes); fp64 from
+//    the end of the tile loop on (warp shuffles -> CTA -> fixed-order sum over the CTAs by the last one), bit-reproducible
+//    run to run.
+//  * Round-2 profile of the first version (57 M warp instructions, issue slots 62 % busy, DRAM 53 %): the position of a
+//    particle inside its residue comes from the species row instead of a ballot / bit-scan chain per tile, residues of one
+//    power-of-two size are summed by a butterfly (the sum lands in every lane), the energy columns are fp32 (shared
+//    memory for a third resident CTA per SM).
 //
 // Kinetic energies, in the reference's own form (:152-188) with V the residue's centre-of-mass velocity:
 //     group tg:   sum_i m_i |v_i - V|^2  -  sum_pairs mu |v_d - v_p|^2      (= sum (m_d+m_p) |cm - V|^2 + normal particles)
@@ -36,46 +42,52 @@
 
 namespace tgnh {
 
-enum { V2_A = 0, V2_B = 1, V2_KE = 2 };
-constexpr int V2_NCONS = 15;                  // consumer warps per CTA (warp 15 is the producer)
+enum { V2_A = 0, V2_B = 1, V2_KE = 2, V2_S = 3 };
+#ifndef TGNH_V2_NCONS
+#define TGNH_V2_NCONS 15
+#endif
+constexpr int V2_NCONS = TGNH_V2_NCONS;       // consumer warps per CTA (the last warp is the producer)
+constexpr int V2_THREADS = (V2_NCONS + 1) * 32;
+constexpr int V2_CTAS = V2_NCONS > 15 ? 1 : 2;   // resident CTAs per SM the kernels are compiled for
 constexpr int V2_TILE = V2_NCONS * 32;        // particles per tile, at most
 constexpr int V2_FW = V2_TILE + 8;            // 4-aligned window of force components that covers any tile
 constexpr int V2_SW = V2_TILE + 32;           // 16-aligned window of species bytes that covers any tile
-constexpr int V2_ROWS = 256;                  // species table rows (row 255 = "no particle")
-constexpr int V2_NULL = 255;
+constexpr int V2_MAX_SPECIES = 255;           // species rows; the table's last row (index = number of species) is "no particle"
 constexpr int V2_ROW_F4 = 3;                  // float4 per row: q0, q1, pad (48 B stride: neighbouring rows fall into different banks)
 
 // species-table row
-//   q0 = { m_hi, m_lo, 1/M_res (hi), meta }          meta: [4:0] temperature group, [6:5] role, [7] first particle of its
-//   q1 = { mu_hi, mu_lo, 1/M_res (lo), f_partner }         residue, [15:8] signed offset to the pair partner (0 = none)
-__host__ __device__ inline uint32_t v2_meta_pack(int tg, uint32_t role, bool first, int partner) {
-    return (uint32_t)(tg & 31) | (role << 5) | (first ? 0x80u : 0u) | ((uint32_t)(partner & 0xff) << 8);
+//   q0 = { m_hi, m_lo, 1/M_res (hi), meta }          meta: [4:0] temperature group, [6:5] role, [12:7] signed offset to the pair
+//   q1 = { mu_hi, mu_lo, 1/M_res (lo), f_partner }         partner (0 = none), [17:13] offset back to the first particle of the
+//                                                          residue, [22:18] offset forward to its last particle
+__host__ __device__ inline uint32_t v2_meta_pack(int tg, uint32_t role, int partner, int offFirst, int offLast) {
+    return (uint32_t)(tg & 31) | (role << 5) | ((uint32_t)(partner & 63) << 7) | ((uint32_t)offFirst << 13) | ((uint32_t)offLast << 18);
 }
 __device__ __forceinline__ int v2_tg(uint32_t m) { return m & 31; }
 __device__ __forceinline__ uint32_t v2_role(uint32_t m) { return (m >> 5) & 3; }
-__device__ __forceinline__ bool v2_first(uint32_t m) { return (m & 0x80u) != 0; }
-__device__ __forceinline__ int v2_partner(uint32_t m) { return ((int32_t)(m << 16)) >> 24; }
+__device__ __forceinline__ int v2_partner(uint32_t m) { return ((int32_t)(m << 19)) >> 26; }
+__device__ __forceinline__ int v2_off_first(uint32_t m) { return (m >> 13) & 31; }
+__device__ __forceinline__ int v2_off_last(uint32_t m) { return (m >> 18) & 31; }
 
 template <int KIND, int FFMT>
 struct V2Layout {
     static constexpr bool HAS_X = (KIND == V2_A);
-    static constexpr bool HAS_F = (KIND != V2_KE);
-    static constexpr bool HAS_KE = (KIND != V2_A);
+    static constexpr bool HAS_F = (KIND == V2_A || KIND == V2_B);
+    static constexpr bool HAS_KE = (KIND == V2_B || KIND == V2_KE);
     static constexpr int FBYTES = FFMT == 1 ? 8 : 4;
-    static constexpr int NSTAGE = HAS_X ? 3 : 4;
+    static constexpr int NSTAGE = V2_NCONS > 15 ? (HAS_X ? 4 : 6) : (HAS_X ? 3 : 4);
     static constexpr int OFF_V = 0;
     static constexpr int OFF_X = OFF_V + V2_TILE * 16;
     static constexpr int OFF_F = OFF_X + (HAS_X ? V2_TILE * 16 : 0);
     static constexpr int OFF_S = OFF_F + (HAS_F ? 3 * V2_FW * FBYTES : 0);
-    static constexpr int OFF_HDR = OFF_S + V2_SW;            // int start, pad[3]; uint16 chunkOff[16]; pad
-    static constexpr int STAGE = OFF_HDR + 64;
+    static constexpr int OFF_HDR = OFF_S + V2_SW;            // int start, pad[3]; uint16 chunkOff[V2_NCONS + 1]; pad
+    static constexpr int STAGE = OFF_HDR + 16 + ((2 * (V2_NCONS + 1) + 15) & ~15);
     static constexpr int OFF_BAR = NSTAGE * STAGE;            // full[NS], empty[NS]
-    static constexpr int OFF_TAB = OFF_BAR + 128;
-    static constexpr int OFF_SCALE = OFF_TAB + V2_ROWS * V2_ROW_F4 * 16;   // double[MAX_T] s^2 (unused), double[MAX_T] s - 1
+    static constexpr int OFF_SCALE = OFF_BAR + 128;           // double[MAX_T] s^2 (unused), double[MAX_T] s - 1
     static constexpr int OFF_MISC = OFF_SCALE + MAX_T * 16;
-    static constexpr int OFF_WARP = OFF_MISC + 16;            // double[T][16]
-    static constexpr int OFF_KE = OFF_WARP + (HAS_KE ? MAX_T * 16 * 8 : 0);
-    static int bytes(int T) { return OFF_KE + (HAS_KE ? T * V2_TILE * 8 : 0); }
+    static constexpr int OFF_WARP = OFF_MISC + 16;            // double[T][32]
+    static constexpr int OFF_KE = OFF_WARP + (HAS_KE ? MAX_T * 32 * 8 : 0);        // float[T][V2_TILE]: per-thread group sums
+    __host__ __device__ static int off_table(int T) { return OFF_KE + (HAS_KE ? T * V2_TILE * 4 : 0); }   // then the species table: rows x 48 B
+    static int bytes(int T, int rows) { return off_table(T) + rows * V2_ROW_F4 * 16; }
 };
 
 template <int FFMT>
@@ -103,24 +115,42 @@ __device__ __forceinline__ void seg_scan(V3<float>& p, int lane, int segStart, i
     }
 }
 
+// Sum of `p` over the residue of every lane, delivered to ALL its lanes.  bfly > 0: every residue of the system has `bfly` particles (a
+// power of two) and chunks are full, so residues are aligned lane groups and a butterfly does it; otherwise a segmented scan
+// followed by a read of the segment's last lane.
+__device__ __forceinline__ V3<float> residue_sum(V3<float> p, int lane, int offFirst, int offLast, int maxRes, int bfly) {
+    if (bfly > 0) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+            if (o < bfly) {
+                p.x += __shfl_xor_sync(0xffffffffu, p.x, o); p.y += __shfl_xor_sync(0xffffffffu, p.y, o); p.z += __shfl_xor_sync(0xffffffffu, p.z, o);
+            }
+        return p;
+    }
+    seg_scan(p, lane, lane - offFirst, maxRes);
+    const int last = lane + offLast;
+    return v3(__shfl_sync(0xffffffffu, p.x, last), __shfl_sync(0xffffffffu, p.y, last), __shfl_sync(0xffffffffu, p.z, last));
+}
+
 // Body of the warp-chunk kernels.  Returns true in the one CTA that finished the grid-wide energy reduction (all threads of it).
 template <int KIND, int FFMT, bool USE_COM, bool HARDWALL>
 __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     using L = V2Layout<KIND, FFMT>;
     constexpr int NS = L::NSTAGE;
-    constexpr bool IS_A = (KIND == V2_A);
+    constexpr bool IS_A = (KIND == V2_A || KIND == V2_S);        // the kinds that apply the thermostat factors
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     uint64_t* empty = full + NS;
-    float4* stab = reinterpret_cast<float4*>(smem + L::OFF_TAB);
-    double* seps = reinterpret_cast<double*>(smem + L::OFF_SCALE) + MAX_T;      // s_g - 1
+    float2* seps = reinterpret_cast<float2*>(smem + L::OFF_SCALE);              // s_g - 1 as a float pair (hi, lo)
+    float* scoef = reinterpret_cast<float*>(smem + L::OFF_SCALE) + 2 * MAX_T;    // s_g - s_Drude
     int* smisc = reinterpret_cast<int*>(smem + L::OFF_MISC);
     double* swarp = reinterpret_cast<double*>(smem + L::OFF_WARP);
-    double* ske = reinterpret_cast<double*>(smem + L::OFF_KE);
+    float* ske = reinterpret_cast<float*>(smem + L::OFF_KE);
     float4* gvelm = static_cast<float4*>(a.velm);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = a.chain.T, G = a.chain.G;
+    float4* stab = reinterpret_cast<float4*>(smem + L::off_table(T));
     const int myTiles = blockIdx.x < a.numTiles ? (a.numTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto tile_of = [&](int it) {
         const int t = blockIdx.x + it * gridDim.x;
@@ -131,10 +161,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
         for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], V2_NCONS); }
         fence_mbar_init();
     }
-    for (int i = tid; i < V2_ROWS * V2_ROW_F4; i += 512) stab[i] = __ldg(a.specTable + i);     // static table: safe before pdl_wait
-    if (L::HAS_KE && tid < V2_TILE)
-        for (int g = 0; g < T; g++) ske[g * V2_TILE + tid] = 0.0;
-    __syncthreads();
+    __syncthreads();                                    // the barriers exist: the producer may start streaming
 
     const uint64_t polOnce = policy_evict_first();
     // Producer: request tile `it` of this CTA into its stage (the whole warp calls; lane 0 issues the copies).
@@ -170,33 +197,42 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     auto chunk_bounds = [&](int it) { return lane <= V2_NCONS ? __ldg(a.chunkStart + V2_NCONS * tile_of(it) + lane) : 0; };
 
     const bool producer = warp == V2_NCONS;
-    // prologue: inputs that no earlier launch of this stream can still be writing may be requested before griddepcontrol.wait
-    // (only when the host knows that the preceding launches are this library's own and do not write them: a.earlyLoads)
-    if (producer && a.earlyLoads)
-        for (int it = 0; it < NS && it < myTiles; it++) issue(it, 1, chunk_bounds(it));
-    pdl_wait();                                         // everything below reads what earlier launches wrote
-    if (tid < T) seps[tid] = (IS_A ? a.chain.scaleA[tid] : 1.0) - 1.0;
+    const int preloaded = myTiles < NS ? myTiles : NS;
+    if (producer) {
+        // The first NS tiles are requested while the consumer warps still copy the species table and clear their energy columns.
+        // Inputs that no earlier launch of this stream can still be writing may even be requested before griddepcontrol.wait (only
+        // when the host knows that the preceding launches are this library's own and do not write them: a.earlyLoads).
+        if (a.earlyLoads)
+            for (int it = 0; it < preloaded; it++) issue(it, 1, chunk_bounds(it));
+        pdl_wait();                                     // everything below reads what earlier launches wrote
+        for (int it = 0; it < preloaded; it++) issue(it, a.earlyLoads ? 2 : 3, chunk_bounds(it));
+    } else {
+        for (int i = tid; i < a.tableRows * V2_ROW_F4; i += V2_TILE) stab[i] = __ldg(a.specTable + i);     // static table: safe before the wait
+        if (L::HAS_KE)
+            for (int g = 0; g < T; g++) ske[g * V2_TILE + tid] = 0.f;
+        pdl_wait();
+        if (tid < T) {
+            const double e = (IS_A ? a.chain.scaleA[tid] : 1.0) - 1.0, eD = (IS_A ? a.chain.scaleA[T - 1] : 1.0) - 1.0;
+            const F2 f = split2(e);
+            seps[tid] = make_float2(f.hi, f.lo);
+            scoef[tid] = (float)(e - eD);
+        }
+    }
     __syncthreads();
 
-    float accT = 0.f, accCOM = 0.f, accDrude = 0.f;    // this thread's running sums (fp32, flushed every 16 tiles)
+    float accT = 0.f, accCOM = 0.f, accDrude = 0.f;    // this thread's running sums: its current group, the COM group, the Drude group
     int curTg = -1;
-    auto flush = [&]() {
-        if (curTg >= 0) ske[curTg * V2_TILE + tid] += (double)accT;
-        ske[G * V2_TILE + tid] += (double)accCOM;
-        ske[(G + 1) * V2_TILE + tid] += (double)accDrude;
-        accT = accCOM = accDrude = 0.f;
-    };
 
     if (producer) {
-        for (int it = 0; it < myTiles; it++) {
+        for (int it = preloaded; it < myTiles; it++) {
             const int cs = chunk_bounds(it);
-            if (it >= NS) mbar_wait(&empty[it % NS], ((it / NS) - 1) & 1);
-            issue(it, (a.earlyLoads && it < NS) ? 2 : 3, cs);
+            mbar_wait(&empty[it % NS], ((it / NS) - 1) & 1);
+            issue(it, 3, cs);
         }
     } else {
-        const float eCOM = IS_A ? (float)seps[G] : 0.f, eDrude = IS_A ? (float)seps[G + 1] : 0.f;
+        F2 eCOM; eCOM.hi = seps[G].x; eCOM.lo = seps[G].y;
         const float dt = (float)a.dt, fscale = (float)a.fscale, rmax = (float)a.rmax, rmax2 = rmax * rmax;
-        const int maxRes = USE_COM ? a.maxRes : 1;
+        const int maxRes = USE_COM ? a.maxRes : 1, bfly = a.butterfly;
         for (int it = 0; it < myTiles; it++) {
             const int stg = it % NS;
             unsigned char* st = smem + stg * L::STAGE;
@@ -211,7 +247,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
             const bool active = lane < cn;
             const int i = c0 + lane;                                 // index inside the tile
             float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            int sp = V2_NULL;
+            int sp = a.tableRows - 1;                              // the "no particle" row
             V3<float> F = v3(0.f, 0.f, 0.f);
             if (active) {
                 v4 = sv[i];
@@ -227,11 +263,8 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
             const float w = v4.w;
             const bool massive = w != 0.f;
             const float fw = fscale * w;
-            // residue segments of this chunk
-            const uint32_t firstMask = __ballot_sync(0xffffffffu, v2_first(meta));
-            const uint32_t below = firstMask & (0xffffffffu >> (31 - lane)), above = firstMask & ~(0xffffffffu >> (31 - lane));
-            const int segStart = 31 - __clz(below);
-            const int lastLane = above ? __ffs(above) - 2 : 31;
+            const int offFirst = v2_off_first(meta), offLast = v2_off_last(meta);    // position inside the residue (all of it in this warp)
+            const unsigned int gidx = (unsigned int)(start + i);                      // unsigned: one IMAD.WIDE per address
 
             if (IS_A) {
                 // thermostat scaling (integrateDrudeTGNHChain, drudeTGNH.cu:255-300) in the unified form of tgnh_kernels.cuh,
@@ -239,15 +272,20 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                 const float4 q1 = stab[sp * V2_ROW_F4 + 1];
                 V3<float> V = v3(0.f, 0.f, 0.f);
                 if (USE_COM) {
-                    V3<float> p = q0.x * v;                          // V only feeds the corrections (sT-1)(v-V), (sCOM-1)V: fp32 masses are ample
-                    seg_scan(p, lane, segStart, maxRes);
-                    V = v3(__shfl_sync(0xffffffffu, p.x, lastLane), __shfl_sync(0xffffffffu, p.y, lastLane), __shfl_sync(0xffffffffu, p.z, lastLane));
-                    V = q0.z * V;
+                    // V only feeds the corrections (sT-1)(v-V), (sCOM-1)V: fp32 masses are ample
+                    V = q0.z * residue_sum(q0.x * v, lane, offFirst, offLast, maxRes, bfly);
                 }
                 const V3<float> vj = v3(__shfl_sync(0xffffffffu, v.x, pl), __shfl_sync(0xffffffffu, v.y, pl), __shfl_sync(0xffffffffu, v.z, pl));
                 const V3<float> rel = vj - v;
-                const float eT = (float)seps[tg];
-                V3<float> vn = scaled_velocity(v, eT, v - V, eCOM, V, (eT - eDrude) * q1.w, rel);
+                const float2 e2 = seps[tg];
+                F2 eT; eT.hi = e2.x; eT.lo = e2.y;
+                V3<float> vn = scaled_velocity2(v, eT, v - V, eCOM, V, scoef[tg] * q1.w, rel);
+                if (KIND == V2_S) {
+                    if (active && massive) st_global(gvelm + gidx, pack4(vn, w));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[stg]);
+                    continue;
+                }
                 vn = kicked(vn, fw, F);
                 float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (active) x4 = sx[i];
@@ -272,25 +310,23 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                     }
                 }
                 if (active && massive) {
-                    st_global(gvelm + start + i, pack4(vn, w));
-                    st_stream(static_cast<float4*>(a.posq) + start + i, make_float4(xn.x, xn.y, xn.z, x4.w));
+                    st_global(gvelm + gidx, pack4(vn, w));
+                    st_stream(static_cast<float4*>(a.posq) + gidx, make_float4(xn.x, xn.y, xn.z, x4.w));
                 }
             } else {
                 // half kick (integrateDrudeTGNHVelocities, :314-364; V2_KE: F = 0, nothing stored), then the energies of
                 // what was stored
                 const V3<float> vn = kicked(v, fw, F);
-                if (KIND == V2_B && active && massive) st_global(gvelm + start + i, pack4(vn, w));
+                if (KIND == V2_B && active && massive) st_global(gvelm + gidx, pack4(vn, w));
                 V3<float> V = v3(0.f, 0.f, 0.f);
                 float keC = 0.f;
-                const bool first = v2_first(meta);
+                const bool first = offFirst == 0;
                 const bool needQ1 = role == ROLE_DRUDE || (USE_COM && first);
                 float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (needQ1) q1 = stab[sp * V2_ROW_F4 + 1];
                 if (USE_COM) {
                     // calcCOMVelocities (:86-105): P = sum m v over the residue, V = P / M
-                    V3<float> p = v3(mul2(q0.x, q0.y, vn.x), mul2(q0.x, q0.y, vn.y), mul2(q0.x, q0.y, vn.z));
-                    seg_scan(p, lane, segStart, maxRes);
-                    const V3<float> P = v3(__shfl_sync(0xffffffffu, p.x, lastLane), __shfl_sync(0xffffffffu, p.y, lastLane), __shfl_sync(0xffffffffu, p.z, lastLane));
+                    const V3<float> P = residue_sum(v3(mul2(q0.x, q0.y, vn.x), mul2(q0.x, q0.y, vn.y), mul2(q0.x, q0.y, vn.z)), lane, offFirst, offLast, maxRes, bfly);
                     V = q0.z * P;
                     if (first) keC = mul2(q0.z, q1.z, dot3(P));      // |P|^2 / M  (:154), carried by the residue's first particle
                 }
@@ -304,14 +340,15 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                     accDrude += keD;
                 }
                 accCOM += keC;
+                // this thread's particles usually stay in one group from tile to tile (molecule-periodic group patterns): the running
+                // sum lives in a register and moves to its shared-memory column only when the group changes
                 if (active && massive) {
                     if (tg != curTg) {
-                        if (curTg >= 0) { ske[curTg * V2_TILE + tid] += (double)accT; accT = 0.f; }
+                        if (curTg >= 0) { ske[curTg * V2_TILE + tid] += accT; accT = 0.f; }
                         curTg = tg;
                     }
                     accT += ke;
                 }
-                if ((it & 15) == 15) flush();
             }
             // hand the stage back: one arrival per consumer warp
             __syncwarp();
@@ -319,25 +356,31 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
         }
     }
     pdl_launch_dependents();
+    if (KIND == V2_S && blockIdx.x == 0 && tid < T) {
+        // the factors are applied: the kinetic energies of the stored velocities are s_g^2 KE_g (residue-uniform groups)
+        const double sg = a.chain.scaleA[tid];
+        a.chain.ke2[tid] *= sg * sg;
+        a.chain.pending[tid] = 1.0;
+    }
     if (!L::HAS_KE) return false;
 
     // ---- deterministic reduction: thread columns -> warp -> CTA -> (last CTA) grid ----
     if (!producer) {
-        flush();
+        if (curTg >= 0) ske[curTg * V2_TILE + tid] += accT;
         for (int g = 0; g < T; g++) {
-            double x = ske[g * V2_TILE + tid];
+            double x = g == G ? (double)accCOM : g == G + 1 ? (double)accDrude : (double)ske[g * V2_TILE + tid];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-            if (lane == 0) swarp[g * 16 + warp] = x;
+            if (lane == 0) swarp[g * 32 + warp] = x;
         }
     }
     __syncthreads();
     if (tid < T) {
         double x = 0.0;
-        for (int w = 0; w < V2_NCONS; w++) x += swarp[tid * 16 + w];
+        for (int w = 0; w < V2_NCONS; w++) x += swarp[tid * 32 + w];
         a.partials[(size_t)blockIdx.x * T + tid] = x;
+        __threadfence();                               // only the writers: a fence in all 512 threads costs a microsecond per CTA
     }
-    __threadfence();
     __syncthreads();
     if (tid == 0) {
         const unsigned int t = atomicAdd(a.ticket, 1u);
@@ -348,7 +391,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     __threadfence();
     // last CTA: warp g sums column g of the partials over all CTAs in a fixed order
     double* out = a.useLocalKE ? a.chain.ke2Local : a.chain.ke2;
-    for (int g = warp; g < T; g += 16) {
+    for (int g = warp; g < T; g += V2_NCONS + 1) {
         double x = 0.0;
         for (int b = lane; b < (int)gridDim.x; b += 32) x += __ldcg(a.partials + (size_t)b * T + g);
 #pragma unroll
@@ -365,14 +408,15 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
 }
 
 template <int KIND, int FFMT, bool USE_COM, bool HARDWALL>
-__global__ void __launch_bounds__(512, 2) tgnh_v2_kernel(const __grid_constant__ StreamArgs a) {
+__global__ void __launch_bounds__(V2_THREADS, V2_CTAS) tgnh_v2_kernel(const __grid_constant__ StreamArgs a) {
     v2_body<KIND, FFMT, USE_COM, HARDWALL>(a);
 }
+
 
 // Small systems (every CTA owns at most one tile): the CTA that finishes the energy reduction runs the Nose-Hoover chain
 // update itself instead of a separate chain launch (see tgnh_stream_chain_kernel).
 template <int KIND, int FFMT, bool USE_COM>
-__global__ void __launch_bounds__(512, 1) tgnh_v2_chain_kernel(const __grid_constant__ StreamArgs a) {
+__global__ void __launch_bounds__(V2_THREADS, 1) tgnh_v2_chain_kernel(const __grid_constant__ StreamArgs a) {
     if (!v2_body<KIND, FFMT, USE_COM, false>(a)) return;
     __syncthreads();                                   // the energy vector written by this CTA's warps
     if (threadIdx.x < 32) chain_phase(a.chain, a.fusedChainMode, threadIdx.x);

@@ -109,7 +109,7 @@ const char* cudadrv_flavour() {
 void* cudadrv_create(int n, const double* masses, int npairs, const int* pairDrude, const int* pairParent, const int* resId, const int* tempGroup,
                      int numTempGroups, double temperature, double couplingTime, double drudeTemperature, double drudeCouplingTime, double stepSize,
                      int drudeSteps, int numNHChains, int useDrudeNHChains, int useCOMTempGroup, double maxDrudeDistance, int hasCMMotionRemover,
-                     int precision, int forceModel, const double* kSpring, int reorderInterval) {
+                     int precision, int forceModel, const double* kSpring, int reorderInterval, int numConstraints, const int* consA, const int* consB) {
     Sim* s = NULL;
     try {
         Quiet q;
@@ -126,6 +126,8 @@ void* cudadrv_create(int n, const double* masses, int npairs, const int* pairDru
         for (int i = 1; i < n; i++) if (resId[i] == resId[i - 1]) bonds->addBond(i - 1, i);
         s->system.addForce(bonds);
         if (hasCMMotionRemover) s->system.addForce(new CMMotionRemover());
+        // constraints enter the DOF bookkeeping (CudaDrudeTGNHKernels.cpp:186-196); the stand-in platform applies none (it counts the calls)
+        for (int i = 0; i < numConstraints; i++) s->system.addConstraint(consA[i], consB[i], 0.1);
         s->integrator = new DrudeTGNHIntegrator(temperature, couplingTime, drudeTemperature, drudeCouplingTime, stepSize, drudeSteps, numNHChains,
                                                 useDrudeNHChains != 0, useCOMTempGroup != 0);
         s->integrator->setMaxDrudeDistance(maxDrudeDistance);

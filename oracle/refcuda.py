@@ -30,7 +30,7 @@ def lib(flavour):
         L.cudadrv_last_error.restype = C.c_char_p
         L.cudadrv_flavour.restype = C.c_char_p
         L.cudadrv_create.restype = vp
-        L.cudadrv_create.argtypes = [C.c_int, dp, C.c_int, ip, ip, ip, ip, C.c_int] + [C.c_double] * 5 + [C.c_int] * 4 + [C.c_double] + [C.c_int] * 3 + [dp, C.c_int]
+        L.cudadrv_create.argtypes = [C.c_int, dp, C.c_int, ip, ip, ip, ip, C.c_int] + [C.c_double] * 5 + [C.c_int] * 4 + [C.c_double] + [C.c_int] * 3 + [dp, C.c_int, C.c_int, ip, ip]
         L.cudadrv_destroy.argtypes = [vp]
         L.cudadrv_num_residues.argtypes = [vp]
         L.cudadrv_set_state.argtypes = [vp, dp, dp, dp]
@@ -69,7 +69,7 @@ class CudaSim:
                 "compute_virtual_sites", "step_count")
 
     def __init__(self, system, flavour="reference", precision="double", force_model=0, has_cm_motion_remover=False, reorder_interval=0,
-                 assign_groups=True):
+                 assign_groups=True, with_constraints=True):
         s = system
         self.L = L = lib(flavour)
         self.flavour, self.n = flavour, s.num_particles
@@ -78,10 +78,14 @@ class CudaSim:
                       np.ascontiguousarray(s.pair_parent, np.int32), np.ascontiguousarray(s.res_id, np.int32),
                       np.ascontiguousarray(s.temp_group, np.int32), np.ascontiguousarray(s.k_spring, np.float64)]
         m, pd, pp, res, tg, k = self._keep
+        cons = np.ascontiguousarray(s.constraints, np.int32).reshape(-1, 2) if with_constraints else np.zeros((0, 2), np.int32)
+        ca, cb = np.ascontiguousarray(cons[:, 0]), np.ascontiguousarray(cons[:, 1])
+        self._keep += [ca, cb]
         self.h = L.cudadrv_create(s.num_particles, _dp(m), len(pd), _ip(pd), _ip(pp), _ip(res), _ip(tg) if assign_groups else None,
                                   s.num_temp_groups, s.temperature, s.coupling_time, s.drude_temperature, s.drude_coupling_time, s.step_size,
                                   s.drude_steps, s.num_nh_chains, int(s.use_drude_nh_chains), int(s.use_com_temp_group), s.max_drude_distance,
-                                  int(has_cm_motion_remover), PRECISION[precision], force_model, _dp(k), reorder_interval)
+                                  int(has_cm_motion_remover), PRECISION[precision], force_model, _dp(k), reorder_interval,
+                                  len(cons), _ip(ca) if len(cons) else None, _ip(cb) if len(cons) else None)
         if not self.h:
             raise CudaDriverError(L.cudadrv_last_error().decode())
 

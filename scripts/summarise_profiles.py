@@ -18,18 +18,23 @@ for name in (f"bench_{R}.json", f"bench_ref_{R}.json", f"bench_wall_{R}.json", f
         shutil.copy(os.path.join(G, name), os.path.join(P, name))
 
 # launch list -> per-kernel table
-rows = [r for r in csv.reader(open(os.path.join(G, f"launches_{R}.csv"))) if len(r) > 5]
-hdr = rows[0]; ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+if not os.path.exists(os.path.join(G, f"launches_{R}.csv")):
+    rows = []
+else:
+    rows = [r for r in csv.reader(open(os.path.join(G, f"launches_{R}.csv"))) if len(r) > 5]
 agg = collections.OrderedDict()
-for r in rows[1:]:
-    agg.setdefault(r[ki], []).append(float(r[vi].replace(",", "")) / 1000.0)
+if rows:
+    hdr = rows[0]; ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    for r in rows[1:]:
+        agg.setdefault(r[ki], []).append(float(r[vi].replace(",", "")) / 1000.0)
 total = sum(sum(v) for v in agg.values())
 lines = [f"# ncu launch list ({R}): `python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline`",
          "# gpu__time_duration.sum per launch, --clock-control none (cold cache, serialised: compare SHARES)", "",
          "| kernel | launches | mean us | min us | max us | share of listed time |", "|---|---|---|---|---|---|"]
 for k, v in agg.items():
     lines.append(f"| `{k}` | {len(v)} | {sum(v)/len(v):.2f} | {min(v):.2f} | {max(v):.2f} | {100*sum(v)/total:.1f} % |")
-open(os.path.join(P, f"launch_summary_{R}.md"), "w").write("\n".join(lines) + "\n")
+if rows:
+    open(os.path.join(P, f"launch_summary_{R}.md"), "w").write("\n".join(lines) + "\n")
 
 # full capture -> raw metrics of interest
 rep = os.path.join(G, f"prof_{R}.ncu-rep")
@@ -43,7 +48,8 @@ if os.path.exists(rep):
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
             "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
             "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
-            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
+            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
     idx = {x: i for i, x in enumerate(h)}
     out = [f"# ncu --set full --clock-control none ({R}), 10M-particle C4 workload; default cache control (L2 flushed before each pass)", ""]
     summary = {}
@@ -53,7 +59,8 @@ if os.path.exists(rep):
             if w in idx:
                 out.append(f"- {w}: {r[idx[w]]} {u[idx[w]]}")
         out.append("")
-        kind = "half1" if "<0," in r[idx["Kernel Name"]] else ("half2" if ("<3," in r[idx["Kernel Name"]] or "<1," in r[idx["Kernel Name"]]) else "reduce")
+        kn = r[idx["Kernel Name"]]
+        kind = "half1" if "<0," in kn else ("half2" if ("<3," in kn or "<1," in kn) else "reduce")
         def num(m):
             return float(r[idx[m]].replace(",", ""))
         ur, uw = u[idx["dram__bytes_read.sum"]], u[idx["dram__bytes_write.sum"]]

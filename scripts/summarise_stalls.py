@@ -4,7 +4,7 @@ R = sys.argv[1] if len(sys.argv) > 1 else "r1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = os.path.join(ROOT, "gpurun_out", f"prof_{R}.ncu-rep")
 out = [f"# Warp-stall sampling per SASS instruction ({R}; `ncu --set full --import-source on`, C4 workload)", ""]
-for skip, title in ((0, "first-half kernel (KIND_A)"), (1, "second-half kernel (KIND_BU)")):
+for skip, title in ((0, "first-half kernel"), (1, "second-half kernel")):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(skip), "--launch-count", "1"],
                          capture_output=True, text=True).stdout
     rr = list(csv.reader(io.StringIO(raw)))

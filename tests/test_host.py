@@ -235,3 +235,94 @@ def test_descriptors_say_which_particles_are_interchangeable():
     assert np.array_equal(tg, np.repeat((np.arange(8) % 2)[:, None], 4, 1))
     assert np.array_equal(role[0], [2, 1, 0, 0]) and np.array_equal(partner[0], [1, -1, 0, 0])       # parent, Drude, H, H
     assert np.array_equal((d[0] >> 10) & 0x7f, [0, 1, 2, 3]) and np.array_equal((d[0] >> 17) & 0x7f, [3, 2, 1, 0])
+
+
+# ---- the warp-chunk plan (csrc/tgnh_v2.cuh): chunks, species bytes, species table ----------------------------------------------------------
+def _assert_chunk_invariants(s, cs, spec, table, nspec, maxres):
+    n = s.num_particles
+    assert cs[0] == 0 and cs[-1] == n and (len(cs) - 1) % 15 == 0 and np.all(np.diff(cs) >= 0) and np.diff(cs).max() <= 32
+    res = np.asarray(s.res_id)
+    starts = np.unique(cs[cs < n])
+    assert np.all(res[starts[1:]] != res[starts[1:] - 1])                       # every chunk starts a residue ...
+    sizes = np.bincount(res)
+    assert maxres == sizes.max()
+    # ... and a pair's partner lies in its own chunk
+    chunk_of = np.searchsorted(cs, np.arange(n), side="right") - 1
+    chunk_of = np.searchsorted(starts, np.arange(n), side="right") - 1
+    assert np.array_equal(chunk_of[s.pair_drude], chunk_of[s.pair_parent])
+    # species rows: masses as hi + lo floats, reduced mass, residue inverse mass, mass fraction of the partner, meta bits
+    assert spec.max() < nspec <= 255
+    m = np.asarray(s.masses, np.float64)
+    row = table[spec].astype(np.float64)
+    meta = table[spec, 3].view(np.uint32)
+    np.testing.assert_allclose(row[:, 0] + row[:, 1], m, rtol=1e-14, atol=0)
+    resmass = np.bincount(res, weights=m)
+    with np.errstate(divide="ignore"):
+        invm = np.where(resmass[res] > 0, 1.0 / resmass[res], 0.0)
+    np.testing.assert_allclose(row[:, 2] + row[:, 6], invm, rtol=1e-13, atol=0)
+    partner = np.zeros(n, np.int64); role = np.zeros(n, np.int64)
+    partner[s.pair_drude] = s.pair_parent - s.pair_drude; partner[s.pair_parent] = s.pair_drude - s.pair_parent
+    role[s.pair_drude] = 1; role[s.pair_parent] = 2
+    assert np.array_equal(meta & 31, s.temp_group) and np.array_equal((meta >> 5) & 3, role)
+    p6 = ((meta.astype(np.int64) >> 7) & 63)
+    assert np.array_equal(np.where(p6 >= 32, p6 - 64, p6), partner)
+    first_idx = np.r_[0, np.nonzero(res[1:] != res[:-1])[0] + 1]
+    off_first = np.arange(n) - np.repeat(first_idx, sizes[res[first_idx]])
+    assert np.array_equal((meta >> 13) & 31, off_first) and np.array_equal((meta >> 18) & 31, sizes[res] - 1 - off_first)
+    mj = np.where(partner != 0, m[np.arange(n) + partner], 0.0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mu = np.where(partner != 0, m * mj / (m + mj), 0.0)
+        fj = np.where(partner != 0, mj / (m + mj), 0.0)
+    np.testing.assert_allclose(row[:, 4] + row[:, 5], mu, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(row[:, 7], fj, rtol=1e-7, atol=0)
+    assert np.all(table[255] == 0)                                                              # the "no particle" row
+
+
+def test_plan_chunks_on_the_synthetic_systems():
+    for s in (synth.water_box(3000, 4), synth.nacl_box(), synth.swm4_box(777),
+              synth.build([synth.WATER4, synth.SOD, synth.SWM4], np.arange(1501) % 3, np.arange(1501) % 2, 2)):
+        _assert_chunk_invariants(s, *capi.plan_chunks(s))
+    for s, why in ((synth.ionic_liquid(20), "more than 32 particles"), (synth.polymer_in_water(100, (300,), 2), "more than 32 particles")):
+        with pytest.raises(capi.TgnhError) as e:
+            capi.plan_chunks(s)
+        assert e.value.code == capi.ERR_UNSUPPORTED and why in str(e.value)
+    with pytest.raises(capi.TgnhError) as e:
+        capi.plan_chunks(synth.water_box(100, 2), precision=capi.PRECISION_MIXED)
+    assert "mixed / double" in str(e.value)
+
+
+def test_plan_chunks_random_topologies():
+    """Random mixtures of residues of 1..32 particles with random masses, random in-residue Drude pairs and random groups: either a
+    valid plan or the documented refusal (more than 255 species)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 32), min_size=1, max_size=200), st.integers(0, 2 ** 31 - 1), st.integers(1, 6))
+    def run(sizes, seed, kinds):
+        import types
+        rng = np.random.default_rng(seed)
+        palette = rng.uniform(1.0, 20.0, kinds)
+        res_id, pd, pp, base = [], [], [], 0
+        for k, size in enumerate(sizes):
+            used = set()
+            for _ in range(size // 3):
+                a = int(rng.integers(0, size)); b = int(rng.integers(0, size))
+                if a != b and a not in used and b not in used:
+                    used.update((a, b)); pd.append(base + b); pp.append(base + a)
+            res_id += [k] * size
+            base += size
+        res_id = np.array(res_id, np.int32)
+        masses = palette[rng.integers(0, kinds, base)]
+        order = np.argsort(pd) if pd else []
+        s = types.SimpleNamespace(
+            num_particles=base, masses=masses, pair_drude=np.array(pd, np.int32)[order], pair_parent=np.array(pp, np.int32)[order],
+            temp_group=(res_id % 3).astype(np.int32), res_id=res_id, constraints=np.zeros((0, 2), np.int32), num_residues=len(sizes),
+            num_temp_groups=3, num_nh_chains=3, drude_steps=20, use_drude_nh_chains=True, use_com_temp_group=True, temperature=300.0,
+            coupling_time=0.1, drude_temperature=1.0, drude_coupling_time=0.005, step_size=0.001, max_drude_distance=0.02)
+        try:
+            plan = capi.plan_chunks(s)
+        except capi.TgnhError as e:
+            assert e.code == capi.ERR_UNSUPPORTED and "more than 255 particle species" in str(e)
+            return
+        _assert_chunk_invariants(s, *plan)
+    run()
