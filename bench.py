@@ -208,6 +208,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the TGNH path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -354,6 +355,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "particles_per_gpu": n, "total_particles": total_particles,
                        "parallelism": f"particle-range shards x{world}" if world > 1 else "single GPU",
+                       "host_numa_binding": None if world == 1 else f"rank 0 on node {numa_node}",
                        "exchange": {0: "none", 1: "ncclAllReduce of double[T] per step", 2: "peer-mapped inboxes over NVLink (no collective launch)"}[exchange_kind],
                        "kernels": "warp-chunk kernels (tgnh_v2.cuh)" if generation == 2 else "first-generation kernels (tgnh_kernels.cuh)",
                        "l2": "inputs larger than L2 (>=440 MB working set per GPU vs 126 MB L2)",
@@ -397,6 +399,28 @@ def run_ours(args):
     if comm is not None:
         comm.close()
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Run this rank (and first-touch its pinned host buffers) on the NUMA node its GPU hangs off: with 8 ranks the host-buffer leg
+    otherwise funnels every rank's PCIe traffic through whichever sockets the scheduler picked.  Returns the node or None."""
+    try:
+        props = torch.cuda.get_device_properties(local)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except (OSError, ValueError, AttributeError):
+        pass
+    return None
 
 
 def device_buffers(torch, system, dev, pinned=False):
@@ -472,9 +496,10 @@ def c5_leg(torch, capi, dev, local, comm, rank, world, stream, barrier, dist, st
     particles from a 10M-particle block of the C4 generator (the host generator makes 1M particles per second; the throughput of the
     integrator does not depend on the values) and builds the full index tables for its range."""
     per_mol = C5_MOLECULES // world
-    block_mol = min(per_mol, C4_MOLECULES)
-    reps = per_mol // block_mol
-    per_mol = reps * block_mol
+    reps = max(1, -(-per_mol // C4_MOLECULES))
+    while per_mol % reps:
+        reps += 1
+    block_mol = per_mol // reps
     block = synth.water_box(block_mol, 4, first_molecule=rank * per_mol, box_molecules=C5_MOLECULES, **C4_STATE["c4"])
     nb = block.num_particles
     n = nb * reps
@@ -533,7 +558,8 @@ def shard_check_leg(torch, capi, dev, local, comm, rank, world, stream, dist):
         dv = float(np.max(np.abs(vel - bufs1[0][:shard.num_particles, :3].double().cpu().numpy())))
         res = {"ranks_identical": bool(same), "ke_vs_single_gpu": rel(state[0], ke1), "vscale_vs_single_gpu": rel(state[1], vs1),
                "eta_dot_vs_single_gpu": rel(state[2], ed1), "max_abs_dv_rank0": dv, "particles": per * world * 4, "steps": steps}
-        res["ok"] = bool(same and res["ke_vs_single_gpu"] < 1e-11 and res["vscale_vs_single_gpu"] < 1e-11 and res["eta_dot_vs_single_gpu"] < 1e-8 and dv < 1e-5)
+        # (summation order differs -> a few fp32 velocities round the other way over 25 steps: 1e-10 on the energies, one ulp on velocities)
+        res["ok"] = bool(same and res["ke_vs_single_gpu"] < 1e-9 and res["vscale_vs_single_gpu"] < 1e-10 and res["eta_dot_vs_single_gpu"] < 1e-8 and dv < 1e-6)
         h1.close()
     return res
 

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
-for name in (f"bench_{R}.json", f"bench_ref_{R}.json", f"bench_wall_{R}.json", f"bench_c1_{R}.json", f"bench_c2_{R}.json", f"bench_c3_{R}.json",
+for name in (f"bench_{R}.json", f"bench_ref_{R}.json", f"bench_c4-wall_{R}.json", f"bench_c4-hot_{R}.json", f"bench_gen1_{R}.json", f"bench_c1_{R}.json", f"bench_c2_{R}.json", f"bench_c3_{R}.json",
              f"launches_{R}.csv", f"gpu_{R}.csv"):
     if os.path.exists(os.path.join(G, name)):
         shutil.copy(os.path.join(G, name), os.path.join(P, name))
