@@ -46,6 +46,20 @@ enum { V2_A = 0, V2_B = 1, V2_KE = 2, V2_S = 3 };
 #ifndef TGNH_V2_NCONS
 #define TGNH_V2_NCONS 15
 #endif
+#ifndef TGNH_V2_NS_A
+#define TGNH_V2_NS_A 3
+#endif
+#ifndef TGNH_V2_NS_B
+#define TGNH_V2_NS_B 4
+#endif
+#ifndef TGNH_V2_PF
+#define TGNH_V2_PF 4
+#endif
+#ifndef TGNH_V2_PF_A
+#define TGNH_V2_PF_A 0
+#endif
+constexpr int V2_PF_A = TGNH_V2_PF_A;         // the same for the first-half kernel
+constexpr int V2_PF = TGNH_V2_PF;             // the producer fetches the chunk bounds of a tile this many tiles ahead
 constexpr int V2_NCONS = TGNH_V2_NCONS;       // consumer warps per CTA (the last warp is the producer)
 constexpr int V2_THREADS = (V2_NCONS + 1) * 32;
 constexpr int V2_CTAS = V2_NCONS > 15 ? 1 : 2;   // resident CTAs per SM the kernels are compiled for
@@ -74,7 +88,7 @@ struct V2Layout {
     static constexpr bool HAS_F = (KIND == V2_A || KIND == V2_B);
     static constexpr bool HAS_KE = (KIND == V2_B || KIND == V2_KE);
     static constexpr int FBYTES = FFMT == 1 ? 8 : 4;
-    static constexpr int NSTAGE = V2_NCONS > 15 ? (HAS_X ? 4 : 6) : (HAS_X ? 3 : 4);
+    static constexpr int NSTAGE = V2_NCONS > 15 ? (HAS_X ? 4 : 6) : (HAS_X ? TGNH_V2_NS_A : TGNH_V2_NS_B);   // ring depth
     static constexpr int OFF_V = 0;
     static constexpr int OFF_X = OFF_V + V2_TILE * 16;
     static constexpr int OFF_F = OFF_X + (HAS_X ? V2_TILE * 16 : 0);
@@ -202,10 +216,19 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
         // The first NS tiles are requested while the consumer warps still copy the species table and clear their energy columns.
         // Inputs that no earlier launch of this stream can still be writing may even be requested before griddepcontrol.wait (only
         // when the host knows that the preceding launches are this library's own and do not write them: a.earlyLoads).
-        if (a.earlyLoads)
-            for (int it = 0; it < preloaded; it++) issue(it, 1, chunk_bounds(it));
+        // (the bounds of all NS tiles are fetched before the first copy is issued: NS independent loads, one latency)
+        int cs0[NS];
+#pragma unroll
+        for (int it = 0; it < NS; it++) cs0[it] = it < preloaded ? chunk_bounds(it) : 0;
+        if (a.earlyLoads) {
+#pragma unroll
+            for (int it = 0; it < NS; it++)
+                if (it < preloaded) issue(it, 1, cs0[it]);
+        }
         pdl_wait();                                     // everything below reads what earlier launches wrote
-        for (int it = 0; it < preloaded; it++) issue(it, a.earlyLoads ? 2 : 3, chunk_bounds(it));
+#pragma unroll
+        for (int it = 0; it < NS; it++)
+            if (it < preloaded) issue(it, a.earlyLoads ? 2 : 3, cs0[it]);
     } else {
         for (int i = tid; i < a.tableRows * V2_ROW_F4; i += V2_TILE) stab[i] = __ldg(a.specTable + i);     // static table: safe before the wait
         if (L::HAS_KE)
@@ -224,8 +247,20 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     int curTg = -1;
 
     if (producer) {
+        // The chunk bounds of a tile are a dependent global load (DRAM latency under load ~ the time a CTA spends on one tile of the
+        // second half): they are fetched V2_PF tiles ahead so that the refill of a released stage never waits for them.
+        constexpr int PF = L::HAS_X ? V2_PF_A : V2_PF;
+        int csq[PF > 0 ? PF : 1];
+#pragma unroll
+        for (int k = 0; k < PF; k++) csq[k] = preloaded + k < myTiles ? chunk_bounds(preloaded + k) : 0;
         for (int it = preloaded; it < myTiles; it++) {
-            const int cs = chunk_bounds(it);
+            int cs;
+            if (PF > 0) {
+                cs = csq[0];
+#pragma unroll
+                for (int k = 0; k + 1 < PF; k++) csq[k] = csq[k + 1];
+                csq[PF - 1] = it + PF < myTiles ? chunk_bounds(it + PF) : 0;
+            } else cs = chunk_bounds(it);
             mbar_wait(&empty[it % NS], ((it / NS) - 1) & 1);
             issue(it, 3, cs);
         }
