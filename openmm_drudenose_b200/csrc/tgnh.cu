@@ -162,6 +162,8 @@ struct tgnh_handle {
     float4* dSpecTable = nullptr;
     int numTiles2 = 0, maxRes = 1, numSpecies = 0, butterfly = 0;
     int gridA2v = 0, gridB2v = 0, gridKE2v = 0, gridS2v = 0, smemA2v = 0, smemB2v = 0, smemKE2v = 0, smemS2v = 0;
+    bool lazyKick = true;         // TGNH_LAZY_KICK=0 at tgnh_create switches the lazy second kick of tgnh_step off (tests, measurements)
+    bool lazyNow = false;         // set by tgnh_step around the launches that leave / find the second half kick pending (StreamArgs::lazyKick)
     bool earlyOK = false;         // set by tgnh_step around launches whose predecessors in the stream are its own
     std::vector<int> hChunkStart; // host copy of dChunkStart (chunk boundaries of the pipelined host-buffer path)
     // pipelined host-buffer path (tgnh_step_host2)
@@ -814,6 +816,8 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
     {
         const char* e = getenv("TGNH_V2");
         h->v2 = hp.v2 && !(e && atoi(e) == 0);
+        const char* lz = getenv("TGNH_LAZY_KICK");
+        h->lazyKick = !(lz && atoi(lz) == 0);
         if (h->v2) {
             h->numTiles2 = hp.numTiles2; h->maxRes = hp.maxRes; h->numSpecies = hp.numSpecies; h->butterfly = hp.butterfly;
             h->hChunkStart = hp.chunkStart;
@@ -1036,6 +1040,7 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     const bool fused = h->fuseChain && reduces && chainMode != CHAIN_NONE && (kind == h->kindB || (kind == h->kindKE && !applyScale));
     a.fusedChainMode = fused ? chainMode : CHAIN_NONE;
     a.earlyLoads = h->earlyOK ? 1 : 0;
+    a.lazyKick = h->lazyNow ? 1 : 0;
     // the two halves and the plain reduction run through the warp-chunk kernels where the system qualifies
     const int kind2 = !h->v2 ? -1 : kind == KIND_A ? V2_A : kind == h->kindB ? V2_B : (kind == h->kindKE && !applyScale) ? V2_KE : kind == KIND_S ? V2_S : -1;
     if (kind2 >= 0) {
@@ -1162,17 +1167,26 @@ extern "C" int tgnh_step(tgnh_handle* h, void* stream, void* velm, void* posq, c
         return TGNH_OK;
     }
     if (int rc = ensure_ke(h, s, velm, CHAIN_FIRST)) return rc;
-    struct EarlyGuard { tgnh_handle* h; ~EarlyGuard() { h->earlyOK = false; } } guard{h};
+    struct EarlyGuard { tgnh_handle* h; ~EarlyGuard() { h->earlyOK = false; h->lazyNow = false; } } guard{h};
+    // Lazy second kick (warp-chunk kernels): between two steps of this call nothing reads velm but the two halves themselves, and
+    // the second half of step i and the first half of step i+1 see the same forces.  The second half then only REDUCES the
+    // energies of v + (dt/2) F/m and stores nothing; the next first half repeats that fp32 operation on the same operands
+    // (bit-identical velocities) before it scales, kicks and drifts: 16 B per particle and step less through HBM.  The last
+    // step's second half stores as usual, so velm is complete when the call returns.
+    const bool lazy = h->lazyKick && h->v2 && !h->fuseChain;
     for (int i = 0; i < nsteps; i++) {
         // from the second launch on, everything that can still be running ahead of a launch is this loop's own work, which
         // writes velm only (and posq in first-half launches that have completed by then): see StreamArgs::earlyLoads
+        h->lazyNow = lazy && i > 0;
         if (int rc = launch_stream(h, s, KIND_A, velm, posq, force, 1, CHAIN_NONE)) return rc;
         h->earlyOK = true;
         // the thermostat half-step that ends step i and the one that begins step i+1 run back to back in one
         // chain launch; their scale factors are applied together by the next first-half pass
         const int mode = (i + 1 < nsteps) ? CHAIN_SECOND_FIRST : CHAIN_SECOND;
+        h->lazyNow = lazy && i + 1 < nsteps;
         if (int rc = launch_stream(h, s, KIND_B, velm, nullptr, force, 0, mode)) return rc;
     }
+    h->lazyNow = false;
     h->keValid = true;
     h->scalePending = true;
     return flush_scale(h, s, velm);

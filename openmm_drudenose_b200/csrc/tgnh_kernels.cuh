@@ -92,6 +92,9 @@ struct StreamArgs {
     int earlyLoads;           // the launches that precede this one in the stream are this library's own and write neither
                               // posq, forces nor posqCorrection: those tiles may be requested before griddepcontrol.wait
     // warp-chunk kernels (tgnh_v2.cuh)
+    int lazyKick;                // second half: the kicked velocities are reduced but NOT stored; first half: velm still lacks the
+                                 // previous step's second half kick, which is applied (same forces, same fp32 operation, bit-identical
+                                 // velocities) before anything else.  Only between the steps of one tgnh_step(n) call.
     const unsigned char* spec;   // [roundup16(N) + 32] species-table row of every particle
     const int* chunkStart;       // [15 * numTiles + 1] first particle of every chunk (tail padded with N)
     const float4* specTable;     // [tableRows * 3] species table (q0, q1, pad); the last row is "no particle"

@@ -178,6 +178,8 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     __syncthreads();                                    // the barriers exist: the producer may start streaming
 
     const uint64_t polOnce = policy_evict_first();
+    // velm of a second half that stores nothing: the next first half starts on the tiles read last, keep them in L2
+    const uint64_t polV = (KIND == V2_B && a.lazyKick) ? policy_evict_normal() : polOnce;
     // Producer: request tile `it` of this CTA into its stage (the whole warp calls; lane 0 issues the copies).
     // parts: 1 = header + everything no launch of this library writes (posq, forces, species bytes), arms the barrier with
     // the full byte count; 2 = velm; 3 = both.  `cs` = chunkStart[15 * tile + lane] for lanes 0..15.
@@ -206,7 +208,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                 bulk_g2s(st + L::OFF_S, a.spec + s0, sn, bar, polOnce);
             }
         }
-        if ((parts & 2) && lane == 0) bulk_g2s(st + L::OFF_V, gvelm + start, n * 16, bar, polOnce);
+        if ((parts & 2) && lane == 0) bulk_g2s(st + L::OFF_V, gvelm + start, n * 16, bar, polV);
     };
     auto chunk_bounds = [&](int it) { return lane <= V2_NCONS ? __ldg(a.chunkStart + V2_NCONS * tile_of(it) + lane) : 0; };
 
@@ -294,10 +296,11 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
             const int tg = v2_tg(meta);
             const uint32_t role = v2_role(meta);
             const int pl = lane + v2_partner(meta);                   // lane of the pair partner (this lane for ordinary particles)
-            const V3<float> v = xyz(v4);
+            V3<float> v = xyz(v4);
             const float w = v4.w;
             const bool massive = w != 0.f;
             const float fw = fscale * w;
+            if (KIND == V2_A && a.lazyKick) v = kicked(v, fw, F);     // the previous step's second half kick (see StreamArgs::lazyKick)
             const int offFirst = v2_off_first(meta), offLast = v2_off_last(meta);    // position inside the residue (all of it in this warp)
             const unsigned int gidx = (unsigned int)(start + i);                      // unsigned: one IMAD.WIDE per address
 
@@ -352,7 +355,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                 // half kick (integrateDrudeTGNHVelocities, :314-364; V2_KE: F = 0, nothing stored), then the energies of
                 // what was stored
                 const V3<float> vn = kicked(v, fw, F);
-                if (KIND == V2_B && active && massive) st_global(gvelm + gidx, pack4(vn, w));
+                if (KIND == V2_B && !a.lazyKick && active && massive) st_global(gvelm + gidx, pack4(vn, w));
                 V3<float> V = v3(0.f, 0.f, 0.f);
                 float keC = 0.f;
                 const bool first = offFirst == 0;

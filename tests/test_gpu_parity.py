@@ -138,6 +138,32 @@ def test_half_calls_equal_step(cuda):
         h.close()
 
 
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_lazy_second_kick_is_bit_identical(cuda, fmt, monkeypatch):
+    """tgnh_step(n) leaves the second half kick of every step but the last to the next first half (tgnh.cu: tgnh_step): same fp32
+    operation on the same operands, so positions, velocities and the thermostat state are BIT-identical to the run that stores the
+    kicked velocities after every second half (TGNH_LAZY_KICK=0).  100k particles: more tiles than SMs (no fused chain launch)."""
+    s = synth.water_box(25000, 4, quantize_masses=True, drude_sigma=0.012)        # some pairs meet the hard wall
+    a, b = DeviceState(s, cuda, force_format=fmt), DeviceState(s, cuda, force_format=fmt)
+    ha = capi.Handle(s, force_format=fmt)
+    monkeypatch.setenv("TGNH_LAZY_KICK", "0")
+    hb = capi.Handle(s, force_format=fmt)
+    monkeypatch.delenv("TGNH_LAZY_KICK")
+    assert ha.kernel_generation == 2
+    ha.step(*a.ptrs, nsteps=7); hb.step(*b.ptrs, nsteps=7)
+    ha.step(*a.ptrs, nsteps=1); hb.step(*b.ptrs, nsteps=1)
+    ha.step(*a.ptrs, nsteps=2); hb.step(*b.ptrs, nsteps=2)
+    torch = a.torch
+    torch.cuda.synchronize()
+    assert torch.equal(a.velm, b.velm) and torch.equal(a.posq, b.posq)
+    for x, y in zip(ha.chain_state(), hb.chain_state()):
+        assert np.array_equal(x, y)
+    assert np.array_equal(ha.kinetic_energies(), hb.kinetic_energies()) and np.array_equal(ha.vscale(), hb.vscale())
+    # and the lazy run launched the same number of kernels
+    assert ha.launch_count == hb.launch_count
+    ha.close(); hb.close()
+
+
 def test_hard_wall(cuda):
     """Pairs placed robustly inside / outside the wall: reflection formulas (drudeTGNH.cu:487-572) within 1e-5."""
     s = synth.water_box(4096, 2, quantize_masses=True, drude_sigma=0.0, pair_force="none", cold_drudes=True, force_sigma=5.0)
