@@ -766,7 +766,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
 
     // chain block: etaMass, invEtaMass, eta, etaDot, etaDotDot, nkbt, ke2, ke2Local, ke2Used, pending, scaleA, vscale, keSum
     const size_t TM = (size_t)T * M;
-    h->chainDoubles = 4 * TM + (size_t)T * (M + 1) + 7 * T + 1;
+    h->chainDoubles = 4 * TM + (size_t)T * (M + 1) + 8 * T + 1;
     if (!dmalloc((void**)&h->dChain, h->chainDoubles * 8)) return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the chain state failed"));
     std::vector<double> init(h->chainDoubles, 0.0);
     {
@@ -775,6 +775,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         c.T = T; c.G = G; c.M = M; c.S = h->S; c.useDrudeNH = h->useDrudeNH;
         c.dt = h->dt; c.kT = h->kT; c.kTD = h->kTD;
         c.dtc = h->dt / h->S;                                         // CudaDrudeTGNHKernels.cpp:440
+        chain_exp_tables(c);
         size_t o = 0;
         c.etaMass = b + o; memcpy(&init[o], h->etaMass.data(), TM * 8); o += TM;
         c.invEtaMass = b + o; for (size_t i = 0; i < TM; i++) init[o + i] = h->etaMass[i] != 0.0 ? 1.0 / h->etaMass[i] : 0.0; o += TM;
@@ -789,6 +790,7 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         c.scaleA = b + o; for (int g = 0; g < T; g++) init[o + g] = 1.0; o += T;
         c.vscale = b + o; for (int g = 0; g < T; g++) init[o + g] = 1.0; o += T;
         c.keSum = b + o; o += 1;
+        c.expHint = b + o; o += T;
         if (!(h->comm && h->comm->worldSize > 1)) c.ke2Local = nullptr;
     }
     cudaMemcpy(h->dChain, init.data(), h->chainDoubles * 8, cudaMemcpyHostToDevice);
@@ -867,6 +869,17 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
     if (h->gridA1 > maxGrid) maxGrid = h->gridA1;
     if (h->gridA2 > maxGrid) maxGrid = h->gridA2;
     if (!dmalloc((void**)&h->dPartials, (size_t)maxGrid * T * 8)) return bail(fail(TGNH_ERR_CUDA, "cudaMalloc of the partial sums failed"));
+    {
+        // the chain kernel is configured nowhere above: load it now (CUDA loads a kernel's code at its first use; that is 1-40 ms
+        // of host time which would otherwise fall into the first step that needs the stand-alone chain launch)
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, (const void*)tgnh_chain_kernel) != cudaSuccess) (void)cudaGetLastError();
+        if (h->numBig) {
+            const void* bk[4] = {(const void*)tgnh_bigcom_kernel<0, 0>, (const void*)tgnh_bigcom_kernel<0, 1>, (const void*)tgnh_bigcom_kernel<1, 0>, (const void*)tgnh_bigcom_kernel<1, 1>};
+            for (const void* k : bk)
+                if (cudaFuncGetAttributes(&fa, k) != cudaSuccess) (void)cudaGetLastError();
+        }
+    }
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(TGNH_ERR_CUDA, "device error during tgnh_create: %s", cudaGetErrorString(cudaGetLastError())));
     *out = h;
     return TGNH_OK;

@@ -121,6 +121,8 @@ struct ChainView {
     int T, G, M, S, useDrudeNH;
     double dt, kT, kTD;
     double dtc;         // dt / S
+    double expA[3][10]; // exp(c y) = sum_k expA[j][k] y^k for c = -dtc/8, -dtc/2, -dtc (j = 0, 1, 2): c^k / k!, filled by chain_exp_tables
+    double expLim[3];   // |y| <= expLim[j]  <=>  |c y| <= 2^-5, the range of the polynomial
     double* etaMass;    // [T][M]
     double* invEtaMass; // [T][M]   1 / etaMass (0 where the mass is 0)
     double* eta;        // [T][M]
@@ -134,6 +136,7 @@ struct ChainView {
     double* scaleA;     // [T]  factors the next streaming kernel applies
     double* vscale;     // [T]  factors of the most recent chain update (vscaleFactorsVec)
     double* keSum;      // [1]
+    double* expHint;    // [T]  1: the last chain update of this thermostat left the range of the short exp polynomial
 };
 
 // ---- sharded runs: the kinetic-energy exchange over NVLink peer memory -------------------------------------------
@@ -248,123 +251,175 @@ __device__ __forceinline__ double exp_full(double x) {
     return y;
 }
 
-// exp(x) for the chain.  |x| is ~1e-3 here (dtc/8 * etaDot) when the thermostats are near equilibrium; for
-// |x| <= 2^-5 a degree-9 Taylor polynomial is exact to < 0.25 ulp before the final rounding, which puts it in
-// the same <= 1 ulp class as CUDA's exp() and glibc's at a fraction of the dependent-instruction depth.  The
-// chain is strictly serial (40 sub-steps x ~4 dependent exps per step) and sits between two streaming kernels,
-// so its latency is directly visible in the step time.  FAST = false is the full-range version.
+// exp(c*y) for the chain, c one of the three constants -dtc/8, -dtc/2, -dtc.  |c*y| is ~1e-3 when the thermostats are near
+// equilibrium; for |c*y| <= 2^-5 a degree-9 Taylor polynomial is exact to < 0.25 ulp before the final rounding, which puts it in
+// the same <= 1 ulp class as CUDA's exp() and glibc's at a fraction of the dependent-instruction depth.  The chain is strictly
+// serial (40 sub-steps x 3 dependent exps per step for M = 3) and sits between two streaming kernels, so its latency is directly
+// visible in the step time.  The constant is folded into the coefficients (a_k = c^k / k!, ChainView::expA), so the polynomial is
+// evaluated in y itself: Estrin form, 4 dependent operations from y to the result.
+__host__ __device__ inline void chain_exp_tables(ChainView& c) {
+    const double invFact[10] = {1.0, 1.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0, 1.0 / 362880.0};
+    const double cs[3] = {-c.dtc / 8.0, -c.dtc / 2.0, -c.dtc};
+    for (int j = 0; j < 3; j++) {
+        double ck = 1.0;
+        for (int k = 0; k < 10; k++) { c.expA[j][k] = ck * invFact[k]; ck *= cs[j]; }
+        c.expLim[j] = cs[j] != 0.0 ? 0.03125 / (cs[j] < 0 ? -cs[j] : cs[j]) : 1e300;
+    }
+}
+// (the coefficients sit in the kernel parameters, i.e. in the constant bank: they cost neither registers nor loads)
 template <bool FAST>
-__device__ __forceinline__ double chain_exp(double x, bool& outOfRange) {
-    if (!FAST) return exp_full(x);
-    outOfRange |= fabs(x) > 0.03125;
-    const double x2 = x * x;
-    // Estrin: pairs of terms, then powers of x^2
-    const double p01 = 1.0 + x;
-    const double p23 = fma(x, 1.0 / 6.0, 0.5);
-    const double p45 = fma(x, 1.0 / 120.0, 1.0 / 24.0);
-    const double p67 = fma(x, 1.0 / 5040.0, 1.0 / 720.0);
-    const double p89 = fma(x, 1.0 / 362880.0, 1.0 / 40320.0);
-    const double x4 = x2 * x2;
-    const double q0 = fma(p23, x2, p01);
-    const double q1 = fma(p67, x2, p45);
-    const double x8 = x4 * x4;
-    return fma(p89, x8, fma(q1, x4, q0));
+__device__ __forceinline__ double chain_exp(const double (&a)[10], double lim, double c, double y, bool& outOfRange) {
+    outOfRange |= !(fabs(y) <= lim);
+    if (!FAST) return exp_full(c * y);
+    const double y2 = y * y;
+    const double p01 = fma(y, a[1], a[0]);
+    const double p23 = fma(y, a[3], a[2]);
+    const double p45 = fma(y, a[5], a[4]);
+    const double p67 = fma(y, a[7], a[6]);
+    const double p89 = fma(y, a[9], a[8]);
+    const double y4 = y2 * y2;
+    const double q0 = fma(p23, y2, p01);
+    const double q1 = fma(p67, y2, p45);
+    const double y8 = y4 * y4;
+    return fma(p89, y8, fma(q1, y4, q0));
 }
 
+template <int NL>
 struct ChainConst {
-    double dtc, dtc2, dtc4, dtc8, kTl, nkbt, invQ0;
-    bool live;
+    double dtc2, dtc4, dtc8, inv4;     // dtc/2, dtc/4, dtc/8, 4/dtc
+    // g_i = (dtc/4) etaDotDot_i = gA[i] z + gB[i],  z = 2KE (i = 0) or etaDot_{i-1}^2 (i >= 1)
+    double gA[NL], gB[NL];
+    bool live;                         // Q_0 > 0 (:561)
+};
+template <int NL>
+struct ChainState {
+    double eta[NL], ed[NL], g[NL], ef[NL];
 };
 
 // One of the S sub-steps of a thermostat's half-step update (the body of the `iter` loops at
-// CudaDrudeTGNHKernels.cpp:565-593 / :606-642).  Returns false when the FAST polynomial left its range.
+// CudaDrudeTGNHKernels.cpp:565-593 / :606-642).  Returns true when an argument left the range of the short polynomial.
+//
+// The reference updates a link as  v *= a; v += G dt/4; v *= a  with a = exp(-dt/8 v_next) and G = (Q_prev v_prev^2 - kT) / Q.
+// The same values are formed here with a shorter dependency chain and fewer operations (a dependent DFMA costs 8.2 cycles on
+// B200 and one warp issues a DFMA every 2.1 cycles, scripts/lat.cu, scripts/lat_ilp.cu):
+//   downward sweep   v = a * fma(v, a, g)               g = G dt/4, known since the previous upward sweep
+//   upward sweep     v = fma(g, a, v a^2)               v a^2 formed while g is still on its way
+//                    g = fma(z, gA, gB)                 (Q_prev / Q)(dt/4) z - (kT / Q)(dt/4): one operation after z = v_prev^2 (or 2KE)
+//   scale factor     s = exp(-dt/2 v_0);  scale *= s;  2KE *= s^2      (the reference evaluates exp(-dt v_0) separately, :575-576)
+//   etaDotDot        = g / (dt/4), formed once after the last sub-step
+// Each rearrangement is exact algebra; results differ from the reference's operation order in the last bits only (tests: chain
+// variables against the oracle after 1 and 1000 steps).
 template <int NL, bool FAST>
-__device__ __forceinline__ bool chain_substep(const ChainConst& k, const double (&Q)[NL], const double (&invQ)[NL], double (&eta)[NL],
-                                              double (&ed)[NL], double (&edd)[NL], double (&ef)[NL], double& ke, double& scale) {
+__device__ __forceinline__ bool chain_substep(const ChainView& c, const ChainConst<NL>& k, ChainState<NL>& st, double& ke, double& scale) {
     bool bad = false;
+    double ef2[NL];
 #pragma unroll
     for (int i = NL - 1; i >= 0; i--) {
-        if (i < NL - 1) ef[i] = chain_exp<FAST>(-k.dtc8 * ed[i + 1], bad);
-        ed[i] *= ef[i]; ed[i] += edd[i] * k.dtc4; ed[i] *= ef[i];
+        if (i < NL - 1) st.ef[i] = chain_exp<FAST>(c.expA[0], c.expLim[0], -k.dtc8, st.ed[i + 1], bad);
+        ef2[i] = st.ef[i] * st.ef[i];
+        st.ed[i] = st.ef[i] * fma(st.ed[i], st.ef[i], st.g[i]);
     }
-    scale *= chain_exp<FAST>(-k.dtc2 * ed[0], bad);
-    ke *= chain_exp<FAST>(-k.dtc * ed[0], bad);
+    const double sf = chain_exp<FAST>(c.expA[1], c.expLim[1], -k.dtc2, st.ed[0], bad);
+    scale *= sf;
+    ke *= sf * sf;
 #pragma unroll
-    for (int i = 0; i < NL; i++) eta[i] += k.dtc2 * ed[i];
-    if (k.live) edd[0] = (ke - k.nkbt) * k.invQ0;
-    ed[0] *= ef[0]; ed[0] += edd[0] * k.dtc4; ed[0] *= ef[0];
+    for (int i = 0; i < NL; i++) st.eta[i] = fma(k.dtc2, st.ed[i], st.eta[i]);
+    if (k.live) st.g[0] = fma(ke, k.gA[0], k.gB[0]);
+    st.ed[0] = fma(st.g[0], st.ef[0], st.ed[0] * ef2[0]);
 #pragma unroll
     for (int i = 1; i < NL; i++) {
-        ed[i] *= ef[i];
-        edd[i] = (Q[i - 1] * ed[i - 1] * ed[i - 1] - k.kTl) * invQ[i];
-        ed[i] += edd[i] * k.dtc4; ed[i] *= ef[i];
+        st.g[i] = fma(st.ed[i - 1] * st.ed[i - 1], k.gA[i], k.gB[i]);
+        st.ed[i] = fma(st.g[i], st.ef[i], st.ed[i] * ef2[i]);
     }
-    return !bad;
+    return bad;
 }
 
-// One thermostat's half-step chain update; restates CudaDrudeTGNHKernels.cpp:560-595 (relative and COM
-// groups) and :597-642 (Drude group) as one loop nest: the Drude group differs only in the number of
-// live links (1 unless useDrudeNHChains) and in kT.  Returns the velocity scale factor.
+// One thermostat's half-step chain update on state held in registers; restates CudaDrudeTGNHKernels.cpp:560-595 (relative and
+// COM groups) and :597-642 (Drude group) as one loop nest: the Drude group differs only in the number of live links (1 unless
+// useDrudeNHChains) and in kT.  Returns the velocity scale factor.
 //
-// Same arithmetic as the reference with latency cuts that do not change any value beyond the last ulp:
+// Same arithmetic as the reference with latency cuts that do not change any value beyond the last bits:
 //   * the factor exp(-dtc/8 * etaDot[top+1]) of the top live link is loop-invariant (etaDot[M] is the
 //     permanent zero) and computed once;
 //   * the second (upward) sweep re-evaluates exp(-dtc/8 * etaDot[i+1]) on values the first sweep left
 //     unchanged, so the first sweep's factors are reused (":583" already reuses a stale expfac this way);
-//   * divisions by the constant thermostat masses become multiplications by their reciprocals;
-//   * every sub-step first runs branch-free with the small-argument exp polynomial; only if an argument
-//     left the polynomial's range is the sub-step redone from the saved state with the full-range exp_full().
+//   * divisions by the constant thermostat masses become multiplications by their reciprocals, folded with dtc/4;
+//   * the link updates in the regrouped form described at chain_substep;
+//   * all S sub-steps run as one straight dependent chain with the small-argument polynomial (no vote, no branch, no state copy
+//     between sub-steps); the arguments are checked on the side and, if one left the polynomial's range, the whole update is
+//     redone from the saved state with the full-range exp.  A thermostat that needed the full range last time starts there
+//     (`hint`, kept in c.expHint between launches: e.g. the first picoseconds of an unequilibrated system); the lanes of the
+//     warp run in lockstep, so the choice is made for all of them together.
 // Deviation (documented in DESIGN.md): the Q0 > 0 guard of :561 is applied to the Drude group too, so a
 // system without Drude pairs yields scale 1 instead of NaN.
-template <int NL>  // live links, known at compile time so that the state sits in registers
-__device__ __forceinline__ double chain_update(const ChainView& c, int g, double ke) {
+template <int NL>
+__device__ __forceinline__ double chain_update(const ChainView& c, const ChainConst<NL>& k, ChainState<NL>& st, double ke, bool& hint) {
+    if (k.live) st.g[0] = fma(ke, k.gA[0], k.gB[0]);             // etaDotDot_0 = (2KE - N kT) / Q_0 (:563)
+    double scale = 1.0;
+    bool full = __any_sync(__activemask(), hint);
+    bool bad = false;
+    if (!full) {
+        const ChainState<NL> st0 = st;
+        const double ke0 = ke;
+#pragma unroll 1
+        for (int iter = 0; iter < c.S; iter++) bad |= chain_substep<NL, true>(c, k, st, ke, scale);
+        full = __any_sync(__activemask(), bad);
+        if (full) { st = st0; ke = ke0; scale = 1.0; }
+    }
+    if (full) {
+        bad = false;
+#pragma unroll 1
+        for (int iter = 0; iter < c.S; iter++) bad |= chain_substep<NL, false>(c, k, st, ke, scale);
+    }
+    hint = full && bad;
+    return scale;
+}
+
+// Thermostat `g` (one lane): state and constants into registers, the one or two chain updates `mode` asks for, state back.
+template <int NL>
+__device__ __forceinline__ void chain_lane(const ChainView& c, int mode, int g, double ke, double& pend, double& used, double& s) {
     const int M = c.M;
     const bool isDrude = (g == c.T - 1);
-    ChainConst k;
-    k.dtc = c.dtc; k.dtc2 = k.dtc / 2.0; k.dtc4 = k.dtc / 4.0; k.dtc8 = k.dtc / 8.0;
-    k.kTl = isDrude ? c.kTD : c.kT;
-    k.nkbt = c.nkbt[g];
-    double Q[NL], invQ[NL], eta[NL], ed[NL], edd[NL], ef[NL];
+    ChainConst<NL> k;
+    k.dtc2 = c.dtc / 2.0; k.dtc4 = c.dtc / 4.0; k.dtc8 = c.dtc / 8.0; k.inv4 = 4.0 / c.dtc;
+    const double kTl = isDrude ? c.kTD : c.kT;
+    ChainState<NL> st;
+    double edd0 = 0.0;
+    k.live = c.etaMass[g * M] > 0;
 #pragma unroll
     for (int i = 0; i < NL; i++) {
-        Q[i] = c.etaMass[g * M + i];
-        invQ[i] = c.invEtaMass[g * M + i];
-        eta[i] = c.eta[g * M + i];
-        ed[i] = c.etaDot[g * (M + 1) + i];
-        edd[i] = c.etaDotDot[g * M + i];
-        ef[i] = 1.0;
+        const double invQ = c.invEtaMass[g * M + i];
+        const double dA = i == 0 ? (k.live ? invQ : 0.0) : c.etaMass[g * M + i - 1] * invQ;
+        const double dB = i == 0 ? (k.live ? -c.nkbt[g] * invQ : 0.0) : -kTl * invQ;
+        k.gA[i] = dA * k.dtc4; k.gB[i] = dB * k.dtc4;
+        st.eta[i] = c.eta[g * M + i];
+        st.ed[i] = c.etaDot[g * (M + 1) + i];
+        const double edd = c.etaDotDot[g * M + i];
+        if (i == 0) edd0 = edd;
+        st.g[i] = edd * k.dtc4;
+        st.ef[i] = 1.0;
     }
     // etaDot[M] is the permanent zero; for a Drude group without chains etaDot[1] may hold user-set state
-    ef[NL - 1] = exp(-k.dtc8 * c.etaDot[g * (M + 1) + NL]);
-    k.live = Q[0] > 0;
-    k.invQ0 = k.live ? invQ[0] : 0.0;
-    double scale = 1.0;
-    if (k.live) edd[0] = (ke - k.nkbt) * k.invQ0;
-    // The lanes of the warp run in lockstep, so a lane that needs the full-range exp makes everybody pay for it:
-    // the choice is therefore made once for all converged lanes and is sticky for the rest of this update.
-    bool full = false;
-    for (int iter = 0; iter < c.S; iter++) {
-        if (!full) {
-            double eta0[NL], ed0[NL], edd0[NL], ef0[NL];
-            const double ke0 = ke, scale0 = scale;
-#pragma unroll
-            for (int i = 0; i < NL; i++) { eta0[i] = eta[i]; ed0[i] = ed[i]; edd0[i] = edd[i]; ef0[i] = ef[i]; }
-            const bool ok = chain_substep<NL, true>(k, Q, invQ, eta, ed, edd, ef, ke, scale);
-            full = __any_sync(__activemask(), !ok);
-            if (!full) continue;
-#pragma unroll
-            for (int i = 0; i < NL; i++) { eta[i] = eta0[i]; ed[i] = ed0[i]; edd[i] = edd0[i]; ef[i] = ef0[i]; }
-            ke = ke0; scale = scale0;
-        }
-        chain_substep<NL, false>(k, Q, invQ, eta, ed, edd, ef, ke, scale);
+    st.ef[NL - 1] = exp(-k.dtc8 * c.etaDot[g * (M + 1) + NL]);
+    bool hint = c.expHint[g] != 0.0;
+    // update 0: the half-step that ends a step (consumes 2KE, its factor stays pending); update 1: the half-step that begins
+    // a step (consumes pending^2 2KE).  One copy of the code for both: this kernel is one warp running a long instruction
+    // stream once, and what it fetches it pays for.
+    const int first = mode == CHAIN_FIRST ? 1 : 0, last = mode == CHAIN_SECOND ? 0 : 1;
+#pragma unroll 1
+    for (int u = first; u <= last; u++) {
+        const double keIn = u == 0 ? ke : pend * pend * ke;
+        used = keIn;
+        s = chain_update<NL>(c, k, st, keIn, hint);
+        if (u == 0) pend = s;
     }
 #pragma unroll
     for (int i = 0; i < NL; i++) {
-        c.eta[g * M + i] = eta[i];
-        c.etaDot[g * (M + 1) + i] = ed[i];
-        c.etaDotDot[g * M + i] = edd[i];
+        c.eta[g * M + i] = st.eta[i];
+        c.etaDot[g * (M + 1) + i] = st.ed[i];
+        c.etaDotDot[g * M + i] = (i == 0 && !k.live) ? edd0 : st.g[i] * k.inv4;
     }
-    return scale;
+    c.expHint[g] = hint ? 1.0 : 0.0;
 }
 
 // runtime chain length (M > 4): same algorithm on local arrays, library exp
@@ -411,14 +466,17 @@ __device__ __noinline__ double chain_update_generic(const ChainView& c, int g, d
     return scale;
 }
 
-__device__ __forceinline__ double chain_update_any(const ChainView& c, int g, double ke) {
-    const int nl = (g == c.T - 1 && !c.useDrudeNH) ? 1 : c.M;
-    switch (nl) {
-        case 1: return chain_update<1>(c, g, ke);
-        case 2: return chain_update<2>(c, g, ke);
-        case 3: return chain_update<3>(c, g, ke);
-        case 4: return chain_update<4>(c, g, ke);
-        default: return chain_update_generic(c, g, ke, nl);
+// runtime chain length (M > 4)
+__device__ __noinline__ void chain_lane_generic(const ChainView& c, int mode, int g, double ke, int nl, double& pend, double& used, double& s) {
+    if (mode == CHAIN_SECOND || mode == CHAIN_SECOND_FIRST) {
+        used = ke;
+        s = chain_update_generic(c, g, ke, nl);
+        pend = s;
+    }
+    if (mode == CHAIN_FIRST || mode == CHAIN_SECOND_FIRST) {
+        const double keEff = pend * pend * ke;
+        used = keEff;
+        s = chain_update_generic(c, g, keEff, nl);
     }
 }
 
@@ -426,17 +484,21 @@ __device__ __forceinline__ double chain_update_any(const ChainView& c, int g, do
 // 2*KE sums of the velocities as stored.
 __device__ void chain_phase(const ChainView& c, int mode, int lane) {
     const bool on = lane < c.T;
-    double ke = on ? c.ke2[lane] : 0.0;
+    const double ke = on ? c.ke2[lane] : 0.0;
     double pend = on ? c.pending[lane] : 1.0;
     double used = 0.0, s = 1.0;
-    if (mode == CHAIN_SECOND || mode == CHAIN_SECOND_FIRST) {
-        used = ke;
-        if (on) { s = chain_update_any(c, lane, ke); pend = s; }
+    if (on) {
+        const int nl = (lane == c.T - 1 && !c.useDrudeNH) ? 1 : c.M;
+        switch (nl) {
+            case 1: chain_lane<1>(c, mode, lane, ke, pend, used, s); break;
+            case 2: chain_lane<2>(c, mode, lane, ke, pend, used, s); break;
+            case 3: chain_lane<3>(c, mode, lane, ke, pend, used, s); break;
+            case 4: chain_lane<4>(c, mode, lane, ke, pend, used, s); break;
+            default: chain_lane_generic(c, mode, lane, ke, nl, pend, used, s); break;
+        }
     }
+    __syncwarp();
     if (mode == CHAIN_FIRST || mode == CHAIN_SECOND_FIRST) {
-        const double keEff = pend * pend * ke;
-        used = keEff;
-        if (on) { s = chain_update_any(c, lane, keEff); }
         if (on) { c.scaleA[lane] = pend * s; c.pending[lane] = 1.0; }
     } else if (on) {
         c.scaleA[lane] = pend;

@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(TILE, 1) tgnh_stream_chain_kernel(const __grid
 }
 
 // The Nose-Hoover chain update(s) between two streaming launches: one warp, lane g = thermostat g.
-__global__ void __launch_bounds__(32, 1) tgnh_chain_kernel(ChainView c, const __grid_constant__ PeerView peers, int mode) {
+__global__ void __launch_bounds__(32, 1) tgnh_chain_kernel(const __grid_constant__ ChainView c, const __grid_constant__ PeerView peers, int mode) {
     pdl_launch_dependents();      // the next streaming launch may start its prologue; it waits for our results
     pdl_wait();
     if (peers.world > 1) peer_gather(peers, c.ke2, c.T, threadIdx.x);    // sharded: global sums from all ranks' partials
