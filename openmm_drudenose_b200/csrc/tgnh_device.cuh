@@ -376,8 +376,12 @@ __device__ __forceinline__ double chain_update(const ChainView& c, const ChainCo
 }
 
 // Thermostat `g` (one lane): state and constants into registers, the one or two chain updates `mode` asks for, state back.
+// `liveLinks` < NL: a Drude thermostat without chains (useDrudeNHChains = false) riding along in the warp's NL-link code instead of
+// running its own 1-link pass after the others.  Its upper links are frozen at zero chain velocity (chain_phase checks that), so
+// with gA = gB = g = 0 for them every factor is exp(0) = 1 and every increment 0: the live link gets bit for bit what the 1-link
+// code gives it, and the frozen links are neither changed nor written back.
 template <int NL>
-__device__ __forceinline__ void chain_lane(const ChainView& c, int mode, int g, double ke, double& pend, double& used, double& s) {
+__device__ __forceinline__ void chain_lane(const ChainView& c, int mode, int g, int liveLinks, double ke, double& pend, double& used, double& s) {
     const int M = c.M;
     const bool isDrude = (g == c.T - 1);
     ChainConst<NL> k;
@@ -391,12 +395,13 @@ __device__ __forceinline__ void chain_lane(const ChainView& c, int mode, int g, 
         const double invQ = c.invEtaMass[g * M + i];
         const double dA = i == 0 ? (k.live ? invQ : 0.0) : c.etaMass[g * M + i - 1] * invQ;
         const double dB = i == 0 ? (k.live ? -c.nkbt[g] * invQ : 0.0) : -kTl * invQ;
-        k.gA[i] = dA * k.dtc4; k.gB[i] = dB * k.dtc4;
+        const bool frozen = i >= liveLinks;
+        k.gA[i] = frozen ? 0.0 : dA * k.dtc4; k.gB[i] = frozen ? 0.0 : dB * k.dtc4;
         st.eta[i] = c.eta[g * M + i];
         st.ed[i] = c.etaDot[g * (M + 1) + i];
         const double edd = c.etaDotDot[g * M + i];
         if (i == 0) edd0 = edd;
-        st.g[i] = edd * k.dtc4;
+        st.g[i] = frozen ? 0.0 : edd * k.dtc4;
         st.ef[i] = 1.0;
     }
     // etaDot[M] is the permanent zero; for a Drude group without chains etaDot[1] may hold user-set state
@@ -415,6 +420,7 @@ __device__ __forceinline__ void chain_lane(const ChainView& c, int mode, int g, 
     }
 #pragma unroll
     for (int i = 0; i < NL; i++) {
+        if (i >= liveLinks) continue;
         c.eta[g * M + i] = st.eta[i];
         c.etaDot[g * (M + 1) + i] = st.ed[i];
         c.etaDotDot[g * M + i] = (i == 0 && !k.live) ? edd0 : st.g[i] * k.inv4;
@@ -488,12 +494,19 @@ __device__ void chain_phase(const ChainView& c, int mode, int lane) {
     double pend = on ? c.pending[lane] : 1.0;
     double used = 0.0, s = 1.0;
     if (on) {
-        const int nl = (lane == c.T - 1 && !c.useDrudeNH) ? 1 : c.M;
-        switch (nl) {
-            case 1: chain_lane<1>(c, mode, lane, ke, pend, used, s); break;
-            case 2: chain_lane<2>(c, mode, lane, ke, pend, used, s); break;
-            case 3: chain_lane<3>(c, mode, lane, ke, pend, used, s); break;
-            case 4: chain_lane<4>(c, mode, lane, ke, pend, used, s); break;
+        const int nl = (lane == c.T - 1 && !c.useDrudeNH) ? 1 : c.M;      // live links of this thermostat (:597-642: the Drude group has one unless useDrudeNHChains)
+        int run = nl;                                                      // links of the code path this lane takes
+        if (nl < c.M && c.M <= 4) {
+            // ride along with the other lanes if the links above the live one are at rest (always, unless a caller set them)
+            bool rest = true;
+            for (int i = 1; i <= c.M; i++) rest &= c.etaDot[lane * (c.M + 1) + i] == 0.0;
+            if (rest) run = c.M;
+        }
+        switch (run) {
+            case 1: chain_lane<1>(c, mode, lane, nl, ke, pend, used, s); break;
+            case 2: chain_lane<2>(c, mode, lane, nl, ke, pend, used, s); break;
+            case 3: chain_lane<3>(c, mode, lane, nl, ke, pend, used, s); break;
+            case 4: chain_lane<4>(c, mode, lane, nl, ke, pend, used, s); break;
             default: chain_lane_generic(c, mode, lane, ke, nl, pend, used, s); break;
         }
     }
