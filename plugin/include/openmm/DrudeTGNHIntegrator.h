@@ -58,6 +58,8 @@ public:
     void setUseCOMTempGroup(int useCOMGroup) { useCOMTempGroup = useCOMGroup; }
     /** Number of temperature groups of the real degrees of freedom. */
     int getNumTempGroups() const { return (int)tempGroups.size(); }
+    /** (not in the reference) number of particles that have been given a temperature group with addParticleTempGroup */
+    int getNumParticleTempGroups() const { return (int)particleTempGroup.size(); }
     /** Creates a temperature group; returns its index (the first call returns 0). */
     int addTempGroup();
     /** Assigns the next particle (in System order) to a group; returns that particle's index. */

@@ -15,7 +15,8 @@ public:
     DrudeTGNHIntegratorProxy();
     void serialize(const void* object, SerializationNode& node) const;
     void* deserialize(const SerializationNode& node) const;
-    /** 1 = byte-compatible with the reference's files; 2 (default) = complete */
+    /** 1 (default) = the reference's format, byte for byte: files interchange with the upstream plugin; 2 = complete (also
+     *  maxDrudeDistance, useCOMTempGroup and the temperature groups, which version 1 loses), not readable by the upstream proxy */
     static int writeVersion;
 };
 

@@ -8,6 +8,7 @@
 
 #include "OpenMMDrudeTGNH.h"
 #include "openmm/serialization/XmlSerializer.h"
+#include "openmm/serialization/DrudeTGNHIntegratorProxy.h"
 
 namespace py = pybind11;
 using namespace OpenMM;
@@ -64,6 +65,14 @@ PYBIND11_MODULE(drudetgnhplugin, m) {
         // SWIG's `int& OUTPUT` typemap: the group comes back as the return value
         .def("getParticleTempGroup", [](const DrudeTGNHIntegrator& i, int particle) { int tg; i.getParticleTempGroup(particle, tg); return tg; }, py::arg("particle"));
     // XmlSerializer.serialize / deserialize for the integrator (what openmm.XmlSerializer does for the SWIG class)
-    m.def("serialize", [](const DrudeTGNHIntegrator& i) { std::stringstream s; XmlSerializer::serialize<DrudeTGNHIntegrator>(&i, "Integrator", s); return s.str(); });
+    // version 1 (default) is the upstream plugin's format; version 2 also keeps maxDrudeDistance, useCOMTempGroup and the temperature groups
+    m.def("serialize", [](const DrudeTGNHIntegrator& i, int version) {
+        const int saved = DrudeTGNHIntegratorProxy::writeVersion;
+        DrudeTGNHIntegratorProxy::writeVersion = version;
+        std::stringstream s;
+        try { XmlSerializer::serialize<DrudeTGNHIntegrator>(&i, "Integrator", s); } catch (...) { DrudeTGNHIntegratorProxy::writeVersion = saved; throw; }
+        DrudeTGNHIntegratorProxy::writeVersion = saved;
+        return s.str();
+    }, py::arg("integrator"), py::arg("version") = 1);
     m.def("deserialize", [](const std::string& xml) { std::stringstream s(xml); return XmlSerializer::deserialize<DrudeTGNHIntegrator>(s); }, py::return_value_policy::take_ownership);
 }

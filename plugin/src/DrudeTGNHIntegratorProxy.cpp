@@ -9,7 +9,7 @@
 
 using namespace OpenMM;
 
-int DrudeTGNHIntegratorProxy::writeVersion = 2;
+int DrudeTGNHIntegratorProxy::writeVersion = 1;
 
 DrudeTGNHIntegratorProxy::DrudeTGNHIntegratorProxy() : SerializationProxy("DrudeTGNHIntegrator") {}
 
@@ -31,9 +31,9 @@ void DrudeTGNHIntegratorProxy::serialize(const void* object, SerializationNode& 
     node.setBoolProperty("useCOMTempGroup", integ.getUseCOMTempGroup());
     node.setIntProperty("numTempGroups", integ.getNumTempGroups());
     SerializationNode& groups = node.createChildNode("ParticleTempGroups");
-    for (int i = 0;; i++) {
+    for (int i = 0; i < integ.getNumParticleTempGroups(); i++) {
         int tg;
-        try { integ.getParticleTempGroup(i, tg); } catch (const OpenMMException&) { break; }
+        integ.getParticleTempGroup(i, tg);
         groups.createChildNode("Particle").setIntProperty("group", tg);
     }
 }

@@ -81,7 +81,9 @@ static void testSerialization() {
     a.addTempGroup(); a.addTempGroup();
     a.addParticleTempGroup(0); a.addParticleTempGroup(1); a.addParticleTempGroup(1);
     stringstream b2;
+    DrudeTGNHIntegratorProxy::writeVersion = 2;
     XmlSerializer::serialize<DrudeTGNHIntegrator>(&a, "Integrator", b2);
+    DrudeTGNHIntegratorProxy::writeVersion = 1;
     DrudeTGNHIntegrator* c2 = XmlSerializer::deserialize<DrudeTGNHIntegrator>(b2);
     ASSERT_EQUAL(0.02, c2->getMaxDrudeDistance()); ASSERT(!c2->getUseCOMTempGroup()); ASSERT_EQUAL(2, c2->getNumTempGroups());
     int tg; c2->getParticleTempGroup(2, tg); ASSERT_EQUAL(1, tg); c2->getParticleTempGroup(0, tg); ASSERT_EQUAL(0, tg);
@@ -97,11 +99,10 @@ static void testSerialization() {
     ASSERT_EQUAL(301.1, c3->getTemperature()); ASSERT_EQUAL(10.5, c3->getDrudeTemperature()); ASSERT_EQUAL(20, c3->getDrudeStepsPerRealStep());
     delete c3;
 
-    // version-1 writing mode: exactly the reference's nine properties, nothing else
-    DrudeTGNHIntegratorProxy::writeVersion = 1;
+    // the default writing mode is version 1: exactly the reference's nine properties, nothing else
+    ASSERT_EQUAL(1, DrudeTGNHIntegratorProxy::writeVersion);
     stringstream b4;
     XmlSerializer::serialize<DrudeTGNHIntegrator>(&integ1, "Integrator", b4);
-    DrudeTGNHIntegratorProxy::writeVersion = 2;
     ASSERT(b4.str() == string(refXml));
     stringstream b5("<?xml version=\"1.0\" ?>\n<Integrator type=\"DrudeTGNHIntegrator\" version=\"3\"/>\n");
     EXPECT_THROW(XmlSerializer::deserialize<DrudeTGNHIntegrator>(b5), "Unsupported version number");

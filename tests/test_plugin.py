@@ -153,6 +153,7 @@ def test_python_module_surface():
     assert integ.addParticleTempGroup(1) == 0 and integ.getParticleTempGroup(0) == 1
     with pytest.raises(dp.OpenMMException, match="not bound to a context"):
         integ.step(1)
-    xml = dp.serialize(integ)
+    assert 'version="1"' in dp.serialize(integ)              # default: the upstream plugin's format
+    xml = dp.serialize(integ, version=2)
     copy = dp.deserialize(xml)
     assert copy.getNumTempGroups() == 2 and copy.getParticleTempGroup(0) == 1 and float(copy.getMaxDrudeDistance()) == 0.02
