@@ -157,3 +157,82 @@ def test_python_module_surface():
     xml = dp.serialize(integ, version=2)
     copy = dp.deserialize(xml)
     assert copy.getNumTempGroups() == 2 and copy.getParticleTempGroup(0) == 1 and float(copy.getMaxDrudeDistance()) == 0.02
+
+
+def _script_style_run(dp, s, precision, steps, springs):
+    """What a user script does (example/nacl_tg.py:30-75), written against drudetgnhplugin + drudetgnhplugin.shim."""
+    mm = dp.shim
+    system = mm.System()
+    for m in s.masses:
+        system.addParticle(float(m))
+    drude = mm.DrudeForce()
+    for d, p in zip(s.pair_drude, s.pair_parent):
+        drude.addParticle(int(d), int(p), -1, -1, -1, -1.0, 1.0, 1.0, 1.0)
+    system.addForce(drude)
+    bonds = mm.BondForce()                       # molecules = the integrator's residues
+    for i in range(1, s.num_particles):
+        if s.res_id[i] == s.res_id[i - 1]:
+            bonds.addBond(i - 1, i)
+    system.addForce(bonds)
+    integ = dp.DrudeTGNHIntegrator(s.temperature, s.coupling_time, s.drude_temperature, s.drude_coupling_time, s.step_size, s.drude_steps,
+                                   s.num_nh_chains, int(s.use_drude_nh_chains), int(s.use_com_temp_group))
+    integ.setMaxDrudeDistance(s.max_drude_distance)
+    for _ in range(s.num_temp_groups):
+        integ.addTempGroup()
+    for g in s.temp_group:
+        integ.addParticleTempGroup(int(g))
+    platform = mm.Platform.getPlatformByName("CUDA")
+    context = mm.Context(system, integ, platform, {"Precision": precision})
+    context.setPositions(s.positions)
+    context.setVelocities(s.velocities)
+    ext = np.rint(s.forces * 4294967296.0) / 4294967296.0
+    if springs:
+        context.setForceModel(ext, [int(x) for x in s.pair_drude], [int(x) for x in s.pair_parent], [float(k) for k in s.k_spring])
+    else:
+        context.setForceModel(ext)
+    integ.step(steps)
+    st = context.getState(getPositions=True, getVelocities=True, getEnergy=True)
+    return st.getPositions(), st.getVelocities(), st.getKineticEnergy(), ext
+
+
+def test_python_shim_surface_and_loud_failure_without_a_device():
+    """The stand-in classes a script needs exist under OpenMM's names; without a CUDA device, creating the Context fails with an
+    OpenMMException (no silent CPU path)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "plugin", "python"))
+    import drudetgnhplugin as dp
+    for name in ("System", "DrudeForce", "BondForce", "CMMotionRemover", "Platform", "Context", "State"):
+        assert hasattr(dp.shim, name)
+    assert dp.shim.Platform.getPlatformByName("CUDA").getName() == "CUDA"
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present: covered by test_python_script_runs_the_integrator_on_the_gpu")
+    s = synth.water_box(8, 2)
+    with pytest.raises(dp.OpenMMException, match="no CUDA device"):
+        _script_style_run(dp, s, "single", 1, False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,springs", [("single", False), ("mixed", True)])
+def test_python_script_runs_the_integrator_on_the_gpu(cuda, precision, springs):
+    """integrator.step(n) from Python: System / DrudeForce / Context(platform "CUDA", Precision) / getState, the way
+    example/nacl_tg.py drives the reference, through the pybind11 module; 20 steps against the oracle."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "plugin", "python"))
+    import drudetgnhplugin as dp
+    kw = dict(quantize_masses=True)
+    if springs:
+        kw.update(pair_force="none", cold_drudes=True, drude_sigma=1.4e-4, force_sigma=2.0)
+    s = synth.water_box(1500, 3, **kw)
+    s.positions = (s.positions - s.positions.mean(0)).astype(np.float32).astype(np.float64)
+    if precision == "single":
+        s.velocities = s.velocities.astype(np.float32).astype(np.float64)
+    steps = 20
+    p, v, ke, ext = _script_style_run(dp, s, precision, steps, springs)
+    o = O.Oracle(s, O.TG)
+    pb, vb = s.positions.copy(), s.velocities.copy()
+    fb = O.harmonic_forces(s, pb, ext) if springs else ext.copy()
+    o.step(pb, vb, fb, steps, 1 if springs else 0, ext if springs else None, s.k_spring if springs else None)
+    tol_v, tol_x = (2e-5, 1e-5) if precision == "single" else (1e-6, 1e-7)
+    assert rel_err(v, vb) < tol_v and rel_err(p, pb) < tol_x
+    assert abs(ke - o.ke_sum) / o.ke_sum < (1e-6 if precision == "single" else 1e-7)
