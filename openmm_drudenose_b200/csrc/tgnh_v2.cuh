@@ -93,8 +93,8 @@ struct V2Layout {
     static constexpr int OFF_X = OFF_V + V2_TILE * 16;
     static constexpr int OFF_F = OFF_X + (HAS_X ? V2_TILE * 16 : 0);
     static constexpr int OFF_S = OFF_F + (HAS_F ? 3 * V2_FW * FBYTES : 0);
-    static constexpr int OFF_HDR = OFF_S + V2_SW;            // int start, pad[3]; uint16 chunkOff[V2_NCONS + 1]; pad
-    static constexpr int STAGE = OFF_HDR + 16 + ((2 * (V2_NCONS + 1) + 15) & ~15);
+    static constexpr int OFF_HDR = OFF_S + V2_SW;            // uint2 per consumer warp: { first particle of the tile, chunk offset | chunk length << 16 }
+    static constexpr int STAGE = OFF_HDR + ((8 * V2_NCONS + 15) & ~15);
     static constexpr int OFF_BAR = NSTAGE * STAGE;            // full[NS], empty[NS]
     static constexpr int OFF_SCALE = OFF_BAR + 128;           // double[MAX_T] s^2 (unused), double[MAX_T] s - 1
     static constexpr int OFF_MISC = OFF_SCALE + MAX_T * 16;
@@ -133,12 +133,12 @@ __device__ __forceinline__ void seg_scan(V3<float>& p, int lane, int segStart, i
 // power of two) and chunks are full, so residues are aligned lane groups and a butterfly does it; otherwise a segmented scan
 // followed by a read of the segment's last lane.
 __device__ __forceinline__ V3<float> residue_sum(V3<float> p, int lane, int offFirst, int offLast, int maxRes, int bfly) {
+    auto level = [&](int o) { p.x += __shfl_xor_sync(0xffffffffu, p.x, o); p.y += __shfl_xor_sync(0xffffffffu, p.y, o); p.z += __shfl_xor_sync(0xffffffffu, p.z, o); };
+    if (bfly == 4) { level(1); level(2); return p; }          // the commonest case first: one warp-uniform test, no per-level tests
     if (bfly > 0) {
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1)
-            if (o < bfly) {
-                p.x += __shfl_xor_sync(0xffffffffu, p.x, o); p.y += __shfl_xor_sync(0xffffffffu, p.y, o); p.z += __shfl_xor_sync(0xffffffffu, p.z, o);
-            }
+            if (o < bfly) level(o);
         return p;
     }
     seg_scan(p, lane, lane - offFirst, maxRes);
@@ -191,8 +191,9 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
         const int f0 = start & ~3, fn = ((end + 3) & ~3) - f0;            // 16-byte aligned windows
         const int s0 = start & ~15, sn = ((end + 15) & ~15) - s0;
         if (parts & 1) {
-            if (lane == 0) *reinterpret_cast<int*>(st + L::OFF_HDR) = start;
-            if (lane <= V2_NCONS) reinterpret_cast<unsigned short*>(st + L::OFF_HDR + 16)[lane] = (unsigned short)(cs - start);
+            const int csNext = __shfl_down_sync(0xffffffffu, cs, 1);
+            if (lane < V2_NCONS)            // one 8-byte word per consumer warp: a single shared-memory load tells it where its chunk is
+                reinterpret_cast<uint2*>(st + L::OFF_HDR)[lane] = make_uint2((unsigned int)start, (unsigned int)(cs - start) | ((unsigned int)(csNext - cs) << 16));
             __syncwarp();
             if (lane == 0) {
                 uint32_t bytes = n * 16 + sn;
@@ -270,17 +271,19 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
         F2 eCOM; eCOM.hi = seps[G].x; eCOM.lo = seps[G].y;
         const float dt = (float)a.dt, fscale = (float)a.fscale, rmax = (float)a.rmax, rmax2 = rmax * rmax;
         const int maxRes = USE_COM ? a.maxRes : 1, bfly = a.butterfly;
-        for (int it = 0; it < myTiles; it++) {
-            const int stg = it % NS;
+        int spRow = -1;                                              // species row held in q0, q1
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+        int stg = 0;
+        uint32_t phase = 0;                                          // (stage, parity) advance incrementally: no division / modulo per tile
+        for (int it = 0; it < myTiles; it++, phase ^= (stg + 1 == NS), stg = (stg + 1 == NS) ? 0 : stg + 1) {
             unsigned char* st = smem + stg * L::STAGE;
             const float4* sv = reinterpret_cast<const float4*>(st + L::OFF_V);
             const float4* sx = reinterpret_cast<const float4*>(st + L::OFF_X);
             const unsigned char* sF = st + L::OFF_F;
             const unsigned char* sS = st + L::OFF_S;
-            mbar_wait(&full[stg], (it / NS) & 1);
-            const int start = *reinterpret_cast<const int*>(st + L::OFF_HDR);
-            const unsigned short* co = reinterpret_cast<const unsigned short*>(st + L::OFF_HDR + 16);
-            const int c0 = co[warp], cn = co[warp + 1] - c0;
+            mbar_wait(&full[stg], phase);
+            const uint2 hdr = reinterpret_cast<const uint2*>(st + L::OFF_HDR)[warp];
+            const int start = (int)hdr.x, c0 = (int)(hdr.y & 0xffffu), cn = (int)(hdr.y >> 16);
             const bool active = lane < cn;
             const int i = c0 + lane;                                 // index inside the tile
             float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -291,7 +294,14 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                 sp = sS[(start & 15) + i];
                 if (L::HAS_F) F = v2_force<FFMT>(sF, (start & 3) + i);
             }
-            const float4 q0 = stab[sp * V2_ROW_F4];
+            // The species row of a lane rarely changes from tile to tile (periodic layouts: every chunk of a water box has the same
+            // composition), and the shared-memory pipe is what bounds the second half (LDS + SHFL: ~26 of its cycles per warp and
+            // tile, 30 warps per SM): the row stays in registers and is fetched again only when the species byte differs.
+            if (sp != spRow) {
+                q0 = stab[sp * V2_ROW_F4];
+                q1 = stab[sp * V2_ROW_F4 + 1];
+                spRow = sp;
+            }
             const uint32_t meta = __float_as_uint(q0.w);
             const int tg = v2_tg(meta);
             const uint32_t role = v2_role(meta);
@@ -307,7 +317,6 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
             if (IS_A) {
                 // thermostat scaling (integrateDrudeTGNHChain, drudeTGNH.cu:255-300) in the unified form of tgnh_kernels.cuh,
                 // half kick (:314-364), drift (:438-465), hard wall (:474-573)
-                const float4 q1 = stab[sp * V2_ROW_F4 + 1];
                 V3<float> V = v3(0.f, 0.f, 0.f);
                 if (USE_COM) {
                     // V only feeds the corrections (sT-1)(v-V), (sCOM-1)V: fp32 masses are ample
@@ -358,35 +367,28 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                 if (KIND == V2_B && !a.lazyKick && active && massive) st_global(gvelm + gidx, pack4(vn, w));
                 V3<float> V = v3(0.f, 0.f, 0.f);
                 float keC = 0.f;
-                const bool first = offFirst == 0;
-                const bool needQ1 = role == ROLE_DRUDE || (USE_COM && first);
-                float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (needQ1) q1 = stab[sp * V2_ROW_F4 + 1];
                 if (USE_COM) {
                     // calcCOMVelocities (:86-105): P = sum m v over the residue, V = P / M
                     const V3<float> P = residue_sum(v3(mul2(q0.x, q0.y, vn.x), mul2(q0.x, q0.y, vn.y), mul2(q0.x, q0.y, vn.z)), lane, offFirst, offLast, maxRes, bfly);
                     V = q0.z * P;
-                    if (first) keC = mul2(q0.z, q1.z, dot3(P));      // |P|^2 / M  (:154), carried by the residue's first particle
+                    keC = offFirst == 0 ? mul2(q0.z, q1.z, dot3(P)) : 0.f;      // |P|^2 / M  (:154), carried by the residue's first particle
                 }
-                // computeNormalizedKineticEnergies (:161-186)
+                // computeNormalizedKineticEnergies (:161-186); no branches: a massless particle, a lane without particle and a particle
+                // that is no Drude particle have m = 0 resp. contribute a term multiplied by 0
                 const V3<float> r = vn - V;                           // normalizeVelocities (:126-128)
-                float ke = mul2(q0.x, q0.y, dot3(r));
                 const V3<float> vjn = v3(__shfl_sync(0xffffffffu, vn.x, pl), __shfl_sync(0xffffffffu, vn.y, pl), __shfl_sync(0xffffffffu, vn.z, pl));
-                if (role == ROLE_DRUDE) {
-                    const float keD = mul2(q1.x, q1.y, dot3(vjn - vn));   // mu |rel|^2 (:185)
-                    ke -= keD;                                        // m_d |r_d|^2 + m_p |r_p|^2 - mu |rel|^2 = (m_d + m_p) |cm|^2 (:184)
-                    accDrude += keD;
-                }
+                const float keD = role == ROLE_DRUDE ? mul2(q1.x, q1.y, dot3(vjn - vn)) : 0.f;   // mu |rel|^2 (:185)
+                // m_d |r_d|^2 + m_p |r_p|^2 - mu |rel|^2 = (m_d + m_p) |cm|^2 (:184)
+                const float ke = mul2(q0.x, q0.y, dot3(r)) - keD;
+                accDrude += keD;
                 accCOM += keC;
                 // this thread's particles usually stay in one group from tile to tile (molecule-periodic group patterns): the running
                 // sum lives in a register and moves to its shared-memory column only when the group changes
-                if (active && massive) {
-                    if (tg != curTg) {
-                        if (curTg >= 0) { ske[curTg * V2_TILE + tid] += accT; accT = 0.f; }
-                        curTg = tg;
-                    }
-                    accT += ke;
+                if (tg != curTg) {
+                    if (curTg >= 0) { ske[curTg * V2_TILE + tid] += accT; accT = 0.f; }
+                    curTg = tg;
                 }
+                accT += ke;
             }
             // hand the stage back: one arrival per consumer warp
             __syncwarp();
