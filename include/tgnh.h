@@ -194,6 +194,10 @@ int tgnh_plan_chunks(const tgnh_params* p, int32_t* chunk_start, int32_t capacit
                      float* table_out /*[256*8]*/, int32_t* num_species, int32_t* max_residue);
 /* 2 when the handle's two halves run through the warp-chunk kernels, 1 otherwise (environment TGNH_V2=0 forces 1) */
 int tgnh_kernel_generation(const tgnh_handle* h);
+/* 1 when tgnh_step(n) leaves the second half kick of every step but the last to the next first half (the second half then only
+ * reduces the kinetic energies: 28 instead of 44 bytes per particle; bit-identical results).  Warp-chunk kernels only, not for
+ * systems small enough to run the chain in the reducing launch; environment TGNH_LAZY_KICK=0 at tgnh_create switches it off. */
+int tgnh_lazy_second_kick(const tgnh_handle* h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t tgnh_launch_count(const tgnh_handle* h);
 /* Per-launch device timing: while enabled every streaming launch is bracketed by CUDA events on its stream.

@@ -179,7 +179,12 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
 
     const uint64_t polOnce = policy_evict_first();
     // velm of a second half that stores nothing: the next first half starts on the tiles read last, keep them in L2
-    const uint64_t polV = (KIND == V2_B && a.lazyKick) ? policy_evict_normal() : polOnce;
+#ifndef TGNH_V2_LAZY_KEEP
+#define TGNH_V2_LAZY_KEEP 100
+#endif
+    // ... but only the part of it that can still be there: the tiles this launch reads last (percent of each CTA's tiles)
+    const uint64_t polKeep = (KIND == V2_B && a.lazyKick) ? policy_evict_normal() : polOnce;
+    const int keepFrom = myTiles - (myTiles * TGNH_V2_LAZY_KEEP + 99) / 100;
     // Producer: request tile `it` of this CTA into its stage (the whole warp calls; lane 0 issues the copies).
     // parts: 1 = header + everything no launch of this library writes (posq, forces, species bytes), arms the barrier with
     // the full byte count; 2 = velm; 3 = both.  `cs` = chunkStart[15 * tile + lane] for lanes 0..15.
@@ -209,7 +214,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                 bulk_g2s(st + L::OFF_S, a.spec + s0, sn, bar, polOnce);
             }
         }
-        if ((parts & 2) && lane == 0) bulk_g2s(st + L::OFF_V, gvelm + start, n * 16, bar, polV);
+        if ((parts & 2) && lane == 0) bulk_g2s(st + L::OFF_V, gvelm + start, n * 16, bar, it >= keepFrom ? polKeep : polOnce);
     };
     auto chunk_bounds = [&](int it) { return lane <= V2_NCONS ? __ldg(a.chunkStart + V2_NCONS * tile_of(it) + lane) : 0; };
 
