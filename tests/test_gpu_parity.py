@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_STEP = 1e-5      # x, v per step
 TOL_THERMO = 1e-6    # group temperatures, chain variables over 1000 steps
+TOL_CHAIN_1000_EACH = 2e-5   # the same, every chain variable relative to its own magnitude
 TOL_CHAIN_1000 = 2e-6  # chain variables after 1000 free-running steps with an fp32 state, relative to the chain's largest
                        # variable (measured 1.2e-6; the temperatures themselves hold 1e-6, see DESIGN.md "Parity")
 
@@ -294,6 +295,12 @@ def test_thousand_steps_thermostat_parity(cuda, drude_chain):
     np.testing.assert_allclose(t_gpu[live], t_ref[live], rtol=TOL_THERMO)
     np.testing.assert_allclose(h.vscale()[live], o.vscale[live], rtol=TOL_THERMO)
     assert chain_err(ed_g[live], ed_r[live]) < TOL_CHAIN_1000 and chain_err(eta_g[live], eta_r[live]) < TOL_CHAIN_1000
+    # ... and per variable (each against its own magnitude): 2e-5, the bound the same layout holds against the reference's CUDA
+    # platform (tests/test_refcuda.py::test_plugin_against_reference_cuda_1000_steps, where the cause is given: with FIXED forces
+    # the fp32 rounding error of v + dv repeats every step instead of averaging out; the mixed layout holds 3e-13 on this run)
+    for got, ref in ((ed_g[live], ed_r[live]), (eta_g[live], eta_r[live])):
+        nz = np.abs(ref) > 1e-6 * np.abs(ref).max()
+        assert np.max(np.abs(got - ref)[nz] / np.abs(ref)[nz]) < TOL_CHAIN_1000_EACH
     if drude_chain:
         assert abs(t_gpu[-1] / t_ref[-1] - 1) < 3e-2
     assert rel_err(st.vel(), v) < (5e-2 if drude_chain else 2e-3)   # individual trajectories after 1000 fp32 steps (Drude members follow their chaotic thermostat)
