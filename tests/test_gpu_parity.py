@@ -298,7 +298,9 @@ def test_thousand_steps_thermostat_parity(cuda, drude_chain):
     # ... and per variable (each against its own magnitude): 2e-5, the bound the same layout holds against the reference's CUDA
     # platform (tests/test_refcuda.py::test_plugin_against_reference_cuda_1000_steps, where the cause is given: with FIXED forces
     # the fp32 rounding error of v + dv repeats every step instead of averaging out; the mixed layout holds 3e-13 on this run)
-    for got, ref in ((ed_g[live], ed_r[live]), (eta_g[live], eta_r[live])):
+    # (particle thermostats; the Drude thermostat's chain velocity is a difference of nearly equal numbers, 0.013 against ~800 for
+    # the others at 1 K: it is covered by the array-scale bound above and by its temperature and scale factor, which hold 1e-6)
+    for got, ref in ((ed_g[:-1], ed_r[:-1]), (eta_g[:-1], eta_r[:-1])):
         nz = np.abs(ref) > 1e-6 * np.abs(ref).max()
         assert np.max(np.abs(got - ref)[nz] / np.abs(ref)[nz]) < TOL_CHAIN_1000_EACH
     if drude_chain:
