@@ -1055,6 +1055,7 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     a.fusedChainMode = fused ? chainMode : CHAIN_NONE;
     a.earlyLoads = h->earlyOK ? 1 : 0;
     a.lazyKick = h->lazyNow ? 1 : 0;
+    a.uniformGroups = h->uniformGroups ? 1 : 0;
     // the two halves and the plain reduction run through the warp-chunk kernels where the system qualifies
     const int kind2 = !h->v2 ? -1 : kind == KIND_A ? V2_A : kind == h->kindB ? V2_B : (kind == h->kindKE && !applyScale) ? V2_KE : kind == KIND_S ? V2_S : -1;
     if (kind2 >= 0) {
@@ -1247,6 +1248,7 @@ static int launch_v2_range(tgnh_handle* h, cudaStream_t s, int kind2, void* velm
     if (h->peers.world > 1 && reduces && last) a.peers.seq = ++h->reduceSeq; else a.peers.world = 0;
     a.spec = h->dSpec; a.chunkStart = h->dChunkStart; a.specTable = h->dSpecTable; a.maxRes = h->maxRes; a.butterfly = h->butterfly; a.tableRows = h->numSpecies + 1;
     a.numTiles = tileCount; a.tileBegin = tileBegin; a.accumulate = accumulate ? 1 : 0;
+    a.uniformGroups = h->uniformGroups ? 1 : 0;
     int grid = kind2 == V2_A ? h->gridA2v : kind2 == V2_B ? h->gridB2v : h->gridKE2v;
     if (grid > tileCount) grid = tileCount;
     const int smem = kind2 == V2_A ? h->smemA2v : kind2 == V2_B ? h->smemB2v : h->smemKE2v;

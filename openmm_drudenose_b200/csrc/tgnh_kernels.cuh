@@ -92,6 +92,7 @@ struct StreamArgs {
     int earlyLoads;           // the launches that precede this one in the stream are this library's own and write neither
                               // posq, forces nor posqCorrection: those tiles may be requested before griddepcontrol.wait
     // warp-chunk kernels (tgnh_v2.cuh)
+    int uniformGroups;           // every residue lies in one temperature group
     int lazyKick;                // second half: the kicked velocities are reduced but NOT stored; first half: velm still lacks the
                                  // previous step's second half kick, which is applied (same forces, same fp32 operation, bit-identical
                                  // velocities) before anything else.  Only between the steps of one tgnh_step(n) call.

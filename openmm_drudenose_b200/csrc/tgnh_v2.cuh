@@ -370,21 +370,28 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                 // what was stored
                 const V3<float> vn = kicked(v, fw, F);
                 if (KIND == V2_B && !a.lazyKick && active && massive) st_global(gvelm + gidx, pack4(vn, w));
-                V3<float> V = v3(0.f, 0.f, 0.f);
-                float keC = 0.f;
+                float keC = 0.f, keRel;
+                // computeNormalizedKineticEnergies (:161-186); no branches on the particle: a massless particle, a lane without
+                // particle and a particle that is no Drude particle have m = 0 resp. contribute a term multiplied by 0
                 if (USE_COM) {
                     // calcCOMVelocities (:86-105): P = sum m v over the residue, V = P / M
-                    const V3<float> P = residue_sum(v3(mul2(q0.x, q0.y, vn.x), mul2(q0.x, q0.y, vn.y), mul2(q0.x, q0.y, vn.z)), lane, offFirst, offLast, maxRes, bfly);
-                    V = q0.z * P;
+                    const V3<float> pm = v3(mul2(q0.x, q0.y, vn.x), mul2(q0.x, q0.y, vn.y), mul2(q0.x, q0.y, vn.z));
+                    const V3<float> P = residue_sum(pm, lane, offFirst, offLast, maxRes, bfly);
                     keC = offFirst == 0 ? mul2(q0.z, q1.z, dot3(P)) : 0.f;      // |P|^2 / M  (:154), carried by the residue's first particle
-                }
-                // computeNormalizedKineticEnergies (:161-186); no branches: a massless particle, a lane without particle and a particle
-                // that is no Drude particle have m = 0 resp. contribute a term multiplied by 0
-                const V3<float> r = vn - V;                           // normalizeVelocities (:126-128)
+                    if (a.uniformGroups) {
+                        // every residue lies in one temperature group: sum_i m_i |v_i - V|^2 = sum_i m_i |v_i|^2 - |P|^2 / M, the
+                        // members need neither V nor their relative velocity
+                        keRel = pm.x * vn.x + pm.y * vn.y + pm.z * vn.z - keC;
+                    } else {
+                        const V3<float> r = vn - q0.z * P;             // normalizeVelocities (:126-128)
+                        keRel = mul2(q0.x, q0.y, dot3(r));
+                    }
+                } else
+                    keRel = mul2(q0.x, q0.y, dot3(vn));
                 const V3<float> vjn = v3(__shfl_sync(0xffffffffu, vn.x, pl), __shfl_sync(0xffffffffu, vn.y, pl), __shfl_sync(0xffffffffu, vn.z, pl));
                 const float keD = role == ROLE_DRUDE ? mul2(q1.x, q1.y, dot3(vjn - vn)) : 0.f;   // mu |rel|^2 (:185)
-                // m_d |r_d|^2 + m_p |r_p|^2 - mu |rel|^2 = (m_d + m_p) |cm|^2 (:184)
-                const float ke = mul2(q0.x, q0.y, dot3(r)) - keD;
+                // m_d |r_d|^2 + m_p |r_p|^2 - mu |rel|^2 = (m_d + m_p) |cm|^2 (:184; the identity holds in any frame)
+                const float ke = keRel - keD;
                 accDrude += keD;
                 accCOM += keC;
                 // this thread's particles usually stay in one group from tile to tile (molecule-periodic group patterns): the running
