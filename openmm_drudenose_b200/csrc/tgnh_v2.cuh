@@ -189,6 +189,13 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     const uint64_t polKeep = (KIND == V2_B && a.lazyKick) ? policy_evict_last() : polOnce;
     const int keepTiles = (int)(((size_t)TGNH_V2_LAZY_KEEP_MB << 20) / ((size_t)gridDim.x * V2_TILE * 16)) + 1;     // per CTA
     const int keepFrom = myTiles - keepTiles;
+#ifndef TGNH_V2_A_STORE_KEEP_MB
+#define TGNH_V2_A_STORE_KEEP_MB 0
+#endif
+#if TGNH_V2_A_STORE_KEEP_MB > 0
+    const uint64_t polStoreKeep = policy_evict_last();
+    const int storeKeepFrom = myTiles - ((int)(((size_t)TGNH_V2_A_STORE_KEEP_MB << 20) / ((size_t)gridDim.x * V2_TILE * 16)) + 1);
+#endif
     // Producer: request tile `it` of this CTA into its stage (the whole warp calls; lane 0 issues the copies).
     // parts: 1 = header + everything no launch of this library writes (posq, forces, species bytes), arms the barrier with
     // the full byte count; 2 = velm; 3 = both.  `cs` = chunkStart[15 * tile + lane] for lanes 0..15.
@@ -366,7 +373,12 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                     }
                 }
                 if (active && massive) {
+#if TGNH_V2_A_STORE_KEEP_MB > 0
+                    // experiment: only the velm this launch writes last can still be in L2 when the next launch reads it
+                    st_global_hint(gvelm + gidx, pack4(vn, w), it >= storeKeepFrom ? polStoreKeep : polOnce);
+#else
                     st_global(gvelm + gidx, pack4(vn, w));
+#endif
                     st_stream(static_cast<float4*>(a.posq) + gidx, make_float4(xn.x, xn.y, xn.z, x4.w));
                 }
             } else {
