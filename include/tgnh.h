@@ -184,7 +184,7 @@ int tgnh_plan_tiles(const tgnh_params* p, int32_t* tile_start, int32_t capacity,
  * swaps molecules whose tables agree ("Atom reordering"). */
 int tgnh_plan_descriptors(const tgnh_params* p, uint32_t* desc_out /*[num_particles]*/);
 /* The plan of the warp-chunk kernels (csrc/tgnh_v2.cuh), host-only: residue-aligned chunks of at most 32 consecutive particles
- * (chunk_start receives num_chunks + 1 particle indices, num_chunks a multiple of 15 = the chunks of one tile, the tail
+ * (chunk_start receives num_chunks + 1 particle indices, num_chunks a multiple of tgnh_chunks_per_tile(), the tail
  * padded with empty chunks), one species byte per particle, and the species table (256 rows of 8 floats: m_hi, m_lo,
  * 1/M_residue hi, meta bits, mu_hi, mu_lo, 1/M_residue lo, m_partner/(m + m_partner); the row after the last species = "no particle", all zero; meta: [4:0] temperature
  * group, [6:5] role, [12:7] signed offset to the pair partner, [17:13] / [22:18] offsets to the first / last particle of the residue).
@@ -192,6 +192,8 @@ int tgnh_plan_descriptors(const tgnh_params* p, uint32_t* desc_out /*[num_partic
  * 255 species): such systems run through the first-generation kernels (tgnh_plan_tiles).  Any output pointer may be NULL. */
 int tgnh_plan_chunks(const tgnh_params* p, int32_t* chunk_start, int32_t capacity, int32_t* num_chunks, uint8_t* species_out /*[N]*/,
                      float* table_out /*[256*8]*/, int32_t* num_species, int32_t* max_residue);
+/* chunks (= consumer warps) per tile of the warp-chunk kernels: tgnh_plan_chunks pads its chunk table to a multiple of it */
+int tgnh_chunks_per_tile(void);
 /* 2 when the handle's two halves run through the warp-chunk kernels, 1 otherwise (environment TGNH_V2=0 forces 1) */
 int tgnh_kernel_generation(const tgnh_handle* h);
 /* 1 when tgnh_step(n) leaves the second half kick of every step but the last to the next first half (the second half then only

@@ -934,6 +934,7 @@ extern "C" int tgnh_plan_chunks(const tgnh_params* p, int32_t* chunk_start, int3
     return TGNH_OK;
 }
 
+extern "C" int tgnh_chunks_per_tile(void) { return V2_NCONS; }
 extern "C" int tgnh_kernel_generation(const tgnh_handle* h) { return h ? (h->v2 ? 2 : 1) : 0; }
 extern "C" int tgnh_lazy_second_kick(const tgnh_handle* h) { return h && h->lazyKick && h->v2 && !h->fuseChain && h->uniformGroups ? 1 : 0; }
 

@@ -11,7 +11,7 @@
 // instructions, 40 % XU pipe, 7.5 M shared-memory bank conflicts, all warps of a CTA coupled through the slowest one):
 //
 //  * WARP-CHUNKS.  The particles are cut into residue-aligned chunks of at most 32 consecutive particles, one per warp
-//    and tile (15 chunks = at most 480 particles per tile).  A Drude pair lies inside a residue, a residue inside a
+//    and tile (14 chunks = at most 448 particles per tile).  A Drude pair lies inside a residue, a residue inside a
 //    chunk, so the pair partner and all members of the residue are lanes of the same warp: partner values travel by
 //    one shuffle, residue sums by a segmented warp scan.  No thread reads another warp's particles, nothing is gathered
 //    from shared memory with a stride (no bank conflicts), and no warp waits for another one inside a tile.
@@ -22,8 +22,11 @@
 //    caller passed in System::getParticleMass): the kinetic-energy sums are unbiased per species (a mass rounded to
 //    fp32 would shift a thermostat's energy systematically and the Nose-Hoover chain integrates that), yet the inner
 //    loop contains no reciprocal, no float<->double conversion and no fp64 instruction at all.
-//  * PRODUCER WARP.  Warp 15 only streams: it waits for a stage to be released by the 15 consumer warps and requests the
-//    next tile (cp.async.bulk / UBLKCP completing on the stage's mbarrier).  No consumer ever blocks on a refill.
+//  * PRODUCER WARPS.  Warps 14 and 15 only stream: a producer waits for a stage to be released by the 14 consumer warps and requests
+//    the next tile (cp.async.bulk / UBLKCP completing on the stage's mbarrier).  No consumer ever blocks on a refill.  The ~60
+//    serial instructions of a refill are on the critical path of the ring in the kernels that move little data per tile, so in
+//    the second-half, reduction and scaling kernels the two producers take every other tile; the HBM-bound first-half kernel
+//    runs best with one producer at its own pace (the other idles).
 //  * fp32 running sums per thread (the thread's group sum moves to its fp32 column when the group changes); fp64 from
 //    the end of the tile loop on (warp shuffles -> CTA -> fixed-order sum over the CTAs by the last one), bit-reproducible
 //    run to run.
@@ -44,7 +47,7 @@ namespace tgnh {
 
 enum { V2_A = 0, V2_B = 1, V2_KE = 2, V2_S = 3 };
 #ifndef TGNH_V2_NCONS
-#define TGNH_V2_NCONS 15
+#define TGNH_V2_NCONS 14
 #endif
 #ifndef TGNH_V2_NS_A
 #define TGNH_V2_NS_A 3
@@ -61,7 +64,11 @@ enum { V2_A = 0, V2_B = 1, V2_KE = 2, V2_S = 3 };
 constexpr int V2_PF_A = TGNH_V2_PF_A;         // the same for the first-half kernel
 constexpr int V2_PF = TGNH_V2_PF;             // the producer fetches the chunk bounds of a tile this many tiles ahead
 constexpr int V2_NCONS = TGNH_V2_NCONS;       // consumer warps per CTA (the last warp is the producer)
-constexpr int V2_THREADS = (V2_NCONS + 1) * 32;
+#ifndef TGNH_V2_NPROD
+#define TGNH_V2_NPROD 2
+#endif
+constexpr int V2_NPROD = TGNH_V2_NPROD;       // producer warps (each refills every V2_NPROD-th tile)
+constexpr int V2_THREADS = (V2_NCONS + V2_NPROD) * 32;
 constexpr int V2_CTAS = V2_NCONS > 15 ? 1 : 2;   // resident CTAs per SM the kernels are compiled for
 constexpr int V2_TILE = V2_NCONS * 32;        // particles per tile, at most
 constexpr int V2_FW = V2_TILE + 8;            // 4-aligned window of force components that covers any tile
@@ -198,7 +205,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
 #endif
     // Producer: request tile `it` of this CTA into its stage (the whole warp calls; lane 0 issues the copies).
     // parts: 1 = header + everything no launch of this library writes (posq, forces, species bytes), arms the barrier with
-    // the full byte count; 2 = velm; 3 = both.  `cs` = chunkStart[15 * tile + lane] for lanes 0..15.
+    // the full byte count; 2 = velm; 3 = both.  `cs` = chunkStart[V2_NCONS * tile + lane] for lanes 0..V2_NCONS.
     auto issue = [&](int it, int parts, int cs) {
         const int start = __shfl_sync(0xffffffffu, cs, 0), end = __shfl_sync(0xffffffffu, cs, V2_NCONS);
         const int n = end - start;
@@ -229,9 +236,16 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     };
     auto chunk_bounds = [&](int it) { return lane <= V2_NCONS ? __ldg(a.chunkStart + V2_NCONS * tile_of(it) + lane) : 0; };
 
-    const bool producer = warp == V2_NCONS;
+    const bool producer = warp >= V2_NCONS;
+    const int pidx = warp - V2_NCONS;                   // which producer
+    // The first-half kernel is bound by HBM and runs best with ONE producer that refills at its own pace (any eagerness of the
+    // producer costs it 3 us: prefetched chunk bounds +3.1, two producers +2.8); in the second-half, reduction and scaling kernels
+    // the producer's ~60 serial instructions per tile are on the critical path of the ring, and two producers that take every
+    // other tile are worth 4.7 us of 66.
+    constexpr int NPROD = L::HAS_X ? 1 : V2_NPROD;
     const int preloaded = myTiles < NS ? myTiles : NS;
-    if (producer) {
+    if (producer && pidx > 0) pdl_wait();
+    else if (producer) {
         // The first NS tiles are requested while the consumer warps still copy the species table and clear their energy columns.
         // Inputs that no earlier launch of this stream can still be writing may even be requested before griddepcontrol.wait (only
         // when the host knows that the preceding launches are this library's own and do not write them: a.earlyLoads).
@@ -271,14 +285,14 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
         constexpr int PF = L::HAS_X ? V2_PF_A : V2_PF;
         int csq[PF > 0 ? PF : 1];
 #pragma unroll
-        for (int k = 0; k < PF; k++) csq[k] = preloaded + k < myTiles ? chunk_bounds(preloaded + k) : 0;
-        for (int it = preloaded; it < myTiles; it++) {
+        for (int k = 0; k < PF; k++) csq[k] = preloaded + pidx + k * NPROD < myTiles ? chunk_bounds(preloaded + pidx + k * NPROD) : 0;
+        for (int it = preloaded + pidx; pidx < NPROD && it < myTiles; it += NPROD) {
             int cs;
             if (PF > 0) {
                 cs = csq[0];
 #pragma unroll
                 for (int k = 0; k + 1 < PF; k++) csq[k] = csq[k + 1];
-                csq[PF - 1] = it + PF < myTiles ? chunk_bounds(it + PF) : 0;
+                csq[PF - 1] = it + PF * NPROD < myTiles ? chunk_bounds(it + PF * NPROD) : 0;
             } else cs = chunk_bounds(it);
             mbar_wait(&empty[it % NS], ((it / NS) - 1) & 1);
             issue(it, 3, cs);
@@ -386,10 +400,19 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                 // what was stored
                 const V3<float> vn = kicked(v, fw, F);
                 if (KIND == V2_B && !a.lazyKick && active && massive) st_global(gvelm + gidx, pack4(vn, w));
+#ifndef TGNH_V2_ABLATE
+#define TGNH_V2_ABLATE 0
+#endif
+#if TGNH_V2_ABLATE == 2            // measurement builds only (wrong energies): what the pipeline costs without the energy arithmetic
+                accT += vn.x + vn.y + vn.z;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stg]);
+                continue;
+#endif
                 float keC = 0.f, keRel;
                 // computeNormalizedKineticEnergies (:161-186); no branches on the particle: a massless particle, a lane without
                 // particle and a particle that is no Drude particle have m = 0 resp. contribute a term multiplied by 0
-                if (USE_COM) {
+                if (USE_COM && TGNH_V2_ABLATE != 1) {
                     // calcCOMVelocities (:86-105): P = sum m v over the residue, V = P / M
                     const V3<float> pm = v3(mul2(q0.x, q0.y, vn.x), mul2(q0.x, q0.y, vn.y), mul2(q0.x, q0.y, vn.z));
                     const V3<float> P = residue_sum(pm, lane, offFirst, offLast, maxRes, bfly);
@@ -404,8 +427,12 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                     }
                 } else
                     keRel = mul2(q0.x, q0.y, dot3(vn));
+#if TGNH_V2_ABLATE == 1            // measurement build: no residue sums, no pair term
+                const float keD = 0.f;
+#else
                 const V3<float> vjn = v3(__shfl_sync(0xffffffffu, vn.x, pl), __shfl_sync(0xffffffffu, vn.y, pl), __shfl_sync(0xffffffffu, vn.z, pl));
                 const float keD = role == ROLE_DRUDE ? mul2(q1.x, q1.y, dot3(vjn - vn)) : 0.f;   // mu |rel|^2 (:185)
+#endif
                 // m_d |r_d|^2 + m_p |r_p|^2 - mu |rel|^2 = (m_d + m_p) |cm|^2 (:184; the identity holds in any frame)
                 const float ke = keRel - keD;
                 accDrude += keD;
@@ -459,7 +486,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     __threadfence();
     // last CTA: warp g sums column g of the partials over all CTAs in a fixed order
     double* out = a.useLocalKE ? a.chain.ke2Local : a.chain.ke2;
-    for (int g = warp; g < T; g += V2_NCONS + 1) {
+    for (int g = warp; g < T; g += V2_NCONS + V2_NPROD) {
         double x = 0.0;
         for (int b = lane; b < (int)gridDim.x; b += 32) x += __ldcg(a.partials + (size_t)b * T + g);
 #pragma unroll

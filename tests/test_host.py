@@ -240,7 +240,7 @@ def test_descriptors_say_which_particles_are_interchangeable():
 # ---- the warp-chunk plan (csrc/tgnh_v2.cuh): chunks, species bytes, species table ----------------------------------------------------------
 def _assert_chunk_invariants(s, cs, spec, table, nspec, maxres):
     n = s.num_particles
-    assert cs[0] == 0 and cs[-1] == n and (len(cs) - 1) % 15 == 0 and np.all(np.diff(cs) >= 0) and np.diff(cs).max() <= 32
+    assert cs[0] == 0 and cs[-1] == n and (len(cs) - 1) % capi.lib().tgnh_chunks_per_tile() == 0 and np.all(np.diff(cs) >= 0) and np.diff(cs).max() <= 32
     res = np.asarray(s.res_id)
     starts = np.unique(cs[cs < n])
     assert np.all(res[starts[1:]] != res[starts[1:] - 1])                       # every chunk starts a residue ...
