@@ -49,8 +49,9 @@ WORKLOADS = {
     "c4-wall": "C4 with the frozen-spring pair forces of SURVEY.md 8d: every Drude pair hits the hard wall on every step "
                "(hard-wall stress case)",
     "c5": "C5 synthetic 200M-particle Drude system sharded over the ranks, G=4",
-    "c1": "C1 NaCl 1M box shape, N=2500, G=2", "c2": "C2 SWM4-NDP 10k waters, N=50000, G=1",
-    "c3": "C3 [BMIM][BF4]-like 1000 ion pairs, N=45000, G=3",
+    "c1": "C1 NaCl 1M box shape, N=2500, G=2, equilibrated start", "c2": "C2 SWM4-NDP 10k waters, N=50000, G=1, equilibrated start",
+    "c1-hot": "C1 from round 1's unequilibrated state", "c2-hot": "C2 from round 1's unequilibrated state", "c3-hot": "C3 from round 1's unequilibrated state",
+    "c3": "C3 [BMIM][BF4]-like 1000 ion pairs, N=45000, G=3, equilibrated start",
 }
 
 
@@ -106,12 +107,16 @@ def make_system(workload, rank, world):
     if workload == "c5":
         per = C5_MOLECULES // world
         return synth.water_box(per, 4, first_molecule=rank * per, box_molecules=C5_MOLECULES, **C4_STATE["c4"])
-    if workload == "c1":
-        return synth.nacl_box()
-    if workload == "c2":
-        return synth.swm4_box(10000)
-    if workload == "c3":
-        return synth.ionic_liquid(1000)
+    # C1-C3: like C4 from an equilibrated dual-thermostat state (thermostats hold their targets, the chain runs its short-polynomial
+    # path); "-hot" = round 1's state (independent 300 K velocities on the Drude particles: the Drude thermostat is far from its
+    # 1 K target for the whole run and the chain takes its full-range exp path every step)
+    small = {} if workload.endswith("-hot") else C4_STATE["c4"]
+    if workload in ("c1", "c1-hot"):
+        return synth.nacl_box(**small)
+    if workload in ("c2", "c2-hot"):
+        return synth.swm4_box(10000, **small)
+    if workload in ("c3", "c3-hot"):
+        return synth.ionic_liquid(1000, **small)
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -277,6 +282,7 @@ def run_ours(args):
     value = total_particles * args.steps / (ms * 1e-3)
     generation = h.kernel_generation
     lazy = h.lazy_second_kick
+    rpl = h.residue_per_lane
 
     # ---- end to end through the C-ABI with HOST buffers: every step copies velm/posq/force in from pinned
     #      memory, runs one step, and copies velm/posq + the 2*KE vector back (tgnh_step_host) ----
@@ -368,6 +374,7 @@ def run_ours(args):
                        "step_achieved_gbs": ALG_BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9,
                        "step_frac_of_peak": ALG_BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9 / peak,
                        "lazy_second_kick": bool(lazy),
+                       "residue_per_lane": int(rpl),
                        "step_bytes_moved_per_particle": moved,
                        "step_frac_of_peak_on_bytes_moved": moved * n * args.steps / (ms * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -459,7 +466,7 @@ def timed_steps(torch, h, ptrs, steps, stream, barrier, warmup=3):
 def small_systems_leg(torch, capi, dev, local, stream, barrier):
     """C1-C3 (BASELINE.json configs[0..2]): launch- and chain-latency bound; microseconds and launches per step."""
     out = {}
-    for w in ("c1", "c2", "c3"):
+    for w in ("c1", "c2", "c3", "c1-hot", "c2-hot", "c3-hot"):
         system = make_system(w, 0, 1)
         padded, _, bufs = device_buffers(torch, system, dev)
         h = capi.Handle(system, padded=padded, device=local)

@@ -97,7 +97,9 @@ typedef struct {
     const int32_t* pair_drude;       /* [P] DrudeForce::getParticleParameters particle  */
     const int32_t* pair_parent;      /* [P] DrudeForce::getParticleParameters particle1 */
     const int32_t* particle_temp_group; /* [N] */
-    const int32_t* particle_res_id;  /* [N]; each residue must be a contiguous index range (the reference assumes it, drudeTGNH.cu:86-101) */
+    const int32_t* particle_res_id;  /* [N]; with use_com_temp_group each residue must be a contiguous index range (the reference assumes it,
+                                        drudeTGNH.cu:86-101) that contains its Drude pairs; without it the reference never reads the residues
+                                        (:87-108) and neither does this library: any ids are accepted */
     const int32_t* constraint_p;     /* [C] */
     const int32_t* constraint_p1;    /* [C] */
     /* sharding: NULL = single GPU.  With a communicator the tables above describe this rank's molecule-aligned
@@ -200,6 +202,11 @@ int tgnh_kernel_generation(const tgnh_handle* h);
  * reduces the kinetic energies: 28 instead of 44 bytes per particle; bit-identical results).  Warp-chunk kernels only, not for
  * systems small enough to run the chain in the reducing launch; environment TGNH_LAZY_KICK=0 at tgnh_create switches it off. */
 int tgnh_lazy_second_kick(const tgnh_handle* h);
+/* k > 0 when the handle's reducing launches (second half, kinetic-energy reduction) run in the residue-per-lane form: every
+ * residue of the system has k particles (2..8) and lies in one temperature group, the COM temperature group is on, warp-chunk
+ * kernels.  A lane then owns a whole residue (no shuffles, ~3 times fewer instructions per particle).  0 otherwise; environment
+ * TGNH_RPL=0 at tgnh_create switches it off, TGNH_RPL=1 restricts it to the launches that store no velocities. */
+int tgnh_residue_per_lane(const tgnh_handle* h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t tgnh_launch_count(const tgnh_handle* h);
 /* Per-launch device timing: while enabled every streaming launch is bracketed by CUDA events on its stream.

@@ -24,7 +24,7 @@ SYMBOLS = [
     "tgnh_thermostat", "tgnh_half2", "tgnh_flush",
     "tgnh_step", "tgnh_step_host", "tgnh_step_host2", "tgnh_set_posq_correction", "tgnh_invalidate", "tgnh_num_thermostats", "tgnh_num_nh_chains", "tgnh_get_kinetic_energies",
     "tgnh_kinetic_energy", "tgnh_compute_kinetic_energies", "tgnh_get_chain_state", "tgnh_set_chain_state",
-    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_get_exchange_timing", "tgnh_plan_tiles", "tgnh_plan_descriptors", "tgnh_plan_chunks", "tgnh_kernel_generation", "tgnh_chunks_per_tile", "tgnh_lazy_second_kick", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
+    "tgnh_get_vscale", "tgnh_get_thermostat_params", "tgnh_launch_count", "tgnh_exchange_kind", "tgnh_get_exchange_timing", "tgnh_plan_tiles", "tgnh_plan_descriptors", "tgnh_plan_chunks", "tgnh_kernel_generation", "tgnh_residue_per_lane", "tgnh_chunks_per_tile", "tgnh_lazy_second_kick", "tgnh_set_profiling", "tgnh_get_profile", "tgnh_comm_get_unique_id",
     "tgnh_comm_create", "tgnh_comm_destroy",
 ]
 
@@ -94,6 +94,7 @@ def lib():
         L.tgnh_plan_chunks.argtypes = [C.POINTER(Params), ip32, C.c_int32, ip32, C.POINTER(C.c_uint8), C.POINTER(C.c_float), ip32, ip32]
         L.tgnh_kernel_generation.argtypes = [vp]
         L.tgnh_lazy_second_kick.argtypes = [vp]
+        L.tgnh_residue_per_lane.argtypes = [vp]
         L.tgnh_set_profiling.argtypes = [vp, C.c_int]
         L.tgnh_get_profile.argtypes = [vp, dp, C.POINTER(C.c_int64)]
         L.tgnh_comm_get_unique_id.argtypes = [vp]
@@ -319,6 +320,11 @@ class Handle:
     def kernel_generation(self):
         """2 = the two halves run through the warp-chunk kernels (tgnh_v2.cuh), 1 = first-generation kernels"""
         return lib().tgnh_kernel_generation(self.h)
+
+    @property
+    def residue_per_lane(self):
+        """k > 0: the reducing launches take a whole k-particle residue per lane (tgnh.h: tgnh_residue_per_lane)"""
+        return lib().tgnh_residue_per_lane(self.h)
 
     @property
     def lazy_second_kick(self):

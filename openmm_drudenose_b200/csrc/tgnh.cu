@@ -161,6 +161,7 @@ struct tgnh_handle {
     int* dChunkStart = nullptr;
     float4* dSpecTable = nullptr;
     int numTiles2 = 0, maxRes = 1, numSpecies = 0, butterfly = 0;
+    int rpl = 0, rplMode = 2;     // residue-per-lane reduction: residue size (0 = off); TGNH_RPL = 0 off, 1 only the launches that store nothing, 2 all reducing launches
     int gridA2v = 0, gridB2v = 0, gridKE2v = 0, gridS2v = 0, smemA2v = 0, smemB2v = 0, smemKE2v = 0, smemS2v = 0;
     bool lazyKick = true;         // TGNH_LAZY_KICK=0 at tgnh_create switches the lazy second kick of tgnh_step off (tests, measurements)
     bool lazyNow = false;         // set by tgnh_step around the launches that leave / find the second half kick pending (StreamArgs::lazyKick)
@@ -409,6 +410,7 @@ struct HostPlan {
     std::vector<unsigned char> spec;
     std::vector<float> specTable;
     int maxRes = 1, numTiles2 = 0, numSpecies = 0, butterfly = 0;
+    int uniformRes = 0;           // every residue has this many particles (2..8), else 0
 };
 
 // Chunks, species bytes and the species table of the warp-chunk kernels.  Needs the legacy plan's resFirst/resLast/partner/role.
@@ -478,11 +480,52 @@ static void build_plan_v2(const tgnh_params* p, HostPlan& hp) {
         bool same = (k & (k - 1)) == 0 && k <= 32;
         for (int r = 0; r < R && same; r++) same = hp.resLast[r] - hp.resFirst[r] + 1 == k;
         if (same) hp.butterfly = k;
+        // residues of one size (any size up to 8): the reducing kernels may take a whole residue per lane (tgnh_v2.cuh)
+        bool one = k >= 2 && k <= 8;
+        for (int r = 0; r < R && one; r++) one = hp.resLast[r] - hp.resFirst[r] + 1 == k;
+        if (one && k % 2 == 0) {
+            // even sizes: the lanes walk their residue in rotated order and keep ONE Drude pair in registers (tgnh_v2.cuh: rpl_residue)
+            std::vector<unsigned char> pairs(R, 0);
+            for (int i = 0; i < N && one; i++)
+                if (hp.role[i] == ROLE_DRUDE && ++pairs[p->particle_res_id[i]] > 1) one = false;
+        }
+        hp.uniformRes = one ? k : 0;
     }
     hp.v2 = true;
 }
 
+static int build_plan_impl(const tgnh_params* p, HostPlan& hp);
+
+// Without the COM temperature group the reference never looks at the residues: calcCOMVelocities leaves every centre-of-mass
+// velocity at zero (drudeTGNH.cu:87-108) and residue masses only enter the COM group's bookkeeping
+// (CudaDrudeTGNHKernels.cpp:186-212).  Here residues also decide where tiles and warp-chunks may be cut, which is why they must be
+// contiguous and contain their Drude pairs; a caller whose residue ids do not satisfy that (non-contiguous molecules, a pair
+// across two residues) is served by residues of our own when the COM group is off: the particle ranges spanned by
+// overlapping Drude pairs, every other particle alone.
 static int build_plan(const tgnh_params* p, HostPlan& hp) {
+    if (p->use_com_temp_group) return build_plan_impl(p, hp);
+    const int N = p->num_particles;
+    std::vector<int> glued(N + 2, 0);                   // glued[i] > 0: particle i stays with particle i - 1
+    for (int k = 0; k < p->num_pairs; k++) {
+        const int d = p->pair_drude[k], q = p->pair_parent[k];
+        if (d < 0 || d >= N || q < 0 || q >= N) continue;            // reported by build_plan_impl
+        const int a = d < q ? d : q, b = d < q ? q : d;
+        glued[a + 1]++; glued[b + 1]--;
+    }
+    std::vector<int> resId(N);
+    int r = -1, open = 0;
+    for (int i = 0; i < N; i++) {
+        open += glued[i];
+        if (i == 0 || open == 0) r++;
+        resId[i] = r;
+    }
+    tgnh_params q = *p;
+    q.particle_res_id = resId.data();
+    q.num_residues = r + 1;
+    return build_plan_impl(&q, hp);
+}
+
+static int build_plan_impl(const tgnh_params* p, HostPlan& hp) {
     const int N = p->num_particles, P = p->num_pairs, R = p->num_residues, G = p->num_temp_groups;
     const int T = G + 2;
     std::vector<int>&resFirst = hp.resFirst, &resLast = hp.resLast, &partner = hp.partner;
@@ -822,6 +865,9 @@ extern "C" int tgnh_create(const tgnh_params* p, tgnh_handle** out) {
         h->lazyKick = !(lz && atoi(lz) == 0);
         if (h->v2) {
             h->numTiles2 = hp.numTiles2; h->maxRes = hp.maxRes; h->numSpecies = hp.numSpecies; h->butterfly = hp.butterfly;
+            const char* rp = getenv("TGNH_RPL");
+            h->rplMode = rp ? atoi(rp) : 2;
+            h->rpl = (h->rplMode > 0 && h->useCOM && uniform) ? hp.uniformRes : 0;
             h->hChunkStart = hp.chunkStart;
             if (!dmalloc((void**)&h->dSpec, hp.spec.size()) || !dmalloc((void**)&h->dChunkStart, hp.chunkStart.size() * 4) ||
                 !dmalloc((void**)&h->dSpecTable, hp.specTable.size() * 4))
@@ -936,6 +982,7 @@ extern "C" int tgnh_plan_chunks(const tgnh_params* p, int32_t* chunk_start, int3
 
 extern "C" int tgnh_chunks_per_tile(void) { return V2_NCONS; }
 extern "C" int tgnh_kernel_generation(const tgnh_handle* h) { return h ? (h->v2 ? 2 : 1) : 0; }
+extern "C" int tgnh_residue_per_lane(const tgnh_handle* h) { return h && h->v2 && !h->fuseChain ? h->rpl : 0; }
 extern "C" int tgnh_lazy_second_kick(const tgnh_handle* h) { return h && h->lazyKick && h->v2 && !h->fuseChain && h->uniformGroups ? 1 : 0; }
 
 extern "C" void tgnh_destroy(tgnh_handle* h) {
@@ -1062,6 +1109,7 @@ static int launch_stream(tgnh_handle* h, cudaStream_t s, int kind, void* velm, v
     if (kind2 >= 0) {
         a.spec = h->dSpec; a.chunkStart = h->dChunkStart; a.specTable = h->dSpecTable; a.maxRes = h->maxRes; a.butterfly = h->butterfly; a.tableRows = h->numSpecies + 1;
         a.numTiles = h->numTiles2;
+        a.resPerLane = (!fused && (kind2 == V2_KE || (kind2 == V2_B && (h->rplMode >= 2 || a.lazyKick)))) ? h->rpl : 0;
         const int grid2 = kind2 == V2_A ? h->gridA2v : kind2 == V2_B ? h->gridB2v : kind2 == V2_S ? h->gridS2v : h->gridKE2v;
         const int smem2 = kind2 == V2_A ? h->smemA2v : kind2 == V2_B ? h->smemB2v : kind2 == V2_S ? h->smemS2v : h->smemKE2v;
         if (fused) CUDA_TRY(launch_pdl(pick_v2_fused(kind2, h->ffmt, h->useCOM), h->numTiles2, V2_THREADS, smem2, s, (const StreamArgs)a));
@@ -1249,6 +1297,7 @@ static int launch_v2_range(tgnh_handle* h, cudaStream_t s, int kind2, void* velm
     if (h->peers.world > 1 && reduces && last) a.peers.seq = ++h->reduceSeq; else a.peers.world = 0;
     a.spec = h->dSpec; a.chunkStart = h->dChunkStart; a.specTable = h->dSpecTable; a.maxRes = h->maxRes; a.butterfly = h->butterfly; a.tableRows = h->numSpecies + 1;
     a.numTiles = tileCount; a.tileBegin = tileBegin; a.accumulate = accumulate ? 1 : 0;
+    a.resPerLane = (kind2 == V2_KE || (kind2 == V2_B && h->rplMode >= 2)) ? h->rpl : 0;
     a.uniformGroups = h->uniformGroups ? 1 : 0;
     int grid = kind2 == V2_A ? h->gridA2v : kind2 == V2_B ? h->gridB2v : h->gridKE2v;
     if (grid > tileCount) grid = tileCount;

@@ -102,6 +102,7 @@ struct StreamArgs {
     int tableRows;
     int maxRes;                  // particles in the longest residue (<= 32)
     int butterfly;               // > 0: every residue has this many particles (a power of two) and every chunk is full or ends the system
+    int resPerLane;              // > 0: reducing launch in the residue-per-lane form (tgnh_v2.cuh): every residue has this many particles (2..8)
     int tileBegin;               // first tile of this launch (launches over a sub-range of the tiles: the chunked host-buffer path)
     int accumulate;              // add this launch's energy sums to what the previous launch over another sub-range left
     double* partials;         // [gridDim.x][T]

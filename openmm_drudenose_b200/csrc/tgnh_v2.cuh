@@ -53,7 +53,10 @@ enum { V2_A = 0, V2_B = 1, V2_KE = 2, V2_S = 3 };
 #define TGNH_V2_NS_A 3
 #endif
 #ifndef TGNH_V2_NS_B
-#define TGNH_V2_NS_B 4
+#define TGNH_V2_NS_B 6
+#endif
+#ifndef TGNH_V2_NS_KE
+#define TGNH_V2_NS_KE 6
 #endif
 #ifndef TGNH_V2_PF
 #define TGNH_V2_PF 4
@@ -95,7 +98,8 @@ struct V2Layout {
     static constexpr bool HAS_F = (KIND == V2_A || KIND == V2_B);
     static constexpr bool HAS_KE = (KIND == V2_B || KIND == V2_KE);
     static constexpr int FBYTES = FFMT == 1 ? 8 : 4;
-    static constexpr int NSTAGE = V2_NCONS > 15 ? (HAS_X ? 4 : 6) : (HAS_X ? TGNH_V2_NS_A : TGNH_V2_NS_B);   // ring depth
+    // ring depth; 6 stages of the second half with 8-byte forces would leave room for only one CTA per SM
+    static constexpr int NSTAGE = V2_NCONS > 15 ? (HAS_X ? 4 : 6) : (HAS_X ? TGNH_V2_NS_A : (HAS_F && FFMT == 1) ? 4 : HAS_F ? TGNH_V2_NS_B : TGNH_V2_NS_KE);
     static constexpr int OFF_V = 0;
     static constexpr int OFF_X = OFF_V + V2_TILE * 16;
     static constexpr int OFF_F = OFF_X + (HAS_X ? V2_TILE * 16 : 0);
@@ -103,7 +107,7 @@ struct V2Layout {
     static constexpr int OFF_HDR = OFF_S + V2_SW;            // uint2 per consumer warp: { first particle of the tile, chunk offset | chunk length << 16 }
     static constexpr int STAGE = OFF_HDR + ((8 * V2_NCONS + 15) & ~15);
     static constexpr int OFF_BAR = NSTAGE * STAGE;            // full[NS], empty[NS]
-    static constexpr int OFF_SCALE = OFF_BAR + 128;           // double[MAX_T] s^2 (unused), double[MAX_T] s - 1
+    static constexpr int OFF_SCALE = OFF_BAR + ((2 * NSTAGE * 8 + 127) & ~127);           // double[MAX_T] s^2 (unused), double[MAX_T] s - 1
     static constexpr int OFF_MISC = OFF_SCALE + MAX_T * 16;
     static constexpr int OFF_WARP = OFF_MISC + 16;            // double[T][32]
     static constexpr int OFF_KE = OFF_WARP + (HAS_KE ? MAX_T * 32 * 8 : 0);        // float[T][V2_TILE]: per-thread group sums
@@ -153,6 +157,72 @@ __device__ __forceinline__ V3<float> residue_sum(V3<float> p, int lane, int offF
     return v3(__shfl_sync(0xffffffffu, p.x, last), __shfl_sync(0xffffffffu, p.y, last), __shfl_sync(0xffffffffu, p.z, last));
 }
 
+// One residue of K consecutive particles of a stage, all of it in one lane (the residue-per-lane form of the reducing kinds, see
+// v2_body): half kick of every member (second half; HAS_F) and the residue's energy terms
+//   e = sum_i m_i |v_i|^2,  keC = |P|^2 / M with P = sum_i m_i v_i  (:86-105, :154),  keD = sum over its Drude particles of mu |rel|^2 (:185).
+//
+// Shared-memory banks.  Lane L reads particle K (32 slot + L) + m: for odd K the 16-byte velocity reads of a quarter-warp and the
+// 4-byte force reads of the warp fall into distinct banks by themselves; for even K they would collide (K = 4: four-way for
+// both; the first version of this path spent its time there: 9.8 M conflicts in 15.7 M wavefronts, mio_throttle the largest
+// stall).  So for even K the lanes walk the members of their residue in ROTATED order, lane L starting at member rpl_rot<K>(L):
+//   K = 2, 6:  ((L >> 2) + (L >> 4)) & 1        K = 4:  ((L >> 1) + (L >> 3)) & 3        K = 8:  (L ^ (L >> 2)) & 7
+// which makes both kinds of reads conflict-free.  The lanes of a warp are then at different members at the same time, so the
+// pair term is not formed where the Drude particle is met (divergent) but once after the loop, from the two velocities kept in
+// registers as they go by (even K: at most one Drude pair per residue, checked by tgnh_create).
+template <int K> __device__ __forceinline__ int rpl_rot(int lane) {
+    if (K == 2 || K == 6) return ((lane >> 2) + (lane >> 4)) & 1;
+    if (K == 4) return ((lane >> 1) + (lane >> 3)) & 3;
+    if (K == 8) return (lane ^ (lane >> 2)) & 7;
+    return 0;
+}
+struct RplOut { float e, keC, keD; int tg; };
+template <int K, int FFMT, bool HAS_F>
+__device__ __forceinline__ RplOut rpl_residue(const float4* __restrict__ sv, const unsigned char* __restrict__ sF, int fo, const unsigned char* __restrict__ sS,
+                                              const float4* __restrict__ stab, float fscale, int lane) {
+    constexpr bool ROT = (K % 2) == 0;
+    V3<float> P = v3(0.f, 0.f, 0.f);
+    RplOut o;
+    o.e = 0.f; o.keD = 0.f; o.tg = 0;
+    float invMhi = 0.f, invMlo = 0.f;
+    V3<float> vd = v3(0.f, 0.f, 0.f), vp = vd;          // ROT: kicked velocities of the residue's Drude particle and of its parent
+    int rowD = -1;
+    int mm = ROT ? rpl_rot<K>(lane) : 0;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const int m = ROT ? mm : j;                       // the member this lane handles now (a compile-time constant without rotation)
+        const int row = sS[m] * V2_ROW_F4;
+        const float4 r0 = stab[row];
+        const float4 v4 = sv[m];
+        V3<float> vn = xyz(v4);
+        if (HAS_F) vn = kicked(vn, fscale * v4.w, v2_force<FFMT>(sF, fo + m));
+        const uint32_t meta = __float_as_uint(r0.w);
+        const uint32_t role = v2_role(meta);
+        if (m == 0) { o.tg = v2_tg(meta); invMhi = r0.z; invMlo = stab[row + 1].z; }
+        const V3<float> pm = v3(mul2(r0.x, r0.y, vn.x), mul2(r0.x, r0.y, vn.y), mul2(r0.x, r0.y, vn.z));
+        P = P + pm;
+        o.e += pm.x * vn.x + pm.y * vn.y + pm.z * vn.z;
+        if (ROT) {
+            if (role == ROLE_DRUDE) { vd = vn; rowD = row; }
+            if (role == ROLE_PARENT) vp = vn;
+            mm = (mm + 1 == K) ? 0 : mm + 1;
+        } else if (role == ROLE_DRUDE) {
+            // mu |v_partner - v_d|^2 (:185); the partner's velocity kicked by the same fp32 operation that its own turn applies
+            const int jp = j + v2_partner(meta);
+            const float4 u4 = sv[jp];
+            V3<float> un = xyz(u4);
+            if (HAS_F) un = kicked(un, fscale * u4.w, v2_force<FFMT>(sF, fo + jp));
+            const float4 r1 = stab[row + 1];
+            o.keD += mul2(r1.x, r1.y, dot3(un - vn));
+        }
+    }
+    if (ROT && rowD >= 0) {
+        const float4 r1 = stab[rowD + 1];
+        o.keD = mul2(r1.x, r1.y, dot3(vp - vd));          // mu |v_parent - v_d|^2 (:185)
+    }
+    o.keC = mul2(invMhi, invMlo, dot3(P));          // |P|^2 / M  (:154)
+    return o;
+}
+
 // Body of the warp-chunk kernels.  Returns true in the one CTA that finished the grid-wide energy reduction (all threads of it).
 template <int KIND, int FFMT, bool USE_COM, bool HARDWALL>
 __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
@@ -178,8 +248,17 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
         return a.tileBegin + (a.reverse ? a.numTiles - 1 - t : t);
     };
 
+    // Residue-per-lane form of the reducing kinds (see the consumer loop): a tile is consumed by `rplSlots` warps instead of all
+    // of them, the groups of `rplSlots` warps take the tiles in turn.
+    constexpr bool CAN_RPL = USE_COM && (KIND == V2_B || KIND == V2_KE);
+    const int rpl = CAN_RPL ? a.resPerLane : 0;
+    const int rplSlots = rpl ? (V2_NCONS * (32 / rpl) + 31) / 32 : V2_NCONS;       // warps that share the residues of one tile
+    // (a stage must always be consumed by the same group — a group that met a stage whose previous tile another group has not even
+    // seen arrive would take that tile's pending phase for its own — so the number of groups divides the ring depth)
+    int rplGroups = V2_NCONS / rplSlots;
+    while (NS % rplGroups) rplGroups--;
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], V2_NCONS); }
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], rplSlots); }
         fence_mbar_init();
     }
     __syncthreads();                                    // the barriers exist: the producer may start streaming
@@ -296,6 +375,71 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
             } else cs = chunk_bounds(it);
             mbar_wait(&empty[it % NS], ((it / NS) - 1) & 1);
             issue(it, 3, cs);
+        }
+    } else if (CAN_RPL && rpl > 0) {
+        // RESIDUE PER LANE (reducing kinds; systems whose residues all have the same number k = 2..8 of particles, every residue in
+        // one temperature group: water boxes).  With one particle per lane the energies cost ~115 warp instructions per 32
+        // particles — the residue sums are 12 shuffles + 12 adds, the pair partner 3 shuffles, and wait / header / ring / arrive
+        // are paid per 32 particles — and the second half without stores and the plain reduction were bound by the issue slots
+        // (77 % busy at 60 % of the HBM peak, profiles/ncu_full_r2.md).  Here a lane owns a whole residue: its members are k
+        // consecutive particles of the stage, the momentum sum is three adds per member in registers, the pair partner is another
+        // read of the stage, nothing is shuffled, and the per-iteration overhead is paid once per 32 k particles.  A tile
+        // has at most V2_NCONS * (32 / k) residues = `rplSlots` warps' worth, so the consumer warps form groups of rplSlots that take
+        // the tiles in turn (group g: tiles g, g + groups, ...); warps beyond the last whole group have nothing to do.
+        // Same formulas as below: sum_i m_i |v_i|^2 - |P|^2 / M - sum_pairs mu |rel|^2 per group, |P|^2 / M for the COM group.
+        const int k = rpl;
+        const int grp = warp / rplSlots, slot = warp - grp * rplSlots;
+        const float fscale = (float)a.fscale;
+        const bool store = (KIND == V2_B) && !a.lazyKick;
+        if (grp < rplGroups) {
+            int stg = grp % NS;
+            uint32_t phase = (uint32_t)(grp / NS) & 1u;
+            for (int it = grp; it < myTiles; it += rplGroups) {
+                unsigned char* st = smem + stg * L::STAGE;
+                const float4* sv = reinterpret_cast<const float4*>(st + L::OFF_V);
+                const unsigned char* sF = st + L::OFF_F;
+                mbar_wait(&full[stg], phase);
+                const uint2 hdr = reinterpret_cast<const uint2*>(st + L::OFF_HDR)[V2_NCONS - 1];     // the last chunk ends the tile
+                const int start = (int)hdr.x, n = (int)((hdr.y & 0xffffu) + (hdr.y >> 16));
+                const int base = (slot * 32 + lane) * k;                  // this lane's residue: particles base .. base + k - 1 of the tile
+                if (store) {
+                    // the storing second half: the kicked velocities leave in particle order (coalesced 16-byte stores; a lane storing
+                    // the members of its own residue would write 16 bytes every 16 k: +9 us at 10 M particles), each formed by the
+                    // same fp32 operation on the same operands as in the energy terms below
+                    const int w0 = slot * 32 * k + lane;
+                    for (int c = 0; c < k; c++) {
+                        const int idx = w0 + 32 * c;
+                        if (idx < n) {
+                            const float4 v4 = sv[idx];
+                            if (v4.w != 0.f) st_global(gvelm + (unsigned int)(start + idx), pack4(kicked(xyz(v4), fscale * v4.w, v2_force<FFMT>(sF, (start & 3) + idx)), v4.w));
+                        }
+                    }
+                }
+                if (base < n) {
+                    const unsigned char* sS = st + L::OFF_S + (start & 15) + base;
+                    RplOut o;
+                    switch (k) {          // warp-uniform; the member loop is unrolled for each size: every address is base + immediate
+                        case 2: o = rpl_residue<2, FFMT, L::HAS_F>(sv + base, sF, (start & 3) + base, sS, stab, fscale, lane); break;
+                        case 3: o = rpl_residue<3, FFMT, L::HAS_F>(sv + base, sF, (start & 3) + base, sS, stab, fscale, lane); break;
+                        case 4: o = rpl_residue<4, FFMT, L::HAS_F>(sv + base, sF, (start & 3) + base, sS, stab, fscale, lane); break;
+                        case 5: o = rpl_residue<5, FFMT, L::HAS_F>(sv + base, sF, (start & 3) + base, sS, stab, fscale, lane); break;
+                        case 6: o = rpl_residue<6, FFMT, L::HAS_F>(sv + base, sF, (start & 3) + base, sS, stab, fscale, lane); break;
+                        case 7: o = rpl_residue<7, FFMT, L::HAS_F>(sv + base, sF, (start & 3) + base, sS, stab, fscale, lane); break;
+                        default: o = rpl_residue<8, FFMT, L::HAS_F>(sv + base, sF, (start & 3) + base, sS, stab, fscale, lane); break;
+                    }
+                    accDrude += o.keD;
+                    accCOM += o.keC;
+                    if (o.tg != curTg) {
+                        if (curTg >= 0) { ske[curTg * V2_TILE + tid] += accT; accT = 0.f; }
+                        curTg = o.tg;
+                    }
+                    accT += (o.e - o.keC) - o.keD;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stg]);
+                stg += rplGroups;
+                while (stg >= NS) { stg -= NS; phase ^= 1u; }
+            }
         }
     } else {
         F2 eCOM; eCOM.hi = seps[G].x; eCOM.lo = seps[G].y;

@@ -18,5 +18,5 @@ def timed(n=200):
     return e0.elapsed_time(e1) / n * 1e3
 t = [round(timed(), 2) for _ in range(3)]
 h.set_profiling(True); h.step(*st.ptrs, nsteps=50, stream=sp); torch.cuda.synchronize()
-print(which, "V2=%s FUSE=%s" % (os.environ.get("TGNH_V2"), os.environ.get("TGNH_FUSE_CHAIN")), "gen", h.kernel_generation(), "N", s.num_particles,
+print(which, "V2=%s FUSE=%s" % (os.environ.get("TGNH_V2"), os.environ.get("TGNH_FUSE_CHAIN")), "gen", h.kernel_generation, "N", s.num_particles,
       "T", len(h.vscale()), "us/step", t, {k: (round(v[0] / max(v[1], 1) * 1e3, 2), v[1]) for k, v in h.profile().items()})

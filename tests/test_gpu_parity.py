@@ -33,7 +33,15 @@ def _systems():
         "ionic_C3": lambda: synth.ionic_liquid(1000, **kw),
         "ragged_tiles": lambda: synth.build([synth.WATER4, synth.SOD, synth.SWM4], np.arange(3001) % 3, np.arange(3001) % 2, 2, **kw),
         "tiny": lambda: synth.water_box(3, 1, **kw),
+        "scattered_residues_nocom": lambda: _scattered(synth.water_box(2000, 2, use_com_temp_group=False, **kw)),
     }
+
+
+def _scattered(s):
+    """Residue ids that are neither contiguous nor aligned with the Drude pairs: legal without the COM temperature group, where the
+    reference never reads them (drudeTGNH.cu:87-108)."""
+    s.res_id = np.random.default_rng(11).integers(0, s.num_residues, s.num_particles).astype(np.int32)
+    return s
 
 
 SYSTEMS = _systems()
@@ -163,6 +171,77 @@ def test_lazy_second_kick_is_bit_identical(cuda, fmt, monkeypatch):
     # and the lazy run launched the same number of kernels
     assert ha.launch_count == hb.launch_count
     ha.close(); hb.close()
+
+
+def _uniform_box(k, molecules, groups=3, **kw):
+    """Boxes whose residues all have k particles (one Drude pair each, the rest ordinary particles, k = 5 with SWM4's massless site)."""
+    if k == 5:
+        t = synth.SWM4
+    else:
+        masses = np.array([15.6, 0.4] + [1.0 + 0.5 * j for j in range(k - 2)])
+        off = np.zeros((k, 3)); off[2:, 0] = 0.05 * np.arange(1, k - 1)
+        t = synth.Template(f"uniform{k}", masses, np.array([[1, 0]], np.int32), off)
+    return synth.build([t], np.zeros(molecules, np.int32), np.arange(molecules) % groups, groups, quantize_masses=True, **kw)
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 7, 8])
+def test_residue_per_lane_reduction(cuda, k, monkeypatch):
+    """Systems whose residues all have k particles reduce their kinetic energies with a whole residue per lane (tgnh_v2.cuh:
+    rpl_residue; rotated member order for even k).  Same sums as the one-particle-per-lane form (TGNH_RPL=0) and as the oracle
+    within 1e-6, for the plain reduction, the storing second half and the second half that stores nothing; the storing and the lazy
+    run stay bit-identical to each other; the last tile is ragged (the molecule count is no multiple of a tile)."""
+    s = _uniform_box(k, 70000 // k + 1011)
+    assert s.num_particles > 148 * 448                       # more tiles than SMs: no fused chain launch
+    a, b, c = DeviceState(s, cuda), DeviceState(s, cuda), DeviceState(s, cuda)
+    ha = capi.Handle(s)
+    monkeypatch.setenv("TGNH_RPL", "0")
+    hb = capi.Handle(s)
+    monkeypatch.delenv("TGNH_RPL")
+    monkeypatch.setenv("TGNH_LAZY_KICK", "0")
+    hc = capi.Handle(s)
+    monkeypatch.delenv("TGNH_LAZY_KICK")
+    assert ha.residue_per_lane == k and hb.residue_per_lane == 0 and hc.residue_per_lane == k
+    o = O.Oracle(s, O.TG, constraints=s.constraints)
+    nkbt = o.thermostat_params()[1]
+    # plain reduction (V2_KE)
+    ref = o.compute_ke2(s.velocities.astype(np.float32).astype(np.float64))
+    ka, kb = ha.compute_kinetic_energies(a.velm.data_ptr()), hb.compute_kinetic_energies(b.velm.data_ptr())
+    assert ke_err(ka, ref, nkbt) < TOL_THERMO and ke_err(kb, ref, nkbt) < TOL_THERMO and ke_err(ka, kb, nkbt) < 2e-7
+    # 6 steps in one call (lazy second halves), against the plain form and against the storing run
+    ha.step(*a.ptrs, nsteps=6); hb.step(*b.ptrs, nsteps=6); hc.step(*c.ptrs, nsteps=6)
+    a.torch.cuda.synchronize()
+    assert a.torch.equal(a.velm, c.velm) and a.torch.equal(a.posq, c.posq)
+    assert np.array_equal(ha.kinetic_energies(), hc.kinetic_energies()) and np.array_equal(ha.vscale(), hc.vscale())
+    assert ke_err(ha.kinetic_energies(), hb.kinetic_energies(), nkbt) < 6 * 2e-7
+    assert rel_err(a.vel(), b.vel()) < 6 * 2e-7 and rel_err(a.pos(), b.pos()) < 6 * 2e-7
+    # one step from the oracle's state (hard-wall hits make free-running fp32 and fp64 trajectories part company, DESIGN.md 6)
+    d = DeviceState(s, cuda)
+    hd = capi.Handle(s)
+    p, v, f = s.positions.copy(), s.velocities.copy(), s.forces.copy()
+    hd.step(*d.ptrs, nsteps=1)
+    o.step(p, v, f, 1)
+    assert rel_err(d.vel(), v) < TOL_STEP and rel_err(d.pos(), p) < TOL_STEP
+    assert ke_err(hd.kinetic_energies(), o.ke2, nkbt) < TOL_THERMO
+    for h in (ha, hb, hc, hd):
+        h.close()
+
+
+def test_residue_per_lane_needs_one_pair_per_even_residue(cuda):
+    """Even residue sizes keep ONE Drude pair in registers: a box of 4-particle residues with two pairs each runs the plain form."""
+    t = synth.Template("twopairs", np.array([12.0, 0.4, 14.0, 0.4]), np.array([[1, 0], [3, 2]], np.int32), np.zeros((4, 3)))
+    s = synth.build([t], np.zeros(20000, np.int32), np.arange(20000) % 2, 2, quantize_masses=True)
+    h = capi.Handle(s)
+    assert h.kernel_generation == 2 and h.residue_per_lane == 0
+    h.close()
+    t3 = synth.Template("twopairs5", np.array([12.0, 0.4, 14.0, 0.4, 1.0]), np.array([[1, 0], [3, 2]], np.int32), np.zeros((5, 3)))
+    s = synth.build([t3], np.zeros(20000, np.int32), np.arange(20000) % 2, 2, quantize_masses=True)
+    st = DeviceState(s, cuda)
+    h = capi.Handle(s)
+    assert h.residue_per_lane == 5                        # odd sizes re-read the partner: any number of pairs
+    o = O.Oracle(s, O.TG)
+    ref = o.compute_ke2(s.velocities.astype(np.float32).astype(np.float64))
+    assert ke_err(h.compute_kinetic_energies(st.velm.data_ptr()), ref, o.thermostat_params()[1]) < TOL_THERMO
+    h.close()
 
 
 def test_hard_wall(cuda):

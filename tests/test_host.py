@@ -224,6 +224,27 @@ def test_plan_reports_the_reference_table_errors():
     assert err(bad_group).code == capi.ERR_INVALID_ARGUMENT
 
 
+def test_residues_are_ignored_without_the_com_group():
+    """Without the COM temperature group the reference never reads the residue table (drudeTGNH.cu:87-108): scattered residue ids
+    and Drude pairs across residues are accepted and planned over residues of the library's own (the ranges spanned by
+    overlapping pairs); with the COM group the same table is refused."""
+    s = synth.water_box(700, 2, use_com_temp_group=False)
+    ref_tiles, _, _ = capi.plan_tiles(s)
+    s.res_id = np.random.default_rng(3).integers(0, s.num_residues, s.num_particles).astype(np.int32)
+    ts, nbig, uniform = capi.plan_tiles(s)
+    assert nbig == 0 and uniform and ts[0] == 0 and ts[-1] == s.num_particles and np.all(np.diff(ts) <= 512)
+    tile_of = np.searchsorted(ts, np.arange(s.num_particles), side="right") - 1
+    assert np.all(tile_of[s.pair_drude] == tile_of[s.pair_parent])
+    cs, spec, table, nspecies, max_res = capi.plan_chunks(s)
+    assert max_res == 2 and nspecies == 6                        # parent, Drude, ordinary particle x 2 temperature groups
+    chunk_of = np.searchsorted(cs, np.arange(s.num_particles), side="right") - 1
+    assert np.all(chunk_of[s.pair_drude] == chunk_of[s.pair_parent]) and np.all(np.diff(cs) <= 32)
+    s.use_com_temp_group = True
+    with pytest.raises(capi.TgnhError) as e:
+        capi.plan_tiles(s)
+    assert "not a contiguous particle range" in str(e.value)
+
+
 def test_descriptors_say_which_particles_are_interchangeable():
     """What a CudaForceInfo built on tgnh_plan_descriptors would tell OpenMM's atom reordering: molecules of the same kind and
     temperature group have equal words particle by particle, molecules in different groups do not."""
