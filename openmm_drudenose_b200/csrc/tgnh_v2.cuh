@@ -411,7 +411,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                         const int idx = w0 + 32 * c;
                         if (idx < n) {
                             const float4 v4 = sv[idx];
-                            if (v4.w != 0.f) st_global(gvelm + (unsigned int)(start + idx), pack4(kicked(xyz(v4), fscale * v4.w, v2_force<FFMT>(sF, (start & 3) + idx)), v4.w));
+                            st_global(gvelm + (unsigned int)(start + idx), v4.w != 0.f ? pack4(kicked(xyz(v4), fscale * v4.w, v2_force<FFMT>(sF, (start & 3) + idx)), v4.w) : v4);
                         }
                     }
                 }
@@ -502,7 +502,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                 F2 eT; eT.hi = e2.x; eT.lo = e2.y;
                 V3<float> vn = scaled_velocity2(v, eT, v - V, eCOM, V, scoef[tg] * q1.w, rel);
                 if (KIND == V2_S) {
-                    if (active && massive) st_global(gvelm + gidx, pack4(vn, w));
+                    if (active) st_global(gvelm + gidx, massive ? pack4(vn, w) : v4);      // (massless: see the first half's stores)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[stg]);
                     continue;
@@ -530,20 +530,25 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
                         }
                     }
                 }
-                if (active && massive) {
+                if (active) {
+                    // A massless particle (virtual site: w = 0) is not integrated (:258, :318, :441); its slots get the bits they held
+                    // back instead of being skipped, so that every 32-byte sector the warp touches is written whole (a box of 5-site
+                    // SWM4 waters skips every fifth slot otherwise and its first half took 182 us per 10 M particles, against 114 us
+                    // for the 4-site box)
+                    const float4 vout = massive ? pack4(vn, w) : v4;
 #if TGNH_V2_A_STORE_KEEP_MB > 0
                     // experiment: only the velm this launch writes last can still be in L2 when the next launch reads it
-                    st_global_hint(gvelm + gidx, pack4(vn, w), it >= storeKeepFrom ? polStoreKeep : polOnce);
+                    st_global_hint(gvelm + gidx, vout, it >= storeKeepFrom ? polStoreKeep : polOnce);
 #else
-                    st_global(gvelm + gidx, pack4(vn, w));
+                    st_global(gvelm + gidx, vout);
 #endif
-                    st_stream(static_cast<float4*>(a.posq) + gidx, make_float4(xn.x, xn.y, xn.z, x4.w));
+                    st_stream(static_cast<float4*>(a.posq) + gidx, massive ? make_float4(xn.x, xn.y, xn.z, x4.w) : x4);
                 }
             } else {
                 // half kick (integrateDrudeTGNHVelocities, :314-364; V2_KE: F = 0, nothing stored), then the energies of
                 // what was stored
                 const V3<float> vn = kicked(v, fw, F);
-                if (KIND == V2_B && !a.lazyKick && active && massive) st_global(gvelm + gidx, pack4(vn, w));
+                if (KIND == V2_B && !a.lazyKick && active) st_global(gvelm + gidx, massive ? pack4(vn, w) : v4);
 #ifndef TGNH_V2_ABLATE
 #define TGNH_V2_ABLATE 0
 #endif
