@@ -593,13 +593,13 @@ __device__ __forceinline__ bool stream_body(const StreamArgs& a) {
         R3 r;                                         // ... relative to the residue (after scaling / kick)
         if (KIND == KIND_K) {
             vn = kicked(v, fw, F);                     // drudeTGNH.cu:314-364
-            if (active && massive) st_global(gvelm + start + tid, pack4(vn, w));
+            if (active) st_global(gvelm + start + tid, massive ? pack4(vn, w) : v4);
             r = vn;
         } else if (LAB) {
             // kick (drudeTGNH.cu:314-364; KIND_KU: F = 0, nothing stored); kinetic energies in the lab frame, the residues'
             // M |V|^2 is removed below
             vn = kicked(v, fw, F);
-            if (KIND == KIND_BU && active && massive) st_global(gvelm + start + tid, pack4(vn, w));
+            if (KIND == KIND_BU && active) st_global(gvelm + start + tid, massive ? pack4(vn, w) : v4);
             const R3 vjn = kicked(vj, fwj, Fj);
             rel = vjn - vn;
             r = vn;
@@ -635,7 +635,7 @@ __device__ __forceinline__ bool stream_body(const StreamArgs& a) {
         } else if (KIND == KIND_B) {
             // integrateDrudeTGNHVelocities (drudeTGNH.cu:314-364), updatePosDelta = false
             vn = kicked(v, fw, F);
-            if (active && massive) st_global(gvelm + start + tid, pack4(vn, w));
+            if (active) st_global(gvelm + start + tid, massive ? pack4(vn, w) : v4);
             rel = axpy(fwj, Fj, axpy(-fw, F, rel));
             r = vn - V;
         } else {
@@ -688,7 +688,7 @@ __device__ __forceinline__ bool stream_body(const StreamArgs& a) {
         }
 
         if (KIND == KIND_KE || KIND == KIND_S) {
-            if (doScale && active && massive) st_global(gvelm + start + tid, pack4(vn, w));
+            if (doScale && active) st_global(gvelm + start + tid, massive ? pack4(vn, w) : v4);
         } else if (KIND == KIND_A1) {
             // scaling + half kick; posDelta = dt * v for OpenMM's constraint kernels (drudeTGNH.cu:322-324, 360-363)
             vn = kicked(vn, fw, F);
@@ -719,6 +719,11 @@ __device__ __forceinline__ bool stream_body(const StreamArgs& a) {
             if (massive) {
                 st_global(gvelm + start + tid, pack4(vn, w));
                 PosTile<PREC>::store(a, start + tid, xn, q);
+            } else if (PREC != 1) {
+                // a massless particle is not integrated; its slots get their own bits back so that whole sectors are written
+                // (tgnh_v2.cuh; not in the mixed layout, where re-splitting a position may move bits between posq and its correction)
+                st_global(gvelm + start + tid, v4);
+                PosTile<PREC>::store(a, start + tid, x, q);
             }
         } else if (KIND == KIND_A && active) {
             // half kick + drift (+ hard wall) (drudeTGNH.cu:314-364, 438-465, 474-573)
@@ -748,6 +753,11 @@ __device__ __forceinline__ bool stream_body(const StreamArgs& a) {
             if (massive) {
                 st_global(gvelm + start + tid, pack4(vn, w));
                 PosTile<PREC>::store(a, start + tid, xn, q);
+            } else if (PREC != 1) {
+                // a massless particle is not integrated; its slots get their own bits back so that whole sectors are written
+                // (tgnh_v2.cuh; not in the mixed layout, where re-splitting a position may move bits between posq and its correction)
+                st_global(gvelm + start + tid, v4);
+                PosTile<PREC>::store(a, start + tid, x, q);
             }
         }
 

@@ -16,5 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file
 # the dominant kernel (first half) and the second-half kernel, full set
 ncu --set full --clock-control none --import-source on -k regex:tgnh_v2 -s 8 -c 2 -o gpurun_out/prof_$R \
     python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline --quick > gpurun_out/ncu_full_$R.log 2>&1
+# residue-per-lane reduction on / off, 10 M particles: 4-site box (C4's molecules) and 5-site SWM4 box (massless M site)
+{ for w in k4 k5 k4i; do for m in 0 2; do TGNH_RPL=$m python scripts/dev_rpl_probe.py $w 2>&1 | tail -1; done; done; } > gpurun_out/rpl_probe_$R.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit --format=csv > gpurun_out/gpu_$R.csv
 echo collected

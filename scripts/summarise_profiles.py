@@ -13,7 +13,7 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
 for name in (f"bench_{R}.json", f"bench_ref_{R}.json", f"bench_c4-wall_{R}.json", f"bench_c4-hot_{R}.json", f"bench_gen1_{R}.json", f"bench_c1_{R}.json", f"bench_c2_{R}.json", f"bench_c3_{R}.json",
-             f"launches_{R}.csv", f"gpu_{R}.csv"):
+             f"launches_{R}.csv", f"gpu_{R}.csv", f"rpl_probe_{R}.log"):
     if os.path.exists(os.path.join(G, name)):
         shutil.copy(os.path.join(G, name), os.path.join(P, name))
 
