@@ -224,7 +224,7 @@ __device__ __forceinline__ RplOut rpl_residue(const float4* __restrict__ sv, con
 }
 
 // Body of the warp-chunk kernels.  Returns true in the one CTA that finished the grid-wide energy reduction (all threads of it).
-template <int KIND, int FFMT, bool USE_COM, bool HARDWALL>
+template <int KIND, int FFMT, bool USE_COM, bool HARDWALL, bool RPL_OK = true>
 __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     using L = V2Layout<KIND, FFMT>;
     constexpr int NS = L::NSTAGE;
@@ -250,7 +250,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
 
     // Residue-per-lane form of the reducing kinds (see the consumer loop): a tile is consumed by `rplSlots` warps instead of all
     // of them, the groups of `rplSlots` warps take the tiles in turn.
-    constexpr bool CAN_RPL = USE_COM && (KIND == V2_B || KIND == V2_KE);
+    constexpr bool CAN_RPL = RPL_OK && USE_COM && (KIND == V2_B || KIND == V2_KE);      // (not compiled into the one-tile-per-CTA kernels of small systems)
     const int rpl = CAN_RPL ? a.resPerLane : 0;
     const int rplSlots = rpl ? (V2_NCONS * (32 / rpl) + 31) / 32 : V2_NCONS;       // warps that share the residues of one tile
     // (a stage must always be consumed by the same group — a group that met a stage whose previous tile another group has not even
@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(V2_THREADS, V2_CTAS) tgnh_v2_kernel(const __gr
 // update itself instead of a separate chain launch (see tgnh_stream_chain_kernel).
 template <int KIND, int FFMT, bool USE_COM>
 __global__ void __launch_bounds__(V2_THREADS, 1) tgnh_v2_chain_kernel(const __grid_constant__ StreamArgs a) {
-    if (!v2_body<KIND, FFMT, USE_COM, false>(a)) return;
+    if (!v2_body<KIND, FFMT, USE_COM, false, false>(a)) return;
     __syncthreads();                                   // the energy vector written by this CTA's warps
     if (threadIdx.x < 32) chain_phase(a.chain, a.fusedChainMode, threadIdx.x);
 }
