@@ -55,6 +55,21 @@ WORKLOADS = {
 }
 
 
+def workload_config(workload, world):
+    """The `config` object of the JSON line: what the workload IS, nothing measured and nothing about the implementation, so that
+    both arms (`--impl ours` / `--impl reference`) print the same object for the same command line.  Everything measured beside the
+    headline (C5 strong split, replicas, shard check, small systems, call patterns ...) goes to `details`."""
+    if workload in ("c4", "c4-wall", "c4-hot"):
+        per = (MOLECULES_OVERRIDE or C4_MOLECULES) * 4
+    elif workload == "c5":
+        per = (C5_MOLECULES // world) * 4
+    else:
+        per = make_system(workload, 0, 1).num_particles
+    return {"workload": WORKLOADS[workload], "particles_per_gpu": per, "total_particles": per * world,
+            "l2": "inputs larger than L2 (44 B of state and forces per particle against 126 MB of L2)" if per * 44 > 2 * 126e6
+                  else "inputs smaller than L2 (latency workload: the step is bound by launches and the serial chain, not by bytes)"}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -189,7 +204,7 @@ def run_reference(args):
         "impl": "reference", "metric": "TGNH step particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload]},
+        "config": workload_config(args.workload, max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -351,6 +366,8 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
+        cfg = workload_config(args.workload, world)
+        assert cfg["particles_per_gpu"] == n, (cfg, n)
         a_ms, a_cnt = prof["half1"]
         b_ms, b_cnt = prof["half2"]
         ach = ALG_BYTES_HALF1 * n / (a_ms / max(a_cnt, 1) * 1e-3) / 1e9 if a_cnt else None
@@ -363,20 +380,19 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "particles_per_gpu": n, "total_particles": total_particles,
-                       "parallelism": f"particle-range shards x{world}" if world > 1 else "single GPU",
-                       "host_numa_binding": None if world == 1 else f"rank 0 on node {numa_node}",
-                       "exchange": {0: "none", 1: "ncclAllReduce of double[T] per step", 2: "peer-mapped inboxes over NVLink (no collective launch)"}[exchange_kind],
-                       "kernels": "warp-chunk kernels (tgnh_v2.cuh)" if generation == 2 else "first-generation kernels (tgnh_kernels.cuh)",
-                       "l2": "inputs larger than L2 (>=440 MB working set per GPU vs 126 MB L2)",
-                       "spin_up": "0.5 s of device-to-device copies before the warm-up steps (clock ramp after the host-side set-up)",
-                       "accumulation": "fp32 state (OpenMM single-precision layouts), fp64 KE reductions and NH chain",
-                       "step_achieved_gbs": ALG_BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9,
-                       "step_frac_of_peak": ALG_BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9 / peak,
-                       "lazy_second_kick": bool(lazy),
-                       "residue_per_lane": int(rpl),
-                       "step_bytes_moved_per_particle": moved,
-                       "step_frac_of_peak_on_bytes_moved": moved * n * args.steps / (ms * 1e-3) / 1e9 / peak},
+            "config": cfg,
+            "details": {"parallelism": f"particle-range shards x{world}" if world > 1 else "single GPU",
+                        "host_numa_binding": None if world == 1 else f"rank 0 on node {numa_node}",
+                        "exchange": {0: "none", 1: "ncclAllReduce of double[T] per step", 2: "peer-mapped inboxes over NVLink (no collective launch)"}[exchange_kind],
+                        "kernels": "warp-chunk kernels (tgnh_v2.cuh)" if generation == 2 else "first-generation kernels (tgnh_kernels.cuh)",
+                        "spin_up": "0.5 s of device-to-device copies before the warm-up steps (clock ramp after the host-side set-up)",
+                        "accumulation": "fp32 state (OpenMM single-precision layouts), fp64 KE reductions and NH chain",
+                        "step_achieved_gbs": ALG_BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9,
+                        "step_frac_of_peak": ALG_BYTES_STEP * n * args.steps / (ms * 1e-3) / 1e9 / peak,
+                        "lazy_second_kick": bool(lazy),
+                        "residue_per_lane": int(rpl),
+                        "step_bytes_moved_per_particle": moved,
+                        "step_frac_of_peak_on_bytes_moved": moved * n * args.steps / (ms * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "tgnh_step_host2 per step: pinned host velm/posq -> device in 8 pipelined particle ranges (the fixed synthetic forces are "
                             "uploaded once: TGNH_HOST_FORCES_UNCHANGED), 1 step, velm/posq/2KE back; H2D and D2H overlap on the two copy engines",
@@ -394,7 +410,7 @@ def run_ours(args):
                                  "(every launch starts on the tiles the previous one touched last); traffic = DRAM bytes per launch from ncu"},
             "ke2_last": [float(x) for x in ke2],
         }
-        out["config"].update(extra)
+        out["details"].update(extra)
         if world == 1 and args.workload == "c4" and not args.quick and not args.no_reference_cuda:
             # the reference's own CUDA kernels on the same system, same box (an extra measured baseline; never on the product path)
             try:

@@ -10,5 +10,5 @@ python - <<PY
 import json
 d=json.loads(open("gpurun_out/scale_n${N}_r2.json").read().strip().splitlines()[-1])
 print({k:d[k] for k in ("value","ms_per_step","n_gpus","gpu_launches")}); print(d["e2e"]["value"])
-c=d["config"]; print({k:c.get(k) for k in ("exchange","shard_check","c5_strong","replicas","exchange_timing_us","openmm_call_pattern_ms")})
+c=d.get("details", d["config"]); print({k:c.get(k) for k in ("exchange","shard_check","c5_strong","replicas","exchange_timing_us","openmm_call_pattern_ms")})
 PY

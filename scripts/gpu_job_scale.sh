@@ -7,5 +7,5 @@ python - <<PY
 import json
 d=json.loads(open("gpurun_out/scale_n${N}_r2.json").read().strip().splitlines()[-1])
 print({k:d[k] for k in ("value","ms_per_step","n_gpus","gpu_launches")}); print("e2e", d["e2e"]["value"])
-c=d["config"]; print(json.dumps({k:c.get(k) for k in ("exchange","shard_check","c5_strong","replicas","exchange_timing_us")}, indent=0))
+c=d.get("details", d["config"]); print(json.dumps({k:c.get(k) for k in ("exchange","shard_check","c5_strong","replicas","exchange_timing_us")}, indent=0))
 PY

@@ -89,6 +89,9 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+    # both arms print the same `config` object for the same command line (nothing measured, nothing about the implementation)
+    import bench
+    assert line["config"] == bench.workload_config("c4", 1) and line["config"]["total_particles"] == 10_000_000
 
 
 _WORKER = r"""
