@@ -73,6 +73,11 @@ constexpr int V2_NCONS = TGNH_V2_NCONS;       // consumer warps per CTA (the las
 constexpr int V2_NPROD = TGNH_V2_NPROD;       // producer warps (each refills every V2_NPROD-th tile)
 constexpr int V2_THREADS = (V2_NCONS + V2_NPROD) * 32;
 constexpr int V2_CTAS = V2_NCONS > 15 ? 1 : 2;   // resident CTAs per SM the kernels are compiled for
+#ifndef TGNH_V2_CTAS_RED
+#define TGNH_V2_CTAS_RED V2_CTAS
+#endif
+constexpr int V2_CTAS_RED = TGNH_V2_CTAS_RED;    // the same for the reducing kinds (second half, reduction): with a ring deeper than half an SM's
+                                                 // shared memory they run one CTA per SM and may use its whole register file
 constexpr int V2_TILE = V2_NCONS * 32;        // particles per tile, at most
 constexpr int V2_FW = V2_TILE + 8;            // 4-aligned window of force components that covers any tile
 constexpr int V2_SW = V2_TILE + 32;           // 16-aligned window of species bytes that covers any tile
@@ -652,7 +657,7 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
 }
 
 template <int KIND, int FFMT, bool USE_COM, bool HARDWALL>
-__global__ void __launch_bounds__(V2_THREADS, V2_CTAS) tgnh_v2_kernel(const __grid_constant__ StreamArgs a) {
+__global__ void __launch_bounds__(V2_THREADS, (KIND == V2_B || KIND == V2_KE) ? V2_CTAS_RED : V2_CTAS) tgnh_v2_kernel(const __grid_constant__ StreamArgs a) {
     v2_body<KIND, FFMT, USE_COM, HARDWALL>(a);
 }
 
