@@ -327,6 +327,11 @@ __device__ __forceinline__ bool v2_body(const StreamArgs& a) {
     // the producer's ~60 serial instructions per tile are on the critical path of the ring, and two producers that take every
     // other tile are worth 4.7 us of 66.
     constexpr int NPROD = L::HAS_X ? 1 : V2_NPROD;
+    // Every stage must have ONE producer (and one consumer group): a producer that polls a stage's `empty` barrier has then issued the
+    // stage's previous tile itself, so the barrier is at most one phase behind and the parity test is unambiguous.  Producers take
+    // every NPROD-th tile, so the ring depth has to be a multiple of NPROD (an odd depth with two producers refills stages that are
+    // still being read: measured).
+    static_assert(NS % NPROD == 0, "ring depth must be a multiple of the number of producer warps");
     const int preloaded = myTiles < NS ? myTiles : NS;
     if (producer && pidx > 0) pdl_wait();
     else if (producer) {
