@@ -94,6 +94,18 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["config"] == bench.workload_config("c4", 1) and line["config"]["total_particles"] == 10_000_000
 
 
+def test_bench_config_names_every_workload():
+    """`config` of the bench line: workload text, particle counts and the L2 statement, for every workload and GPU count, without a device."""
+    import bench
+    for w in bench.WORKLOADS:
+        for world in (1, 2, 8):
+            cfg = bench.workload_config(w, world)
+            assert set(cfg) == {"workload", "particles_per_gpu", "total_particles", "l2"} and cfg["workload"] == bench.WORKLOADS[w]
+            assert cfg["total_particles"] == (200_000_000 if w == "c5" else cfg["particles_per_gpu"] * world)
+            assert ("larger than L2" in cfg["l2"]) == (w.startswith("c4") or w == "c5")
+    assert bench.workload_config("c1", 1)["particles_per_gpu"] == 2500 and bench.workload_config("c2", 1)["particles_per_gpu"] == 50000
+
+
 _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
